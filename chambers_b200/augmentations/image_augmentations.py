@@ -1,0 +1,379 @@
+"""The 16 policy op layers plus ``RandomChance`` / ``RandomChoice`` with the reference's names,
+constructor arguments, ``get_config`` keys and error behaviour
+(/root/reference/chambers/augmentations/image_augmentations.py, cited per class), backed by the
+fused sm_100a kernel instead of TensorFlow ops.
+
+A layer here holds only its constructor arguments; ``_fill_op`` writes them into the ``chb_op``
+struct of the C ABI and every pixel is produced by ``libchambers_aug.so``.
+"""
+
+from .. import _lib
+from .base import Layer, register, serialize, deserialize, run_policy, check_uint8
+
+_INTERP = _lib.INTERPOLATIONS
+_FILL = _lib.FILL_MODES
+
+
+class _OpLayer(Layer):
+    """An op layer called directly behaves like RandomChoice([op], 1, elementwise=False): one
+    sign flip per call for the whole batch (_randomly_negate_value, :52-56), CutOut centres per
+    image (tfa.image.random_cutout draws [B] centres)."""
+
+    _kind = None
+    _keys = ()
+
+    def call(self, inputs, seed=None, call_counter=None, replay=None, record=False, batch_total=None,
+             image_index_base=0, **kwargs):
+        seed, call_counter = self._stream(seed, call_counter)
+        out, sched = run_policy(inputs, [[(self, None)]], 1, False, seed, call_counter,
+                                batch_total=batch_total, image_index_base=image_index_base,
+                                replay=replay, record=record)
+        self.last_schedule = sched
+        return out
+
+    def get_config(self):
+        config = {k: getattr(self, k) for k in self._keys}
+        return dict(list(super().get_config().items()) + list(config.items()))
+
+    def _fill_op(self, op):
+        op.kind = _lib.OP_KIND[self._kind]
+        op.interpolation = 0
+        op.fill_mode = 0
+        op.ivalue[0] = 0
+        op.ivalue[1] = 0
+        op.fill_value = 0.0
+        op.value = 0.0
+
+
+class _GeometricLayer(_OpLayer):
+    _value_key = None
+
+    def __init__(self, value, interpolation="nearest", fill_mode="constant", fill_value=0.0, name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        setattr(self, self._value_key, value)
+        self.interpolation = interpolation
+        self.fill_mode = fill_mode
+        self.fill_value = fill_value
+
+    def _fill_op(self, op):
+        super()._fill_op(op)
+        if str(self.interpolation).lower() not in _INTERP:
+            raise ValueError("Unknown interpolation %r (nearest | bilinear)" % (self.interpolation,))
+        if str(self.fill_mode).lower() not in _FILL:
+            raise ValueError("Unknown fill_mode %r (constant | reflect | wrap | nearest)" % (self.fill_mode,))
+        op.interpolation = _INTERP[str(self.interpolation).lower()]
+        op.fill_mode = _FILL[str(self.fill_mode).lower()]
+        op.fill_value = float(self.fill_value)
+        op.value = float(getattr(self, self._value_key))
+
+
+class _FactorLayer(_OpLayer):
+    _keys = ("factor",)
+
+    def __init__(self, factor, name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.factor = factor
+
+    def _fill_op(self, op):
+        super()._fill_op(op)
+        op.value = float(self.factor)
+
+
+# ---------------------------------------------------------------- ops without parameters
+@register
+class AutoContrast(_OpLayer):
+    """image_augmentations.py:62-90."""
+    _kind = "AutoContrast"
+
+    def __init__(self, name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+
+
+@register
+class Equalize(_OpLayer):
+    """image_augmentations.py:93-103 (tfa.image.equalize)."""
+    _kind = "Equalize"
+
+    def __init__(self, name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+
+
+@register
+class Invert(_OpLayer):
+    """image_augmentations.py:106-116."""
+    _kind = "Invert"
+
+    def __init__(self, name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+
+
+# ------------------------------------------------------------------------- geometric ops
+@register
+class Rotate(_GeometricLayer):
+    """image_augmentations.py:119-160 (tfa.image.rotate about the image centre)."""
+    _kind = "Rotate"
+    _value_key = "degrees"
+    _keys = ("degrees", "interpolation", "fill_mode", "fill_value")
+
+    def __init__(self, degrees, interpolation="nearest", fill_mode="constant", fill_value=0.0, name=None, **kwargs):
+        super().__init__(degrees, interpolation, fill_mode, fill_value, name=name, **kwargs)
+
+
+@register
+class ShearX(_GeometricLayer):
+    """image_augmentations.py:315-355."""
+    _kind = "ShearX"
+    _value_key = "level"
+    _keys = ("level", "interpolation", "fill_mode", "fill_value")
+
+    def __init__(self, level, interpolation="nearest", fill_mode="constant", fill_value=0.0, name=None, **kwargs):
+        super().__init__(level, interpolation, fill_mode, fill_value, name=name, **kwargs)
+
+
+@register
+class ShearY(_GeometricLayer):
+    """image_augmentations.py:358-398."""
+    _kind = "ShearY"
+    _value_key = "level"
+    _keys = ("level", "interpolation", "fill_mode", "fill_value")
+
+    def __init__(self, level, interpolation="nearest", fill_mode="constant", fill_value=0.0, name=None, **kwargs):
+        super().__init__(level, interpolation, fill_mode, fill_value, name=name, **kwargs)
+
+
+@register
+class TranslateX(_GeometricLayer):
+    """image_augmentations.py:401-441."""
+    _kind = "TranslateX"
+    _value_key = "pixels"
+    _keys = ("pixels", "interpolation", "fill_mode", "fill_value")
+
+    def __init__(self, pixels, interpolation="nearest", fill_mode="constant", fill_value=0.0, name=None, **kwargs):
+        super().__init__(pixels, interpolation, fill_mode, fill_value, name=name, **kwargs)
+
+
+@register
+class TranslateY(_GeometricLayer):
+    """image_augmentations.py:444-484."""
+    _kind = "TranslateY"
+    _value_key = "pixels"
+    _keys = ("pixels", "interpolation", "fill_mode", "fill_value")
+
+    def __init__(self, pixels, interpolation="nearest", fill_mode="constant", fill_value=0.0, name=None, **kwargs):
+        super().__init__(pixels, interpolation, fill_mode, fill_value, name=name, **kwargs)
+
+
+# ----------------------------------------------------------------------- integer colour ops
+@register
+class Posterize(_OpLayer):
+    """image_augmentations.py:163-182."""
+    _kind = "Posterize"
+    _keys = ("bits",)
+
+    def __init__(self, bits, name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.bits = bits
+        self._shift = 8 - bits
+
+    def _fill_op(self, op):
+        super()._fill_op(op)
+        op.ivalue[0] = int(self.bits)
+
+
+@register
+class Solarize(_OpLayer):
+    """image_augmentations.py:185-201."""
+    _kind = "Solarize"
+    _keys = ("threshold",)
+
+    def __init__(self, threshold=128, name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.threshold = threshold
+
+    def _fill_op(self, op):
+        super()._fill_op(op)
+        op.ivalue[0] = int(self.threshold)
+
+
+@register
+class SolarizeAdd(_OpLayer):
+    """image_augmentations.py:204-223."""
+    _kind = "SolarizeAdd"
+    _keys = ("addition", "threshold")
+
+    def __init__(self, addition=0, threshold=128, name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.addition = addition
+        self.threshold = threshold
+
+    def _fill_op(self, op):
+        super()._fill_op(op)
+        op.ivalue[0] = int(self.addition)
+        op.ivalue[1] = int(self.threshold)
+
+
+# ----------------------------------------------------------------------------- blend ops
+@register
+class Color(_FactorLayer):
+    """image_augmentations.py:226-243."""
+    _kind = "Color"
+
+
+@register
+class Contrast(_FactorLayer):
+    """image_augmentations.py:246-273 (including the sum(hist)/256 quirk)."""
+    _kind = "Contrast"
+
+
+@register
+class Brightness(_FactorLayer):
+    """image_augmentations.py:276-293."""
+    _kind = "Brightness"
+
+
+@register
+class Sharpness(_FactorLayer):
+    """image_augmentations.py:296-312 (tfa.image.sharpness)."""
+    _kind = "Sharpness"
+
+
+@register
+class CutOut(_OpLayer):
+    """image_augmentations.py:487-507 (tfa.image.random_cutout)."""
+    _kind = "CutOut"
+    _keys = ("mask_size", "constant_values")
+
+    def __init__(self, mask_size, constant_values=0, name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.mask_size = mask_size
+        self.constant_values = constant_values
+
+    def _fill_op(self, op):
+        super()._fill_op(op)
+        if int(self.mask_size) % 2 != 0:
+            raise ValueError("mask_size should be divisible by 2")
+        op.ivalue[0] = int(self.mask_size)
+        op.ivalue[1] = int(self.constant_values)
+
+
+# ------------------------------------------------------------------------ control layers
+class Sequential(Layer):
+    """Minimal tf.keras.Sequential stand-in for composing RandomChance / op layers inside a
+    RandomChoice (AutoAugment's sub-policies, augmentation_schemes.py:139-146)."""
+
+    def __init__(self, layers=None, name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.layers = list(layers or [])
+
+    def call(self, inputs, **kwargs):
+        x = inputs
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+    def get_config(self):
+        config = {"layers": [serialize(l) for l in self.layers]}
+        return dict(list(super().get_config().items()) + list(config.items()))
+
+    @classmethod
+    def from_config(cls, config):
+        config = dict(config)
+        config["layers"] = [deserialize(l) for l in config["layers"]]
+        return cls(**config)
+
+
+register(Sequential)
+
+
+def _flatten_transform(t):
+    """A RandomChoice entry -> list of (op layer, probability or None)."""
+    if isinstance(t, _OpLayer):
+        return [(t, None)]
+    if isinstance(t, RandomChance):
+        if not isinstance(t.transform, _OpLayer):
+            raise ValueError("RandomChance inside a fused policy must wrap one of the 16 op layers, got %r"
+                             % type(t.transform).__name__)
+        return [(t.transform, t.probability)]
+    if isinstance(t, Sequential):
+        out = []
+        for l in t.layers:
+            out.extend(_flatten_transform(l))
+        return out
+    raise ValueError("Unsupported transform %r: expected an op layer, RandomChance or Sequential of those"
+                     % type(t).__name__)
+
+
+@register
+class RandomChance(Layer):
+    """image_augmentations.py:513-545: apply ``transform`` with the given probability (one coin
+    per call, i.e. per batch, exactly like tf.random.uniform([]) < p at :523)."""
+
+    def __init__(self, transform, probability, name=None, **kwargs):
+        if name is None and getattr(transform, "name", None) is not None:
+            name = "random_chance_" + transform.name
+        super().__init__(name=name, **kwargs)
+        self.transform = transform
+        self.probability = probability
+
+    def call(self, inputs, seed=None, call_counter=None, replay=None, record=False, batch_total=None,
+             image_index_base=0, **kwargs):
+        seed, call_counter = self._stream(seed, call_counter)
+        out, sched = run_policy(inputs, [_flatten_transform(self)], 1, False, seed, call_counter,
+                                batch_total=batch_total, image_index_base=image_index_base,
+                                replay=replay, record=record)
+        self.last_schedule = sched
+        return out
+
+    def compute_output_shape(self, input_shape):
+        return self.transform.compute_output_shape(input_shape)
+
+    def get_config(self):
+        config = {"transform": serialize(self.transform), "probability": self.probability}
+        return dict(list(super().get_config().items()) + list(config.items()))
+
+    @classmethod
+    def from_config(cls, config):
+        config = dict(config)
+        config["transform"] = deserialize(config["transform"])
+        return cls(**config)
+
+
+@register
+class RandomChoice(Layer):
+    """image_augmentations.py:548-617: ``n_transforms`` draws with replacement from ``transforms``;
+    one schedule for the whole batch (elementwise=False, :569) or one per image (:565-567)."""
+
+    def __init__(self, transforms, n_transforms, elementwise=False, name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.transforms = list(transforms)
+        self.n_transforms = n_transforms
+        self.elementwise = elementwise
+
+    def call(self, inputs, seed=None, call_counter=None, replay=None, record=False, batch_total=None,
+             image_index_base=0, out=None, **kwargs):
+        seed, call_counter = self._stream(seed, call_counter)
+        table = [_flatten_transform(t) for t in self.transforms]
+        res, sched = run_policy(inputs, table, self.n_transforms, self.elementwise, seed, call_counter,
+                                batch_total=batch_total, image_index_base=image_index_base,
+                                replay=replay, record=record, out=out)
+        self.last_schedule = sched
+        return res
+
+    def compute_output_shape(self, input_shape):
+        # every transform preserves the shape; the reference's np.float-based merge (:572-586) would
+        # return the same list for shape-preserving transforms (and crashes on numpy >= 1.24).
+        return input_shape
+
+    def get_config(self):
+        config = {
+            "transforms": [serialize(t) for t in self.transforms],
+            "n_transforms": self.n_transforms,
+            "elementwise": self.elementwise,
+        }
+        return dict(list(super().get_config().items()) + list(config.items()))
+
+    @classmethod
+    def from_config(cls, config):
+        config = dict(config)
+        config["transforms"] = [deserialize(t) for t in config["transforms"]]
+        return cls(**config)

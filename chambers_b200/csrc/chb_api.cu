@@ -1,0 +1,582 @@
+// Host side of libchambers_aug.so: the C ABI of include/chambers_aug.h.
+//
+// Everything the reference computes in Python at layer construction (magnitude -> kwargs,
+// augmentation_schemes.py:42-128) or per call on the host (float32 conversion of the signed
+// parameters, the projective coefficients, image_augmentations.py:135-146, :334-341, :420-427) is
+// resolved here into a DevOp table; the pixels are only ever touched by chb_kernels.cu.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "chb_internal.h"
+
+using chb::DevOp;
+
+struct PolicyEntry {
+  std::vector<DevOp> host;
+  DevOp* dev = nullptr;
+  bool uploaded = false;
+};
+
+static const int kPipe = 3;         // e2e pipeline depth (streams / staging buffers)
+static const int kCounterSlots = 256;
+
+struct chb_ctx {
+  int device = 0;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  std::string err;
+  int64_t launches = 0;
+  unsigned int* d_counters = nullptr;  // kCounterSlots x {next, done}
+  uint8_t* d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  std::vector<PolicyEntry*> cache;
+  // e2e pipeline
+  cudaStream_t streams[kPipe] = {nullptr, nullptr, nullptr};
+  uint8_t* st_in[kPipe] = {nullptr, nullptr, nullptr};
+  uint8_t* st_out[kPipe] = {nullptr, nullptr, nullptr};
+  int32_t* st_replay[kPipe] = {nullptr, nullptr, nullptr};
+  int32_t* st_record[kPipe] = {nullptr, nullptr, nullptr};
+  size_t st_img_bytes = 0, st_sched_bytes = 0;
+};
+
+static std::string g_init_error;
+
+static int fail(chb_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg; else g_init_error = msg;
+  return code;
+}
+static int cuda_fail(chb_ctx* ctx, cudaError_t e, const char* what) {
+  return fail(ctx, CHB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CHB_CUDA(ctx, call)                                   \
+  do {                                                        \
+    cudaError_t e_ = (call);                                  \
+    if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);  \
+  } while (0)
+
+// ---------------------------------------------------------------------------- table builders
+static chb_op make_op(int kind) {
+  chb_op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = kind;
+  op.probability = -1.0;
+  if (kind == CHB_OP_SHEAR_X || kind == CHB_OP_SHEAR_Y || kind == CHB_OP_TRANSLATE_X ||
+      kind == CHB_OP_TRANSLATE_Y || kind == CHB_OP_ROTATE) {
+    op.interpolation = CHB_INTERP_NEAREST;  // augmentation_schemes.py:7
+    op.fill_mode = CHB_FILL_CONSTANT;       // :8
+    op.fill_value = 128.0f;                 // :9
+  }
+  return op;
+}
+
+// _get_transform(name, magnitude), augmentation_schemes.py:105-128 with the maps of :42-102.
+// Same IEEE double arithmetic, same left-to-right order, int() truncation.
+static chb_op op_from_magnitude(int kind, double m) {
+  const double kMax = 10.0;  // _MAX_MAGNITUDE :10
+  chb_op op = make_op(kind);
+  switch (kind) {
+    case CHB_OP_BRIGHTNESS: case CHB_OP_CONTRAST: case CHB_OP_COLOR: case CHB_OP_SHARPNESS:
+      op.value = m / kMax * 1.8 + 0.1;  // :43
+      break;
+    case CHB_OP_SHEAR_X: case CHB_OP_SHEAR_Y:
+      op.value = m / kMax * 0.3;  // :49
+      break;
+    case CHB_OP_TRANSLATE_X: case CHB_OP_TRANSLATE_Y:
+      op.value = m / kMax * 100;  // :60
+      break;
+    case CHB_OP_POSTERIZE:
+      op.ivalue[0] = (int)(m / kMax * 4);  // :71
+      break;
+    case CHB_OP_SOLARIZE:
+      op.ivalue[0] = (int)(m / kMax * 256);  // :77
+      break;
+    case CHB_OP_SOLARIZE_ADD:
+      op.ivalue[0] = (int)(m / kMax * 110);  // :83
+      op.ivalue[1] = 128;                    // SolarizeAdd default threshold, image_augmentations.py:206
+      break;
+    case CHB_OP_ROTATE:
+      op.value = m / kMax * 30.0;  // :89
+      break;
+    case CHB_OP_CUTOUT:
+      op.ivalue[0] = (int)(m / kMax * 80);  // :100
+      op.ivalue[1] = 128;                   // :101
+      break;
+    default:
+      break;
+  }
+  return op;
+}
+
+extern "C" int chb_randaugment_table(double magnitude, chb_transform* out16) {
+  if (!out16) return CHB_ERR_INVALID;
+  for (int k = 0; k < CHB_OP_COUNT; ++k) {  // fixed order, augmentation_schemes.py:181-198
+    memset(&out16[k], 0, sizeof(chb_transform));
+    out16[k].n_ops = 1;
+    out16[k].ops[0] = op_from_magnitude(k, magnitude);
+  }
+  return CHB_OK;
+}
+
+extern "C" int chb_autoaugment_table(chb_transform* out25) {
+  if (!out25) return CHB_ERR_INVALID;
+  struct E { int k1; double p1; double m1; int k2; double p2; double m2; };
+  // _AUTO_AUGMENT_POLICY_V0, augmentation_schemes.py:12-39 (magnitude None -> 0, unused).
+  static const E v0[25] = {
+      {CHB_OP_EQUALIZE, 0.8, 0, CHB_OP_SHEAR_Y, 0.8, 4},
+      {CHB_OP_COLOR, 0.4, 9, CHB_OP_EQUALIZE, 0.6, 0},
+      {CHB_OP_COLOR, 0.4, 1, CHB_OP_ROTATE, 0.6, 8},
+      {CHB_OP_SOLARIZE, 0.8, 3, CHB_OP_EQUALIZE, 0.4, 7},
+      {CHB_OP_SOLARIZE, 0.4, 2, CHB_OP_SOLARIZE, 0.6, 2},
+      {CHB_OP_COLOR, 0.2, 0, CHB_OP_EQUALIZE, 0.8, 0},
+      {CHB_OP_EQUALIZE, 0.4, 0, CHB_OP_SOLARIZE_ADD, 0.8, 3},
+      {CHB_OP_SHEAR_X, 0.2, 9, CHB_OP_ROTATE, 0.6, 8},
+      {CHB_OP_COLOR, 0.6, 1, CHB_OP_EQUALIZE, 1.0, 0},
+      {CHB_OP_INVERT, 0.4, 0, CHB_OP_ROTATE, 0.6, 0},
+      {CHB_OP_EQUALIZE, 1.0, 0, CHB_OP_SHEAR_Y, 0.6, 3},
+      {CHB_OP_COLOR, 0.4, 7, CHB_OP_EQUALIZE, 0.6, 0},
+      {CHB_OP_POSTERIZE, 0.4, 6, CHB_OP_AUTOCONTRAST, 0.4, 0},
+      {CHB_OP_SOLARIZE, 0.6, 8, CHB_OP_COLOR, 0.6, 9},
+      {CHB_OP_SOLARIZE, 0.2, 4, CHB_OP_ROTATE, 0.8, 9},
+      {CHB_OP_ROTATE, 1.0, 7, CHB_OP_TRANSLATE_Y, 0.8, 9},
+      {CHB_OP_SHEAR_X, 0.0, 0, CHB_OP_SOLARIZE, 0.8, 4},
+      {CHB_OP_SHEAR_Y, 0.8, 0, CHB_OP_COLOR, 0.6, 4},
+      {CHB_OP_COLOR, 1.0, 0, CHB_OP_ROTATE, 0.6, 2},
+      {CHB_OP_EQUALIZE, 0.8, 0, CHB_OP_EQUALIZE, 0.0, 0},
+      {CHB_OP_EQUALIZE, 1.0, 0, CHB_OP_AUTOCONTRAST, 0.6, 0},
+      {CHB_OP_SHEAR_Y, 0.4, 7, CHB_OP_SOLARIZE_ADD, 0.6, 7},
+      {CHB_OP_POSTERIZE, 0.8, 2, CHB_OP_SOLARIZE, 0.6, 10},
+      {CHB_OP_SOLARIZE, 0.6, 8, CHB_OP_EQUALIZE, 0.6, 1},
+      {CHB_OP_COLOR, 0.8, 6, CHB_OP_ROTATE, 0.4, 5},
+  };
+  for (int i = 0; i < 25; ++i) {
+    memset(&out25[i], 0, sizeof(chb_transform));
+    out25[i].n_ops = 2;
+    out25[i].ops[0] = op_from_magnitude(v0[i].k1, v0[i].m1);
+    out25[i].ops[0].probability = v0[i].p1;  // RandomChance, :141-142
+    out25[i].ops[1] = op_from_magnitude(v0[i].k2, v0[i].m2);
+    out25[i].ops[1].probability = v0[i].p2;
+  }
+  return CHB_OK;
+}
+
+// --------------------------------------------------------------------- chb_op -> DevOp
+static int wrap_threshold(int t) {  // oracle/switches.py SOLARIZE_THRESHOLD_OVERFLOW = "wrap"
+  if (t >= 0 && t <= 255) return t;
+  return ((t % 256) + 256) % 256;
+}
+
+static int blend_mode_of(double factor) {  // image_augmentations.py:28-31, :43
+  if (factor == 0.0) return chb::BLEND_IMAGE1;
+  if (factor == 1.0) return chb::BLEND_IMAGE2;
+  if (factor > 0.0 && factor < 1.0) return chb::BLEND_INTERP;
+  return chb::BLEND_EXTRAP;
+}
+
+static void affine_identity(float* t) {
+  const float id[8] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f};
+  memcpy(t, id, sizeof(id));
+}
+
+static int build_devop(const chb_op& op, int H, int W, int C, long long contrast_pixels, DevOp& d,
+                       std::string& err) {
+  memset(&d, 0, sizeof(d));
+  d.kind = op.kind;
+  d.interp = op.interpolation;
+  d.fill_mode = op.fill_mode;
+  if (op.probability < 0.0) {
+    d.thr24 = 1 << 24;
+  } else {
+    double t = ceil(op.probability * 16777216.0);  // oracle/philox.py prob_threshold24
+    if (t < 0) t = 0;
+    if (t > 16777216.0) t = 16777216.0;
+    d.thr24 = (int)t;
+  }
+  affine_identity(d.coef[0]);
+  affine_identity(d.coef[1]);
+  switch (op.kind) {
+    case CHB_OP_AUTOCONTRAST: case CHB_OP_EQUALIZE: case CHB_OP_INVERT:
+      break;
+    case CHB_OP_BRIGHTNESS: case CHB_OP_CONTRAST: case CHB_OP_COLOR: case CHB_OP_SHARPNESS: {
+      d.factor = (float)op.value;
+      d.blend_mode = blend_mode_of(op.value);
+      if ((op.kind == CHB_OP_CONTRAST || op.kind == CHB_OP_COLOR) && C != 3) {
+        err = "Color / Contrast need 3 channels (tf.image.rgb_to_grayscale)";
+        return CHB_ERR_INVALID;
+      }
+      if (op.kind == CHB_OP_CONTRAST) {
+        // image_augmentations.py:260-264: sum(hist)/256 = (#pixels passed in)/256, clip, trunc.
+        float mean = (float)contrast_pixels / 256.0f;
+        mean = fminf(fmaxf(mean, 0.0f), 255.0f);
+        d.ip0 = (int)mean;
+      }
+    } break;
+    case CHB_OP_POSTERIZE: {
+      int shift = 8 - op.ivalue[0];  // :168
+      if (shift < 0) shift = 0;
+      if (shift > 7) shift = 7;  // oracle/switches.py POSTERIZE_SHIFT8 = "clamp7"
+      d.ip0 = shift;
+    } break;
+    case CHB_OP_SOLARIZE:
+      d.ip0 = wrap_threshold(op.ivalue[0]);
+      break;
+    case CHB_OP_SOLARIZE_ADD:
+      d.ip0 = op.ivalue[0];
+      d.ip1 = wrap_threshold(op.ivalue[1]);
+      break;
+    case CHB_OP_CUTOUT:
+      if (op.ivalue[0] < 0 || (op.ivalue[0] & 1)) {
+        err = "CutOut mask_size should be a non-negative multiple of 2 (tfa.image.cutout)";
+        return CHB_ERR_INVALID;
+      }
+      d.ip0 = op.ivalue[0] / 2;
+      d.ip1 = op.ivalue[1] & 0xFF;
+      break;
+    case CHB_OP_SHEAR_X: case CHB_OP_SHEAR_Y: case CHB_OP_TRANSLATE_X: case CHB_OP_TRANSLATE_Y:
+    case CHB_OP_ROTATE: {
+      if (op.interpolation != CHB_INTERP_NEAREST && op.interpolation != CHB_INTERP_BILINEAR) {
+        err = "interpolation must be nearest or bilinear";
+        return CHB_ERR_INVALID;
+      }
+      if (op.fill_mode < CHB_FILL_CONSTANT || op.fill_mode > CHB_FILL_NEAREST) {
+        err = "fill_mode must be constant, reflect, wrap or nearest";
+        return CHB_ERR_INVALID;
+      }
+      d.fill_u8 = ((int)op.fill_value) & 0xFF;
+      for (int neg = 0; neg < 2; ++neg) {
+        float* t = d.coef[neg];
+        // _randomly_negate_value, image_augmentations.py:52-56: +-value as a float32 tensor.
+        const float v = (float)(neg ? -op.value : op.value);
+        if (op.kind == CHB_OP_SHEAR_X) {
+          t[1] = v;  // :337
+        } else if (op.kind == CHB_OP_SHEAR_Y) {
+          t[3] = v;  // :380
+        } else if (op.kind == CHB_OP_TRANSLATE_X) {
+          t[2] = v;  // :421-427 translate([-px, 0]) -> [1,0,px, 0,1,-0, 0,0]
+          t[5] = -0.0f;
+        } else if (op.kind == CHB_OP_TRANSLATE_Y) {
+          t[2] = -0.0f;
+          t[5] = v;  // :464-470
+        } else {
+          // Rotate: radians in double (:135), sign flip to float32 (:139), then tfa's
+          // angles_to_projective_transforms in stepwise float32 (oracle/ops.py rotate_coeffs).
+          const double radians = op.value * M_PI / 180.0;
+          const float ang = (float)(neg ? -radians : radians);
+          const float c = (float)cos((double)ang);
+          const float s = (float)sin((double)ang);
+          const float w1 = (float)W - 1.0f, h1 = (float)H - 1.0f;
+          volatile float cw = c * w1, sh = s * h1, sw = s * w1, ch = c * h1;
+          volatile float a = cw - sh, b = sw + ch;
+          volatile float xo = w1 - a, yo = h1 - b;
+          t[0] = c; t[1] = -s; t[2] = xo / 2.0f;
+          t[3] = s; t[4] = c;  t[5] = yo / 2.0f;
+        }
+      }
+    } break;
+    default:
+      err = "unknown op kind";
+      return CHB_ERR_INVALID;
+  }
+  return CHB_OK;
+}
+
+// ------------------------------------------------------------------------------------ context
+extern "C" int chb_version(void) { return CHB_VERSION_MAJOR * 1000 + CHB_VERSION_MINOR; }
+
+extern "C" const char* chb_last_error(const chb_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_init_error.c_str();
+}
+
+extern "C" int64_t chb_kernel_launches(const chb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int chb_init(int device, chb_ctx** out) {
+  if (!out) return fail(nullptr, CHB_ERR_INVALID, "chb_init: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, CHB_ERR_NO_DEVICE,
+                std::string("chb_init: no CUDA device (") + cudaGetErrorString(e) +
+                    "); libchambers_aug has no CPU fallback");
+  if (device < 0 || device >= n) return fail(nullptr, CHB_ERR_INVALID, "chb_init: bad device index");
+  CHB_CUDA(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CHB_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, CHB_ERR_NO_DEVICE,
+                "chb_init: this library is built for sm_100a (B200) only; found sm_" +
+                    std::to_string(prop.major) + std::to_string(prop.minor));
+  chb_ctx* ctx = new chb_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  e = chb::configure_kernels(ctx->smem_optin);
+  if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "configure_kernels"); delete ctx; return r; }
+  e = cudaMalloc(&ctx->d_counters, kCounterSlots * 2 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(ctx->d_counters, 0, kCounterSlots * 2 * sizeof(unsigned int));
+  if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "counter alloc"); delete ctx; return r; }
+  *out = ctx;
+  return CHB_OK;
+}
+
+extern "C" void chb_destroy(chb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (PolicyEntry* pe : ctx->cache) { cudaFree(pe->dev); delete pe; }
+  cudaFree(ctx->d_counters);
+  cudaFree(ctx->d_scratch);
+  for (int i = 0; i < kPipe; ++i) {
+    if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
+    cudaFree(ctx->st_in[i]); cudaFree(ctx->st_out[i]);
+    cudaFree(ctx->st_replay[i]); cudaFree(ctx->st_record[i]);
+  }
+  delete ctx;
+}
+
+extern "C" int64_t chb_smem_image_limit(const chb_ctx* ctx, int C) {
+  if (!ctx || C < 1 || C > 4) return 0;
+  const int64_t lim = (int64_t)ctx->smem_optin - (int64_t)chb::smem_overhead(C);
+  return lim > 0 ? (lim / 128) * 128 : 0;
+}
+
+// ------------------------------------------------------------------------------------- launch
+static int validate_policy(chb_ctx* ctx, const chb_policy* pol, int& K) {
+  if (!pol || !pol->table) return fail(ctx, CHB_ERR_INVALID, "policy is NULL");
+  if (pol->n_table < 1) return fail(ctx, CHB_ERR_INVALID, "policy has no transforms");
+  if (pol->n_draws < 0) return fail(ctx, CHB_ERR_INVALID, "n_transforms must be >= 0");
+  K = 1;
+  for (int t = 0; t < pol->n_table; ++t) {
+    const int n = pol->table[t].n_ops;
+    if (n < 0 || n > CHB_MAX_SUBOPS)
+      return fail(ctx, CHB_ERR_UNSUPPORTED, "a transform holds more than CHB_MAX_SUBOPS ops");
+    if (n > K) K = n;
+  }
+  if ((long long)pol->n_draws * K > CHB_MAX_CHAIN)
+    return fail(ctx, CHB_ERR_UNSUPPORTED, "n_transforms * ops-per-transform exceeds CHB_MAX_CHAIN");
+  return CHB_OK;
+}
+
+static int get_policy(chb_ctx* ctx, const chb_policy* pol, int K, int H, int W, int C,
+                      int64_t batch_total, cudaStream_t stream, PolicyEntry** out) {
+  std::vector<DevOp> host((size_t)pol->n_table * K);
+  const long long contrast_pixels = (long long)(pol->elementwise ? 1 : batch_total) * H * W;
+  for (int t = 0; t < pol->n_table; ++t)
+    for (int j = 0; j < K; ++j) {
+      DevOp& d = host[(size_t)t * K + j];
+      if (j < pol->table[t].n_ops) {
+        std::string err;
+        const int r = build_devop(pol->table[t].ops[j], H, W, C, contrast_pixels, d, err);
+        if (r != CHB_OK) return fail(ctx, r, err);
+      } else {
+        memset(&d, 0, sizeof(d));
+        d.kind = -1;
+      }
+    }
+  PolicyEntry* hit = nullptr;
+  for (PolicyEntry* pe : ctx->cache)
+    if (pe->host.size() == host.size() && memcmp(pe->host.data(), host.data(), host.size() * sizeof(DevOp)) == 0) {
+      hit = pe;
+      break;
+    }
+  if (!hit) {
+    if (ctx->cache.size() >= 64) {  // bounded cache: drop everything once nothing can be in flight
+      CHB_CUDA(ctx, cudaDeviceSynchronize());
+      for (PolicyEntry* pe : ctx->cache) { cudaFree(pe->dev); delete pe; }
+      ctx->cache.clear();
+    }
+    hit = new PolicyEntry();
+    hit->host = host;
+    cudaError_t e = cudaMalloc(&hit->dev, host.size() * sizeof(DevOp));
+    if (e != cudaSuccess) { delete hit; return cuda_fail(ctx, e, "policy table alloc"); }
+    // pageable source: the runtime stages the bytes before returning, so `host` may go away.
+    e = cudaMemcpyAsync(hit->dev, hit->host.data(), host.size() * sizeof(DevOp), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) { cudaFree(hit->dev); delete hit; return cuda_fail(ctx, e, "policy table upload"); }
+    // other streams may use this entry later: make the upload visible to them too.
+    e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { cudaFree(hit->dev); delete hit; return cuda_fail(ctx, e, "policy table upload sync"); }
+    ctx->cache.push_back(hit);
+  }
+  *out = hit;
+  return CHB_OK;
+}
+
+static int ensure_scratch(chb_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return CHB_OK;
+  if (ctx->d_scratch) CHB_CUDA(ctx, cudaFree(ctx->d_scratch));  // cudaFree synchronises the device
+  ctx->d_scratch = nullptr;
+  ctx->scratch_bytes = 0;
+  CHB_CUDA(ctx, cudaMalloc(&ctx->d_scratch, bytes));
+  ctx->scratch_bytes = bytes;
+  return CHB_OK;
+}
+
+static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int B, int H, int W, int C,
+                         const chb_policy* pol, int64_t batch_total, int64_t image_index_base,
+                         uint64_t seed, uint32_t call_counter, const int32_t* d_replay,
+                         int32_t* d_record, cudaStream_t stream) {
+  if (!ctx) return CHB_ERR_INVALID;
+  if (B < 0 || H < 0 || W < 0) return fail(ctx, CHB_ERR_INVALID, "negative shape");
+  if (C < 1 || C > 4) return fail(ctx, CHB_ERR_UNSUPPORTED, "channels must be 1..4");
+  int K = 1;
+  int r = validate_policy(ctx, pol, K);
+  if (r != CHB_OK) return r;
+  if ((long long)H * W * C > 0x3FFFFFFFll) return fail(ctx, CHB_ERR_UNSUPPORTED, "image larger than 1 GiB");
+  if ((long long)H * W > 32ll * 65535) return fail(ctx, CHB_ERR_UNSUPPORTED, "image larger than 2M pixels (16-bit histogram replicas)");
+  CHB_CUDA(ctx, cudaSetDevice(ctx->device));
+  PolicyEntry* pe = nullptr;
+  r = get_policy(ctx, pol, K, H, W, C, batch_total, stream, &pe);  // validates ops even when B == 0
+  if (r != CHB_OK) return r;
+  if (B == 0 || H == 0 || W == 0) return CHB_OK;
+  if (!d_in || !d_out) return fail(ctx, CHB_ERR_INVALID, "NULL image pointer");
+  const chb::LaunchInfo li = chb::plan_launch(B, H, W, C, ctx->num_sms, ctx->smem_optin);
+  if (!li.image_in_smem && d_in == d_out)
+    return fail(ctx, CHB_ERR_INVALID, "in-place call needs an image that fits in shared memory");
+  const size_t stride = ((size_t)H * W * C + 255) / 256 * 256;
+  r = ensure_scratch(ctx, (size_t)ctx->num_sms * 2 * stride);
+  if (r != CHB_OK) return r;
+
+  chb::KParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = d_in; p.out = d_out; p.B = B; p.H = H; p.W = W;
+  p.ops = pe->dev; p.T = pol->n_table; p.n_draws = pol->n_draws; p.K = K;
+  p.elementwise = pol->elementwise ? 1 : 0;
+  p.seed = seed; p.call_counter = call_counter; p.image_index_base = (unsigned long long)image_index_base;
+  p.replay = d_replay; p.record = d_record;
+  p.scratch = ctx->d_scratch; p.scratch_stride = stride;
+  p.work_counter = ctx->d_counters + 2 * (size_t)(ctx->launches % kCounterSlots);
+  cudaError_t e = chb::launch_policy(p, C, li, stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "policy kernel launch");
+  ctx->launches += 1;
+  return CHB_OK;
+}
+
+extern "C" int chb_policy_apply(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int B, int H, int W,
+                                int C, const chb_policy* policy, int64_t batch_total,
+                                int64_t image_index_base, uint64_t seed, uint32_t call_counter,
+                                const int32_t* d_replay, int32_t* d_record, void* stream) {
+  return launch_device(ctx, d_in, d_out, B, H, W, C, policy, batch_total, image_index_base, seed,
+                       call_counter, d_replay, d_record, (cudaStream_t)stream);
+}
+
+extern "C" int chb_randaugment(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int B, int H, int W,
+                               int C, int n_transforms, double magnitude, int elementwise,
+                               int64_t batch_total, int64_t image_index_base, uint64_t seed,
+                               uint32_t call_counter, const int32_t* d_replay, int32_t* d_record,
+                               void* stream) {
+  chb_transform table[CHB_OP_COUNT];
+  chb_randaugment_table(magnitude, table);
+  chb_policy pol = {CHB_OP_COUNT, n_transforms, elementwise, 0, table};
+  return launch_device(ctx, d_in, d_out, B, H, W, C, &pol, batch_total, image_index_base, seed,
+                       call_counter, d_replay, d_record, (cudaStream_t)stream);
+}
+
+extern "C" int chb_autoaugment(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int B, int H, int W,
+                               int C, int elementwise, int64_t batch_total, int64_t image_index_base,
+                               uint64_t seed, uint32_t call_counter, const int32_t* d_replay,
+                               int32_t* d_record, void* stream) {
+  chb_transform table[25];
+  chb_autoaugment_table(table);
+  chb_policy pol = {25, 1, elementwise, 0, table};
+  return launch_device(ctx, d_in, d_out, B, H, W, C, &pol, batch_total, image_index_base, seed,
+                       call_counter, d_replay, d_record, (cudaStream_t)stream);
+}
+
+extern "C" int chb_apply_op(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int B, int H, int W, int C,
+                            const chb_op* op, int64_t batch_total, int64_t image_index_base,
+                            uint64_t seed, uint32_t call_counter, const int32_t* d_replay,
+                            int32_t* d_record, void* stream) {
+  if (!op) return fail(ctx, CHB_ERR_INVALID, "op is NULL");
+  chb_transform t;
+  memset(&t, 0, sizeof(t));
+  t.n_ops = 1;
+  t.ops[0] = *op;
+  chb_policy pol = {1, 1, 0, 0, &t};
+  return launch_device(ctx, d_in, d_out, B, H, W, C, &pol, batch_total, image_index_base, seed,
+                       call_counter, d_replay, d_record, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------ e2e pipeline
+static int ensure_staging(chb_ctx* ctx, size_t img_bytes, size_t sched_bytes) {
+  for (int i = 0; i < kPipe; ++i)
+    if (!ctx->streams[i]) CHB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
+  if (img_bytes > ctx->st_img_bytes) {
+    for (int i = 0; i < kPipe; ++i) {
+      if (ctx->st_in[i]) CHB_CUDA(ctx, cudaFree(ctx->st_in[i]));
+      if (ctx->st_out[i]) CHB_CUDA(ctx, cudaFree(ctx->st_out[i]));
+      ctx->st_in[i] = ctx->st_out[i] = nullptr;
+    }
+    ctx->st_img_bytes = 0;
+    for (int i = 0; i < kPipe; ++i) {
+      CHB_CUDA(ctx, cudaMalloc(&ctx->st_in[i], img_bytes));
+      CHB_CUDA(ctx, cudaMalloc(&ctx->st_out[i], img_bytes));
+    }
+    ctx->st_img_bytes = img_bytes;
+  }
+  if (sched_bytes > ctx->st_sched_bytes) {
+    for (int i = 0; i < kPipe; ++i) {
+      if (ctx->st_replay[i]) CHB_CUDA(ctx, cudaFree(ctx->st_replay[i]));
+      if (ctx->st_record[i]) CHB_CUDA(ctx, cudaFree(ctx->st_record[i]));
+      ctx->st_replay[i] = ctx->st_record[i] = nullptr;
+    }
+    ctx->st_sched_bytes = 0;
+    for (int i = 0; i < kPipe; ++i) {
+      CHB_CUDA(ctx, cudaMalloc(&ctx->st_replay[i], sched_bytes));
+      CHB_CUDA(ctx, cudaMalloc(&ctx->st_record[i], sched_bytes));
+    }
+    ctx->st_sched_bytes = sched_bytes;
+  }
+  return CHB_OK;
+}
+
+extern "C" int chb_policy_apply_host(chb_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, int B, int H,
+                                     int W, int C, const chb_policy* policy, int64_t batch_total,
+                                     int64_t image_index_base, uint64_t seed, uint32_t call_counter,
+                                     const int32_t* h_replay, int32_t* h_record) {
+  if (!ctx) return CHB_ERR_INVALID;
+  if (B < 0 || H < 0 || W < 0) return fail(ctx, CHB_ERR_INVALID, "negative shape");
+  if (C < 1 || C > 4) return fail(ctx, CHB_ERR_UNSUPPORTED, "channels must be 1..4");
+  int K = 1;
+  int r = validate_policy(ctx, policy, K);
+  if (r != CHB_OK) return r;
+  CHB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t img = (size_t)H * W * C;
+  if (B == 0 || img == 0) {
+    // still validate the ops the way a real call would
+    return launch_device(ctx, nullptr, nullptr, 0, H, W, C, policy, batch_total, image_index_base,
+                         seed, call_counter, nullptr, nullptr, 0);
+  }
+  if (!h_in || !h_out) return fail(ctx, CHB_ERR_INVALID, "NULL image pointer");
+  // chunk so that copy-in, kernel and copy-out of neighbouring chunks overlap.
+  int n_chunks = 8;
+  if (B < n_chunks) n_chunks = B;
+  const int per = (B + n_chunks - 1) / n_chunks;
+  const size_t sched_per_img = (size_t)policy->n_draws * K * CHB_SCHED_FIELDS * sizeof(int32_t);
+  r = ensure_staging(ctx, (size_t)per * img, (size_t)per * sched_per_img + 16);
+  if (r != CHB_OK) return r;
+  for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
+    const int nb = (B - b0 < per) ? (B - b0) : per;
+    const int sl = c % kPipe;
+    cudaStream_t st = ctx->streams[sl];
+    // staging slot reuse is ordered by the slot's own stream.
+    CHB_CUDA(ctx, cudaMemcpyAsync(ctx->st_in[sl], h_in + (size_t)b0 * img, (size_t)nb * img, cudaMemcpyHostToDevice, st));
+    if (h_replay && sched_per_img)
+      CHB_CUDA(ctx, cudaMemcpyAsync(ctx->st_replay[sl], (const uint8_t*)h_replay + (size_t)b0 * sched_per_img,
+                                    (size_t)nb * sched_per_img, cudaMemcpyHostToDevice, st));
+    r = launch_device(ctx, ctx->st_in[sl], ctx->st_out[sl], nb, H, W, C, policy, batch_total,
+                      image_index_base + b0, seed, call_counter,
+                      (h_replay && sched_per_img) ? ctx->st_replay[sl] : nullptr,
+                      (h_record && sched_per_img) ? ctx->st_record[sl] : nullptr, st);
+    if (r != CHB_OK) return r;
+    CHB_CUDA(ctx, cudaMemcpyAsync(h_out + (size_t)b0 * img, ctx->st_out[sl], (size_t)nb * img, cudaMemcpyDeviceToHost, st));
+    if (h_record && sched_per_img)
+      CHB_CUDA(ctx, cudaMemcpyAsync((uint8_t*)h_record + (size_t)b0 * sched_per_img, ctx->st_record[sl],
+                                    (size_t)nb * sched_per_img, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < kPipe; ++i) CHB_CUDA(ctx, cudaStreamSynchronize(ctx->streams[i]));
+  return CHB_OK;
+}

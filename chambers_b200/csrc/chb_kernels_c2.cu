@@ -1,0 +1,5 @@
+// policy_kernel<2, *> instantiations (see chb_kernels.cuh).
+#include "chb_kernels.cuh"
+namespace chb {
+CHB_DEFINE_CHANNEL_ENTRY(2)
+}

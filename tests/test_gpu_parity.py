@@ -1,0 +1,286 @@
+"""GPU parity tests (``-m gpu``): the CUDA path, called through the Python layers -> ctypes ->
+C ABI, against the oracle on identical inputs and identical schedules.
+
+Bar (BASELINE.json north_star): bit-exact for the integer ops (posterize, solarize, invert,
+equalize, cutout, nearest warps given equal coordinates) and within +-1 LSB for the float-blended /
+interpolated ops.  The kernel restates the oracle's float32 step order with unfused *_rn
+arithmetic, so these tests assert 0 LSB everywhere; TOL documents the contractual bar.
+"""
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import random_images
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+TOL = {"Brightness": 1, "Contrast": 1, "Color": 1, "Sharpness": 1, "AutoContrast": 1}  # contractual, LSB
+ASSERT_TOL = 0  # what we actually hold ourselves to
+
+
+@pytest.fixture(scope="module")
+def A():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    from chambers_b200 import build, augmentations
+    build.build_library()
+    return augmentations
+
+
+def to_gpu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def run_layer(layer, x, **kw):
+    y = layer(to_gpu(x), **kw)
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+def assert_same(got, want, what=""):
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    bad = int((diff > ASSERT_TOL).sum())
+    assert bad == 0, "%s: %d mismatching bytes of %d, max |diff| %d, first at %r" % (
+        what, bad, diff.size, int(diff.max()), tuple(np.argwhere(diff > ASSERT_TOL)[0]))
+
+
+def policy_of(layer):
+    """oracle policy (transforms, n) equivalent to a chambers_b200 layer."""
+    from chambers_b200.augmentations.image_augmentations import _flatten_transform, RandomChoice, _OpLayer
+    def spec(l, p):
+        cfg = {k: v for k, v in l.get_config().items() if k != "name"}
+        return (type(l).__name__, cfg, p)
+    if isinstance(layer, RandomChoice):
+        return [[spec(l, p) for l, p in _flatten_transform(t)] for t in layer.transforms], layer.n_transforms
+    if hasattr(layer, "_transform"):
+        return policy_of(layer._transform)
+    return [[spec(l, p) for l, p in _flatten_transform(layer)]], 1
+
+
+SINGLE_OPS = [
+    ("AutoContrast", {}), ("Equalize", {}), ("Invert", {}),
+    ("Brightness", {"factor": 1.9000000000000001}), ("Brightness", {"factor": 0.28}),
+    ("Brightness", {"factor": 1.0}), ("Brightness", {"factor": 0.0}),
+    ("Contrast", {"factor": 1.9000000000000001}), ("Contrast", {"factor": 0.46}),
+    ("Color", {"factor": 1.9000000000000001}), ("Color", {"factor": 0.1}), ("Color", {"factor": 0.0}),
+    ("Sharpness", {"factor": 1.9000000000000001}), ("Sharpness", {"factor": 0.28}), ("Sharpness", {"factor": 0.0}),
+    ("ShearX", {"level": 0.3, "fill_value": 128}), ("ShearY", {"level": 0.44999999999999996, "fill_value": 128}),
+    ("TranslateX", {"pixels": 100.0, "fill_value": 128}), ("TranslateY", {"pixels": 17.0, "fill_value": 3}),
+    ("Posterize", {"bits": 4}), ("Posterize", {"bits": 0}), ("Posterize", {"bits": 8}),
+    ("Solarize", {"threshold": 256}), ("Solarize", {"threshold": 384}), ("Solarize", {"threshold": 77}),
+    ("SolarizeAdd", {"addition": 110}), ("SolarizeAdd", {"addition": -40, "threshold": 200}),
+    ("CutOut", {"mask_size": 80, "constant_values": 128}), ("CutOut", {"mask_size": 0}),
+    ("Rotate", {"degrees": 30.0, "fill_value": 128}), ("Rotate", {"degrees": 45.0}), ("Rotate", {"degrees": 0.0}),
+]
+
+
+@pytest.mark.parametrize("name,kwargs", SINGLE_OPS, ids=lambda v: str(v) if isinstance(v, str) else "-".join("%s" % x for x in v.values()))
+@pytest.mark.parametrize("shape,kind", [((5, 37, 53, 3), "uniform"), ((3, 224, 224, 3), "smooth"), ((2, 96, 64, 3), "lowentropy")])
+def test_single_op_layers(A, name, kwargs, shape, kind):
+    x = random_images(*shape, seed=11, kind=kind)
+    layer = getattr(A, name)(**kwargs)
+    for call in range(2):  # two calls: both sign flips / different centres are likely to occur
+        y = run_layer(layer, x, seed=99, call_counter=call, record=True)
+        sched = layer.last_schedule
+        want = oracle.apply_schedule(x, policy_of(layer), sched, elementwise=False)
+        assert_same(y, want, "%s%r call %d" % (name, kwargs, call))
+
+
+def test_device_schedule_matches_oracle_philox(A):
+    x = random_images(300, 32, 40, 3, seed=1)
+    for layer, ew in [(A.RandAugment(3, 15, elementwise=True), True), (A.RandAugment(2, 10), False),
+                      (A.AutoAugment(elementwise=True), True), (A.AutoAugment(), False)]:
+        run_layer(layer, x, training=True, seed=0xDEADBEEFCAFE1234, call_counter=5, image_index_base=1000,
+                  batch_total=5000, record=True)
+        want = oracle.decode_schedule(policy_of(layer), 0xDEADBEEFCAFE1234, 5, 1000, 300, 32, 40, ew)
+        assert (layer.last_schedule == want).all(), type(layer).__name__
+
+
+def _replay_all_pairs(n_ops=16):
+    pairs = [(i, j) for i in range(n_ops) for j in range(n_ops)]
+    B = len(pairs)
+    rng = np.random.default_rng(7)
+    s = np.zeros((B, 2, 1, 5), np.int32)
+    for b, (i, j) in enumerate(pairs):
+        s[b, 0, 0, 0], s[b, 1, 0, 0] = i, j
+    s[..., 1] = 1
+    s[..., 2] = rng.integers(0, 2, size=(B, 2, 1))
+    return s, rng
+
+
+@pytest.mark.parametrize("magnitude,shape", [(10, (64, 64)), (15, (50, 70)), (3, (224, 224))])
+def test_all_256_op_pairs_fused(A, magnitude, shape):
+    """Every ordered pair of the 16 ops through the fused chain kernel (replayed schedule)."""
+    H, W = shape
+    s, rng = _replay_all_pairs()
+    s[..., 3] = rng.integers(0, H, size=s.shape[:3])
+    s[..., 4] = rng.integers(0, W, size=s.shape[:3])
+    x = random_images(256, H, W, 3, seed=21, kind="smooth" if magnitude == 3 else "uniform")
+    layer = A.RandAugment(2, magnitude, elementwise=True)
+    y = run_layer(layer, x, training=True, replay=s)
+    want = oracle.apply_schedule(x, policy_of(layer), s, elementwise=True)
+    for b in range(256):
+        assert_same(y[b], want[b], "pair %s -> %s" % (oracle.OP_NAMES[s[b, 0, 0, 0]], oracle.OP_NAMES[s[b, 1, 0, 0]]))
+
+
+def test_random_triples_m15(A):
+    x = random_images(768, 40, 56, 3, seed=5)
+    layer = A.RandAugment(3, 15, elementwise=True)
+    y = run_layer(layer, x, training=True, seed=3, call_counter=0, record=True)
+    want = oracle.apply_schedule(x, policy_of(layer), layer.last_schedule, elementwise=True)
+    for b in range(x.shape[0]):
+        assert_same(y[b], want[b], "triple %r" % ([oracle.OP_NAMES[i] for i in layer.last_schedule[b, :, 0, 0]],))
+
+
+@pytest.mark.parametrize("elementwise", [False, True])
+def test_config0_randaugment_on_reference_sample_data(A, c1_batch, elementwise):
+    """BASELINE.json configs[0]: RandAugment N=2 M=10 on the 32x224x224x3 sample_data batch."""
+    layer = A.RandAugment(2, 10, elementwise=elementwise)
+    for call in range(6 if not elementwise else 2):
+        y = run_layer(layer, c1_batch, training=True, seed=0, call_counter=call, record=True)
+        want = oracle.apply_schedule(c1_batch, policy_of(layer), layer.last_schedule, elementwise)
+        assert_same(y, want, "call %d" % call)
+
+
+def test_autoaugment_every_subpolicy(A, c1_batch):
+    """All 25 sub-policies with both coins forced on (replay), then the device's own coins."""
+    x = np.concatenate([c1_batch[:25], c1_batch[:25]])
+    s = np.zeros((50, 1, 2, 5), np.int32)
+    s[:, 0, :, 0] = np.tile(np.arange(25), 2)[:, None]
+    s[..., 1] = 1
+    s[:25, :, :, 2] = 1
+    layer = A.AutoAugment(elementwise=True)
+    y = run_layer(layer, x, training=True, replay=s)
+    want = oracle.apply_schedule(x, policy_of(layer), s, elementwise=True)
+    for b in range(50):
+        assert_same(y[b], want[b], "sub-policy %d" % s[b, 0, 0, 0])
+    y = run_layer(layer, c1_batch, training=True, seed=17, call_counter=0, record=True)
+    want = oracle.apply_schedule(c1_batch, policy_of(layer), layer.last_schedule, elementwise=True)
+    assert_same(y, want, "device coins")
+    batch_layer = A.AutoAugment()
+    for call in range(4):
+        y = run_layer(batch_layer, c1_batch[:8], training=True, seed=4, call_counter=call, record=True)
+        want = oracle.apply_schedule(c1_batch[:8], policy_of(batch_layer), batch_layer.last_schedule, False)
+        assert_same(y, want, "batch mode call %d" % call)
+
+
+@pytest.mark.parametrize("shape", [(6, 256, 256, 3), (3, 512, 512, 3), (4, 301, 299, 3)])
+def test_large_images_global_path(A, shape):
+    """Images that do not fit in shared memory run from global memory (config 4's 512x512)."""
+    from chambers_b200 import _lib
+    assert shape[1] * shape[2] * 3 > _lib.smem_image_limit(torch.cuda.current_device(), 3)
+    x = random_images(*shape, seed=9, kind="smooth")
+    layer = A.RandAugment(3, 15, elementwise=True)
+    for call in range(3):
+        y = run_layer(layer, x, training=True, seed=8, call_counter=call, record=True)
+        want = oracle.apply_schedule(x, policy_of(layer), layer.last_schedule, elementwise=True)
+        assert_same(y, want, "call %d %r" % (call, layer.last_schedule[:, :, 0, 0].tolist()))
+
+
+def test_large_images_all_pairs(A):
+    s, rng = _replay_all_pairs()
+    H, W = 244, 260
+    s[..., 3] = rng.integers(0, H, size=s.shape[:3])
+    s[..., 4] = rng.integers(0, W, size=s.shape[:3])
+    x = random_images(256, H, W, 3, seed=2)
+    layer = A.RandAugment(2, 10, elementwise=True)
+    y = run_layer(layer, x, training=True, replay=s)
+    want = oracle.apply_schedule(x, policy_of(layer), s, elementwise=True)
+    for b in range(256):
+        assert_same(y[b], want[b], "pair %s -> %s" % (oracle.OP_NAMES[s[b, 0, 0, 0]], oracle.OP_NAMES[s[b, 1, 0, 0]]))
+
+
+@pytest.mark.parametrize("C", [1, 2, 4])
+def test_other_channel_counts(A, C):
+    x = random_images(40, 28, 28, C, seed=C)
+    names = [n for n in oracle.OP_NAMES if n not in ("Color", "Contrast")]
+    layers = [getattr(A, n)(**oracle.magnitude_kwargs(n, 10)) for n in names]
+    choice = A.RandomChoice(layers, 2, elementwise=True)
+    y = run_layer(choice, x, seed=1, call_counter=0, record=True)
+    want = oracle.apply_schedule(x, policy_of(choice), choice.last_schedule, elementwise=True)
+    assert_same(y, want, "C=%d" % C)
+    from chambers_b200._lib import ChambersAugError
+    with pytest.raises(ChambersAugError):
+        run_layer(A.Color(1.5), x)
+
+
+@pytest.mark.parametrize("interpolation", ["nearest", "bilinear"])
+@pytest.mark.parametrize("fill_mode", ["constant", "reflect", "wrap", "nearest"])
+def test_geometric_interpolation_and_fill_modes(A, interpolation, fill_mode):
+    x = random_images(3, 45, 61, 3, seed=13, kind="smooth")
+    kw = dict(interpolation=interpolation, fill_mode=fill_mode, fill_value=77.0)
+    for layer in (A.Rotate(33.0, **kw), A.ShearX(0.7, **kw), A.ShearY(0.21, **kw), A.TranslateX(70.0, **kw),
+                  A.TranslateY(12.5, **kw)):
+        for call in range(2):
+            y = run_layer(layer, x, seed=5, call_counter=call, record=True)
+            want = oracle.apply_schedule(x, policy_of(layer), layer.last_schedule, elementwise=False)
+            assert_same(y, want, "%s %s %s" % (type(layer).__name__, interpolation, fill_mode))
+    # a bilinear warp inside a chain (materialisation path)
+    chain = A.RandomChoice([A.Sequential([A.Equalize(), A.Rotate(20.0, **kw), A.Sharpness(1.5), A.ShearX(0.2, **kw)])], 1,
+                           elementwise=True)
+    y = run_layer(chain, x, seed=2, call_counter=0, record=True)
+    want = oracle.apply_schedule(x, policy_of(chain), chain.last_schedule, elementwise=True)
+    assert_same(y, want, "bilinear chain")
+
+
+def test_shard_invariance_and_host_path(A):
+    """RNG keyed by global image index: 1 shard == 4 shards; numpy host path == device path."""
+    x = random_images(64, 64, 64, 3, seed=3)
+    for layer in (A.RandAugment(2, 10, elementwise=True), A.RandAugment(2, 10, elementwise=False), A.AutoAugment(True)):
+        whole = run_layer(layer, x, training=True, seed=77, call_counter=3)
+        parts = [run_layer(layer, x[i:i + 16], training=True, seed=77, call_counter=3, image_index_base=i, batch_total=64)
+                 for i in range(0, 64, 16)]
+        assert (np.concatenate(parts) == whole).all()
+        host = layer(x, training=True, seed=77, call_counter=3)  # numpy in -> chb_policy_apply_host
+        assert isinstance(host, np.ndarray) and (host == whole).all()
+        pinned = torch.from_numpy(x).pin_memory()
+        host_t = layer(pinned, training=True, seed=77, call_counter=3)
+        assert (host_t.numpy() == whole).all()
+
+
+def test_in_place_and_empty_batches(A):
+    x = random_images(9, 32, 32, 3, seed=4)
+    layer = A.RandAugment(2, 10, elementwise=True)
+    want = run_layer(layer, x, training=True, seed=1, call_counter=0)
+    t = to_gpu(x)
+    out = layer._transform(t, seed=1, call_counter=0, out=t)
+    torch.cuda.synchronize()
+    assert out.data_ptr() == t.data_ptr() and (t.cpu().numpy() == want).all()
+    empty = layer(torch.empty((0, 32, 32, 3), dtype=torch.uint8, device="cuda"), training=True)
+    assert tuple(empty.shape) == (0, 32, 32, 3)
+    with pytest.raises(ValueError):
+        run_layer(A.CutOut(3), x)
+
+
+def test_full_size_batches_sampled_against_oracle(A):
+    """BASELINE configs[1] (256x224x224x3) and a slice of configs[4]'s 8192 sweep: sampled images are
+    checked against the oracle; whole-batch size-independent properties are checked on the device."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randint(0, 256, (256, 224, 224, 3), dtype=torch.uint8, generator=g)
+    xg = x.cuda()
+    layer = A.RandAugment(2, 10, elementwise=True)
+    y = layer(xg, training=True, seed=0, call_counter=0, record=True)
+    idx = [0, 1, 17, 100, 147, 148, 200, 255]
+    want = oracle.apply_schedule(x.numpy()[idx], policy_of(layer), layer.last_schedule[idx], elementwise=True)
+    assert_same(y[idx].cpu().numpy(), want, "config 1 sample")
+    big = torch.randint(0, 256, (2048, 224, 224, 3), dtype=torch.uint8, generator=g).cuda()
+    inv = A.Invert()
+    assert torch.equal(inv(inv(big)), big)                                  # involution
+    post = A.Posterize(4)
+    p1 = post(big)
+    assert torch.equal(post(p1), p1) and int((p1 & 15).max()) == 0         # idempotent, low bits cleared
+    sol = A.Solarize(256)
+    assert torch.equal(sol(big), inv(big))                                  # wrapped threshold == invert
+    eq = A.Equalize()(big)
+    assert int((eq.amax(dim=(1, 2)) - eq.amin(dim=(1, 2))).min()) >= 250    # equalised noise spans the range
+    tx = A.TranslateX(100.0, fill_value=128)
+    t = tx(big, seed=1, call_counter=0, record=True)
+    if tx.last_schedule[0, 0, 0, 2]:   # negated: src_x = x - 100
+        assert torch.equal(t[:, :, 100:], big[:, :, :124]) and int((t[:, :, :100] != 128).sum()) == 0
+    else:
+        assert torch.equal(t[:, :, :124], big[:, :, 100:]) and int((t[:, :, 124:] != 128).sum()) == 0
+    cut = A.CutOut(80, 128)(big, seed=2, call_counter=0)
+    changed = (cut != big).any(dim=3).sum(dim=(1, 2))
+    assert int(changed.max()) <= 80 * 80 and int(((cut != big) & (cut != 128)).sum()) == 0
