@@ -98,45 +98,70 @@ def cpu_port_throughput(batch, policy_name, elementwise, min_seconds=8.0, max_ba
 
 # --------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
-        self.samples = []
-        self.proc = None
         self.gpu = gpu_index
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            # CUDA_VISIBLE_DEVICES may renumber devices; go through the PCI bus id of the torch device.
+            import torch
+            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(gpu_index), "pci_bus_id") else None
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index) if bus is None else self._by_bus(bus, gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _by_bus(self, bus, fallback):
+        nv = self._nv
+        try:
+            for i in range(nv.nvmlDeviceGetCount()):
+                h = nv.nvmlDeviceGetHandleByIndex(i)
+                if int(nv.nvmlDeviceGetPciInfo(h).bus) == int(bus):
+                    return h
+        except Exception:
+            pass
+        return nv.nvmlDeviceGetHandleByIndex(fallback)
+
+    def _sample(self):
+        nv = self._nv
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)) if hasattr(
+                nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+            for name, bit in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._sample()
+            time.sleep(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+        if self._h is None:
+            return
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [v.strip() for v in s.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self._thread is not None:
+            self._sample()
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def measured_peak():

@@ -17,13 +17,19 @@
 //   * nearest-neighbour Rotate / Shear / Translate and CutOut are appended to the spatial list;
 //   * Sharpness and bilinear warps need a materialised neighbourhood: the virtual image is written
 //     to a per-CTA scratch (L2-resident) and read back.
-// The final pass pulls every output pixel through the spatial list, the raw image and the LUT and
-// stores 16-byte vectors.
+// The final pass either maps 16-byte vectors through the LUT straight to global memory, or gathers
+// every output pixel through the spatial list into a shared-memory staging tile that a TMA bulk
+// store (cp.async.bulk.global.shared) drains while the next tile is computed.
+//
+// All hot loops have small bodies (4 pixels / 16 bytes per trip): the first version unrolled 16
+// pixels per trip and ncu showed instruction-cache misses ("no_instruction") as its top stall
+// (profiles/r01_v2_*).
 //
 // Semantics follow /root/reference/chambers/augmentations/image_augmentations.py (cited per op) and
 // the oracle in /oracle (which this file never calls).  All float32 arithmetic that feeds a
 // truncation uses explicit round-to-nearest intrinsics so that no FMA contraction can change a
 // result (TensorFlow's CPU kernels round after every op).
+#pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,9 +39,11 @@ namespace chb {
 
 namespace {
 
+constexpr int NT = 512;                      // threads per CTA (up to 128 registers each)
 constexpr int MAXC = 4;
 constexpr int HIST_WORDS_PER_CH = 128 * 32;  // 128 bin pairs x 32 lane replicas, u16x2 packed
 constexpr int TAB_WORDS = 256 * 32;          // replicated LUT table: word = {lut0,lut1,lut2,lut3}[v]
+constexpr int STAGE_PIX = NT * 4;            // pixels per staging tile: one 4-pixel group per thread
 
 enum { SP_GEOM = 0, SP_MASK = 1 };
 
@@ -48,23 +56,29 @@ struct Spatial {
 };
 
 struct ProgEntry {
-  int op, negate, cy, cx;
+  DevOp op;  // private copy: the interpreter never goes back to global memory for parameters
+  int negate, cy, cx, table_index;
 };
 
 struct Small {
   unsigned long long mbar;
   int n_prog, n_sp, lut_identity, next_img;
+  uint32_t rnd[32][4];   // schedule decode scratch: Philox words per slot (stream / own image)
+  uint32_t rndc[32][4];
   ProgEntry prog[CHB_MAX_CHAIN];
   Spatial sp[CHB_MAX_CHAIN];
   uint8_t lut[MAXC][256];
   uint8_t etab[MAXC][256];
   unsigned int hmap[MAXC][256];
-  DevOp ops[CHB_MAX_TABLE_OPS];
 };
 
 __host__ __device__ constexpr size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ constexpr size_t big_region_bytes(int C) {
   return (size_t)(C * HIST_WORDS_PER_CH > TAB_WORDS ? C * HIST_WORDS_PER_CH : TAB_WORDS) * 4;
+}
+__host__ __device__ constexpr size_t stage_bytes(int C) { return (size_t)STAGE_PIX * C; }  // one buffer
+__host__ __device__ constexpr size_t smem_overhead_bytes(int C) {
+  return big_region_bytes(C) + 2 * stage_bytes(C) + align_up(sizeof(Small), 128) + 128;
 }
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -101,8 +115,52 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
       "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
       : "memory");
 }
+// TMA 1-D bulk copy shared -> global, tracked by bulk async-groups.
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_addr(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // <= N groups still reading their shared source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {  // <= N groups not yet complete (writes visible)
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// Explicit shared-space accesses on 32-bit shared addresses.  Going through generic pointers made
+// the compiler rebuild a shared::cluster address (S2R SR_CgaCtaId + LEA) in front of every access.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) {  // fire-and-forget shared atomic add
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint4 ld_cg(const uint4* p) { return __ldcg(p); }
 __device__ __forceinline__ void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
@@ -123,6 +181,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 
 // ------------------------------------------------------------------------- per-value semantics
 // chambers' blend, image_augmentations.py:10-49, on one value (image1 = degenerate, image2 = x).
+// Table-building form (768 entries per op, not hot).
 __device__ __forceinline__ int blend_value(int i1, int i2, float f, int mode) {
   if (mode == BLEND_IMAGE2) return i2;  // factor == 1.0, :30-31
   if (mode == BLEND_IMAGE1) return i1;  // factor == 0.0, :28-29
@@ -155,7 +214,7 @@ __device__ __forceinline__ int pointwise_value(const DevOp& op, int v) {
 }
 
 // Color (:233-235): blend(grayscale(x) broadcast, x, factor); tf.image.rgb_to_grayscale restated
-// (oracle/ops.py rgb_to_grayscale).
+// (oracle/ops.py rgb_to_grayscale).  Integer form for the few spatial colours.
 __device__ __forceinline__ void color_pixel(int& r, int& g, int& b, float f, int mode) {
   const float k = __int_as_float(0x3b808081);  // float32(1/255)
   const float fr = __fmul_rn((float)r, k), fg = __fmul_rn((float)g, k), fb = __fmul_rn((float)b, k);
@@ -168,11 +227,54 @@ __device__ __forceinline__ void color_pixel(int& r, int& g, int& b, float f, int
   b = blend_value(gray, b, f, mode);
 }
 
-// std::round (half away from zero) on float32, exactly (oracle/ops.py round_half_away).
+__device__ __forceinline__ int get_byte(uint32_t w, int i) { return (w >> (8 * i)) & 0xFF; }
+// Byte i (compile-time) of w, zero-extended: one PRMT.
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0u, 0x4440u | (uint32_t)i); }
+// acc with byte i (compile-time) replaced by the low byte of v: one PRMT.
+__device__ __forceinline__ uint32_t put_byte(uint32_t acc, uint32_t v, int i) {
+  return __byte_perm(acc, v, i == 0 ? 0x3214u : i == 1 ? 0x3240u : i == 2 ? 0x3410u : 0x4210u);
+}
+// float(byte i of w) without a conversion-pipe instruction: 0x4B0000vv is 2^23 + v, minus 2^23.
+__device__ __forceinline__ float byte_to_float(uint32_t w, int i) {
+  return __fadd_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)i)), -8388608.0f);
+}
+__device__ __forceinline__ float small_uint_to_float(uint32_t v) {  // v < 2^23, exact
+  return __fadd_rn(__uint_as_float(0x4B000000u | v), -8388608.0f);
+}
+// trunc(t) for 0 <= t < 2^23 as the low bits of fl_rz(t + 2^23) (ulp there is 1).
+__device__ __forceinline__ uint32_t trunc_bits(float t) { return __float_as_uint(__fadd_rz(t, 8388608.0f)); }
+// rint (half-to-even) for 0 <= t < 2^22 as the low bits of fl_rn(t + 1.5 * 2^23).
+__device__ __forceinline__ uint32_t rint_bits(float t) { return __float_as_uint(__fadd_rn(t, 12582912.0f)); }
+__device__ __forceinline__ float clamp255(float t) { return fminf(fmaxf(t, 0.0f), 255.0f); }
+
+// std::round(v) (half away from zero) as an int, exact for |v| < 2^23; saturates beyond.
+__device__ __forceinline__ int round_half_away_i(float v) {
+  const int i = __float2int_rz(__fadd_rn(v, copysignf(0.5f, v)));
+  return fabsf(v) < 0.5f ? 0 : i;
+}
+// std::round on float32 (oracle/ops.py round_half_away), float result.
 __device__ __forceinline__ float round_half_away(float v) {
   const float r = truncf(v);
   const float d = __fsub_rn(v, r);
   return r + (d >= 0.5f ? 1.0f : 0.0f) - (d <= -0.5f ? 1.0f : 0.0f);
+}
+
+// Hot-loop form of chambers' blend on floats holding integers: trunc(clip(a + f * (b - a))).  The
+// clip is a no-op for 0 <= f <= 1 (image_augmentations.py:43-45), so one formula serves both modes,
+// and f == 0 yields a exactly.
+__device__ __forceinline__ uint32_t blend_trunc(float a, float b, float f) {
+  return trunc_bits(clamp255(__fadd_rn(a, __fmul_rn(f, __fsub_rn(b, a)))));
+}
+// Color on float channels; returns the three result bytes in the low bits of R, G, B.
+__device__ __forceinline__ void color_pixel_f(float r, float g, float b, float f, uint32_t& R, uint32_t& G, uint32_t& B) {
+  const float k = __int_as_float(0x3b808081);  // float32(1/255)
+  float s = __fmul_rn(__fmul_rn(r, k), __int_as_float(0x3e99096c));
+  s = __fadd_rn(s, __fmul_rn(__fmul_rn(g, k), __int_as_float(0x3f1645a2)));
+  s = __fadd_rn(s, __fmul_rn(__fmul_rn(b, k), __int_as_float(0x3de978d5)));
+  const float gray = __fadd_rn(__fadd_rz(__fmul_rn(s, 255.5f), 8388608.0f), -8388608.0f);  // float(trunc(.))
+  R = blend_trunc(gray, r, f);
+  G = blend_trunc(gray, g, f);
+  B = blend_trunc(gray, b, f);
 }
 
 // image_ops.h MapCoordinate for the non-constant fill modes (oracle/ops.py _map_coordinate).
@@ -250,40 +352,35 @@ __device__ __forceinline__ int pull_resolve(const Small* s, int n_sp, int H, int
   return -1;
 }
 
-template <int C>
-struct Unit {
-  static constexpr int BYTES = (C == 3) ? 48 : 16;
-  static constexpr int WORDS = BYTES / 4;
-  static constexpr int VECS = BYTES / 16;
-};
-
-__device__ __forceinline__ int get_byte(uint32_t w, int i) { return (w >> (8 * i)) & 0xFF; }
-
 // The kernel's view of one image while its chain is interpreted.
 template <int C, bool SMEM>
 struct Ctx {
   Small* s;
   uint32_t* big;       // histogram replicas / replicated LUT table (aliased)
+  uint8_t* stage;      // 2 x stage_bytes(C) staging tiles for TMA stores
   uint8_t* simg;       // shared-memory image (SMEM only)
   const uint8_t* raw;  // current raw image: simg, the input image, or a scratch buffer
   uint8_t* scrA;
   uint8_t* scrB;
   int H, W, HW, img_bytes;
-  int tid, nthreads, lane;
+  int tid, lane;
+  uint32_t stage_seq;  // staging tiles issued so far by this CTA
   bool tab_valid;
 
   // In the shared-memory variant every read of the image is provably a shared-space load.
   __device__ __forceinline__ const uint8_t* img_src() const { return SMEM ? simg : raw; }
   __device__ __forceinline__ int raw_at(int idx) const { return img_src()[idx]; }
 
-  __device__ __forceinline__ int lut_byte(int c, int v) const {
-    // bank-conflict-free lookup: every lane reads its own replica (bank == lane).
-    return (big[v * 32 + lane] >> (8 * c)) & 0xFF;
+  __device__ __forceinline__ const uint8_t* lane_tab() const {
+    return reinterpret_cast<const uint8_t*>(big) + (lane << 2);
   }
+  // bank-conflict-free lookup: every lane reads its own replica (bank == lane); LEA + LDS.U8.
+  __device__ __forceinline__ uint32_t lut_at(const uint8_t* tab, int c, uint32_t v) const { return tab[(v << 7) + c]; }
+  __device__ __forceinline__ uint32_t lut_byte(int c, uint32_t v) const { return lut_at(lane_tab(), c, v); }
 
   // (Re)build the replicated table from the compact per-channel LUTs.
   __device__ void build_table() {
-    for (int i = tid; i < TAB_WORDS; i += nthreads) {
+    for (int i = tid; i < TAB_WORDS; i += NT) {
       const int v = i >> 5;
       uint32_t w = 0;
 #pragma unroll
@@ -297,188 +394,325 @@ struct Ctx {
   __device__ uint8_t* free_scratch() const { return (raw == scrA) ? scrB : scrA; }
 
   // ---- pass: dst[i] = LUT[channel(i)][raw[i]] for the whole image (no spatial ops pending).
+  // 16 bytes per trip; the channel of byte b of unit u is (u + b) mod 3 for C == 3, so the three
+  // per-position channel offsets rotate with u instead of unrolling 48 bytes.
   __device__ void map_pass(uint8_t* dst, bool identity) {
-    using U = Unit<C>;
     if (!identity && !tab_valid) build_table();
-    const int n_units = img_bytes / U::BYTES;
+    const int n_units = img_bytes >> 4;
     const bool dst_vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-    for (int u = tid; u < n_units; u += nthreads) {
-      uint32_t w[U::WORDS];
-      const uint4* src = reinterpret_cast<const uint4*>(img_src() + (size_t)u * U::BYTES);
-#pragma unroll
-      for (int q = 0; q < U::VECS; ++q) {
-        const uint4 v = src[q];
-        w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    const uint8_t* src = img_src();
+    const uint8_t* tab = lane_tab();
+    if (identity) {
+      if (dst_vec) {
+        for (int u = tid; u < n_units; u += NT)
+          st_stream(reinterpret_cast<uint4*>(dst) + u, reinterpret_cast<const uint4*>(src)[u]);
+      } else {
+        for (int i = tid; i < (n_units << 4); i += NT) dst[i] = src[i];
       }
-      if (!identity) {
+    } else {
+      for (int u = tid; u < n_units; u += NT) {
+        const uint4 v = reinterpret_cast<const uint4*>(src)[u];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int ph = (C == 3) ? (u % 3) : 0;  // channel of byte 0 of this unit
+        const uint8_t* t0 = tab + ((C == 3) ? ph : 0);
+        const uint8_t* t1 = tab + ((C == 3) ? (ph == 2 ? 0 : ph + 1) : (1 % C));
+        const uint8_t* t2 = tab + ((C == 3) ? (ph == 0 ? 2 : ph - 1) : (2 % C));
+        const uint8_t* t3 = tab + ((C == 3) ? ph : (3 % C));
 #pragma unroll
-        for (int j = 0; j < U::WORDS; ++j) {
-          uint32_t o = 0;
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int c = (4 * j + b) % C;
-            o |= (uint32_t)lut_byte(c, get_byte(w[j], b)) << (8 * b);
+        for (int j = 0; j < 4; ++j) {
+          uint32_t o;
+          if (C == 3) {
+            // byte index 4j+b -> channel offset pointer t[(4j+b) % 3]
+            const uint8_t* q0 = ((4 * j) % 3 == 0) ? t0 : ((4 * j) % 3 == 1) ? t1 : t2;
+            const uint8_t* q1 = ((4 * j + 1) % 3 == 0) ? t0 : ((4 * j + 1) % 3 == 1) ? t1 : t2;
+            const uint8_t* q2 = ((4 * j + 2) % 3 == 0) ? t0 : ((4 * j + 2) % 3 == 1) ? t1 : t2;
+            const uint8_t* q3 = ((4 * j + 3) % 3 == 0) ? t0 : ((4 * j + 3) % 3 == 1) ? t1 : t2;
+            o = q0[byte_of(w[j], 0) << 7];
+            o = put_byte(o, q1[byte_of(w[j], 1) << 7], 1);
+            o = put_byte(o, q2[byte_of(w[j], 2) << 7], 2);
+            o = put_byte(o, q3[byte_of(w[j], 3) << 7], 3);
+          } else {
+            o = t0[byte_of(w[j], 0) << 7];
+            o = put_byte(o, t1[byte_of(w[j], 1) << 7], 1);
+            o = put_byte(o, t2[byte_of(w[j], 2) << 7], 2);
+            o = put_byte(o, t3[byte_of(w[j], 3) << 7], 3);
           }
           w[j] = o;
         }
-      }
-      uint8_t* d = dst + (size_t)u * U::BYTES;
-      if (dst_vec) {
+        uint8_t* d = dst + ((size_t)u << 4);
+        if (dst_vec) {
+          *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < U::VECS; ++q)
-          reinterpret_cast<uint4*>(d)[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-      } else {
+          for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int j = 0; j < U::WORDS; ++j)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) d[4 * j + b] = (uint8_t)get_byte(w[j], b);
+            for (int b = 0; b < 4; ++b) d[4 * j + b] = (uint8_t)get_byte(w[j], b);
+        }
       }
     }
-    for (int i = n_units * U::BYTES + tid; i < img_bytes; i += nthreads) {
-      const int v = raw_at(i);
+    for (int i = (n_units << 4) + tid; i < img_bytes; i += NT) {
+      const int v = src[i];
       dst[i] = (uint8_t)(identity ? v : lut_byte(i % C, v));
     }
   }
 
   // ---- pass: Color with the pending LUT fused in; dst may alias raw (per-pixel op).
+  // 4 pixels (12 bytes, three words) per trip.
   __device__ void color_pass(uint8_t* dst, float f, int mode, bool identity) {
-    static_assert(C == 3 || C != 3, "");
     if (!identity && !tab_valid) build_table();
     if (C != 3) return;
-    using U = Unit<3>;
-    const int n_units = img_bytes / U::BYTES;
-    for (int u = tid; u < n_units; u += nthreads) {
-      uint32_t w[U::WORDS];
-      const uint4* src = reinterpret_cast<const uint4*>(img_src() + (size_t)u * U::BYTES);
+    const uint8_t* src = img_src();
+    const uint8_t* tab = lane_tab();
+    const int n_groups = HW >> 2;
+    for (int g = tid; g < n_groups; g += NT) {
+      const uint32_t* sp = reinterpret_cast<const uint32_t*>(src) + 3 * g;
+      const uint32_t w[3] = {sp[0], sp[1], sp[2]};
+      uint32_t o[3] = {0, 0, 0};
 #pragma unroll
-      for (int q = 0; q < U::VECS; ++q) {
-        const uint4 v = src[q];
-        w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-      }
-      uint32_t o[U::WORDS];
-#pragma unroll
-      for (int j = 0; j < U::WORDS; ++j) o[j] = 0;
-#pragma unroll
-      for (int px = 0; px < 16; ++px) {
-        int ch[3];
+      for (int px = 0; px < 4; ++px) {
+        float ch[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const int bi = px * 3 + c;
-          int v = get_byte(w[bi >> 2], bi & 3);
-          if (!identity) v = lut_byte(c, v);
-          ch[c] = v;
+          if (identity) ch[c] = byte_to_float(w[bi >> 2], bi & 3);
+          else ch[c] = small_uint_to_float(lut_at(tab, c, byte_of(w[bi >> 2], bi & 3)));
         }
-        color_pixel(ch[0], ch[1], ch[2], f, mode);
+        uint32_t res[3];
+        color_pixel_f(ch[0], ch[1], ch[2], f, res[0], res[1], res[2]);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const int bi = px * 3 + c;
-          o[bi >> 2] |= (uint32_t)ch[c] << (8 * (bi & 3));
+          o[bi >> 2] = put_byte(o[bi >> 2], res[c], bi & 3);
         }
       }
-      uint4* d = reinterpret_cast<uint4*>(dst + (size_t)u * U::BYTES);
-#pragma unroll
-      for (int q = 0; q < U::VECS; ++q) d[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      uint32_t* dp = reinterpret_cast<uint32_t*>(dst) + 3 * g;
+      dp[0] = o[0]; dp[1] = o[1]; dp[2] = o[2];
     }
-    const int first_px = n_units * 16;
-    for (int px = first_px + tid; px < HW; px += nthreads) {
+    for (int px = (n_groups << 2) + tid; px < HW; px += NT) {
       int ch[3];
       for (int c = 0; c < 3; ++c) {
-        const int v = raw_at(px * 3 + c);
-        ch[c] = identity ? v : lut_byte(c, v);
+        const int v = src[px * 3 + c];
+        ch[c] = identity ? v : (int)lut_byte(c, v);
       }
       color_pixel(ch[0], ch[1], ch[2], f, mode);
       for (int c = 0; c < 3; ++c) dst[px * 3 + c] = (uint8_t)ch[c];
     }
   }
 
-  // ---- pass: write the virtual image (spatial list + raw + LUT) to dst, 16 pixels per thread.
-  __device__ void pull_pass(uint8_t* dst, bool identity) {
-    if (!identity && !tab_valid) build_table();
-    const int n_sp = s->n_sp;
-    const int n_pu = (HW + 15) >> 4;
-    const bool dst_vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-    for (int pu = tid; pu < n_pu; pu += nthreads) {
-      const int pix0 = pu << 4;
-      int y = pix0 / W;
-      int x = pix0 - y * W;
-      uint32_t o[4 * C];
+  // ---- gather passes.  The virtual image is produced tile by tile (STAGE_PIX pixels, one 4-pixel
+  // group per thread) into a shared-memory staging buffer; one elected thread hands each finished
+  // tile to the TMA (bulk store shared -> global) and the CTA moves on to the other buffer.
+  // `stage_seq` counts tiles across images, so a store may still be draining its buffer while the
+  // next image is already being loaded and computed; a buffer is reused only after the store issued
+  // two tiles earlier has finished reading it.  `complete`: also wait until the data is in global
+  // memory (needed when this CTA reads it back).
+  template <typename GroupFn>
+  __device__ void staged_emit(uint8_t* dst, bool complete, GroupFn&& group_fn) {
+    const int n_tiles = (HW + STAGE_PIX - 1) / STAGE_PIX;
+    const bool use_tma = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    for (int tile = 0; tile < n_tiles; ++tile, ++stage_seq) {
+      uint8_t* buf = stage + (size_t)(stage_seq & 1u) * stage_bytes(C);
+      if (tid == 0) bulk_wait_read<1>();  // the store issued two tiles ago has released this buffer
+      __syncthreads();
+      const int pix0 = tile * STAGE_PIX;
+      const int npix = min(STAGE_PIX, HW - pix0);
+      const int p = pix0 + (tid << 2);
+      if ((tid << 2) < npix) {
+        uint32_t o[C];
+        group_fn(p, min(4, HW - p), o);
+        uint32_t* bp = reinterpret_cast<uint32_t*>(buf) + tid * C;
 #pragma unroll
-      for (int j = 0; j < 4 * C; ++j) o[j] = 0;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (pix0 + i < HW) {
-          int sx = x, sy = y;
-          const int k = pull_resolve(s, n_sp, H, W, sx, sy);
-          const int base = (sy * W + sx) * C;
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            int v;
-            if (k < 0) {
-              v = raw_at(base + c);
-              if (!identity) v = lut_byte(c, v);
-            } else {
-              v = s->sp[k].color[c];
-            }
-            const int bi = i * C + c;
-            o[bi >> 2] |= (uint32_t)v << (8 * (bi & 3));
-          }
-        }
-        if (++x == W) { x = 0; ++y; }
+        for (int q = 0; q < C; ++q) bp[q] = o[q];
       }
+      const uint32_t bytes = (uint32_t)npix * C;
+      const uint32_t bulk = use_tma ? (bytes & ~15u) : 0u;
+      if (bulk) fence_proxy_async();  // generic-proxy writes -> visible to the async proxy
+      __syncthreads();
       uint8_t* d = dst + (size_t)pix0 * C;
-      if (dst_vec && pix0 + 16 <= HW) {
-#pragma unroll
-        for (int q = 0; q < C; ++q)
-          st_stream(reinterpret_cast<uint4*>(d) + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
-      } else {
-        const int nb = min(16, HW - pix0) * C;
-#pragma unroll
-        for (int b = 0; b < 16 * C; ++b)
-          if (b < nb) d[b] = (uint8_t)get_byte(o[b >> 2], b & 3);
+      if (tid == 0) {
+        if (bulk) bulk_store(d, buf, bulk);
+        bulk_commit();  // one (possibly empty) group per tile keeps the wait arithmetic uniform
       }
+      if (bulk < bytes) {  // unaligned dst / ragged tail: plain copies
+        for (uint32_t i = bulk + tid; i < bytes; i += NT) d[i] = buf[i];
+        __syncthreads();
+      }
+    }
+    if (complete) {
+      if (tid == 0) bulk_wait_all<0>();
+      __syncthreads();
     }
   }
 
+  // Fast gather: the spatial list is one or two constant-fill nearest-neighbour affine warps (the
+  // only form the policies produce).  Coefficients live in registers; ops whose matrix leaves a
+  // coordinate alone (Shear / Translate) skip that coordinate.
+  // MODE 0: general; 1: source row == output row (ShearX, TranslateX); 2: source column == output column.
+  template <int MODE>
+  __device__ void pull_affine(uint8_t* dst, bool complete, bool identity, bool two) {
+    const Spatial& ea = s->sp[s->n_sp - 1];  // applied last -> evaluated first
+    const float t0 = ea.t[0], t1 = ea.t[1], t2 = ea.t[2], t3 = ea.t[3], t4 = ea.t[4], t5 = ea.t[5];
+    float u0 = 1.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, u4 = 1.f, u5 = 0.f;
+    uint32_t fill_a = 0, fill_b = 0;  // colours packed one byte per channel
+#pragma unroll
+    for (int c = 0; c < C; ++c) fill_a |= (uint32_t)ea.color[c] << (8 * c);
+    if (two) {
+      const Spatial& eb = s->sp[s->n_sp - 2];
+      u0 = eb.t[0]; u1 = eb.t[1]; u2 = eb.t[2]; u3 = eb.t[3]; u4 = eb.t[4]; u5 = eb.t[5];
+#pragma unroll
+      for (int c = 0; c < C; ++c) fill_b |= (uint32_t)eb.color[c] << (8 * c);
+    }
+    const uint8_t* src = img_src();
+    const uint8_t* tab = lane_tab();
+    const int Wl = W, Hl = H;
+    staged_emit(dst, complete, [&](int p, int n, uint32_t* o) {
+      int y = p / Wl;
+      int x = p - y * Wl;
+#pragma unroll
+      for (int q = 0; q < C; ++q) o[q] = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < n) {
+          const float fx = small_uint_to_float((uint32_t)x), fy = small_uint_to_float((uint32_t)y);
+          int ix = x, iy = y;
+          if (MODE != 2) ix = round_half_away_i(__fadd_rn(__fadd_rn(__fmul_rn(t0, fx), __fmul_rn(t1, fy)), t2));
+          if (MODE != 1) iy = round_half_away_i(__fadd_rn(__fadd_rn(__fmul_rn(t3, fx), __fmul_rn(t4, fy)), t5));
+          bool inside = (unsigned)ix < (unsigned)Wl && (unsigned)iy < (unsigned)Hl;
+          uint32_t fill = fill_a;
+          if (two && inside) {
+            const float gx = small_uint_to_float((uint32_t)ix), gy = small_uint_to_float((uint32_t)iy);
+            ix = round_half_away_i(__fadd_rn(__fadd_rn(__fmul_rn(u0, gx), __fmul_rn(u1, gy)), u2));
+            iy = round_half_away_i(__fadd_rn(__fadd_rn(__fmul_rn(u3, gx), __fmul_rn(u4, gy)), u5));
+            inside = (unsigned)ix < (unsigned)Wl && (unsigned)iy < (unsigned)Hl;
+            fill = fill_b;
+          }
+          const uint8_t* px = src + (iy * Wl + ix) * C;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            uint32_t v = byte_of(fill, c);
+            if (inside) {
+              v = px[c];
+              if (!identity) v = lut_at(tab, c, v);
+            }
+            const int bi = i * C + c;
+            o[bi >> 2] = put_byte(o[bi >> 2], v, bi & 3);
+          }
+        }
+        if (++x == Wl) { x = 0; ++y; }
+      }
+    });
+  }
+
+  // General gather: any spatial list (CutOut rectangles, non-constant fill modes, 3+ warps).
+  __device__ void pull_generic(uint8_t* dst, bool complete, bool identity) {
+    const int n_sp = s->n_sp;
+    const uint8_t* src = img_src();
+    const uint8_t* tab = lane_tab();
+    const int Wl = W, Hl = H;
+    const Small* sl = s;
+    staged_emit(dst, complete, [&](int p, int n, uint32_t* o) {
+      int y = p / Wl;
+      int x = p - y * Wl;
+#pragma unroll
+      for (int q = 0; q < C; ++q) o[q] = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < n) {
+          int sx = x, sy = y;
+          const int k = pull_resolve(sl, n_sp, Hl, Wl, sx, sy);
+          const uint8_t* px = src + (sy * Wl + sx) * C;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            uint32_t v;
+            if (k < 0) {
+              v = px[c];
+              if (!identity) v = lut_at(tab, c, v);
+            } else {
+              v = (uint32_t)sl->sp[k].color[c];
+            }
+            const int bi = i * C + c;
+            o[bi >> 2] = put_byte(o[bi >> 2], v, bi & 3);
+          }
+        }
+        if (++x == Wl) { x = 0; ++y; }
+      }
+    });
+  }
+
+  // ---- pass: write the virtual image (spatial list + raw + LUT) to dst.
+  __device__ void pull_pass(uint8_t* dst, bool identity, bool complete) {
+    if (!identity && !tab_valid) build_table();
+    const int n_sp = s->n_sp;
+    bool fast = n_sp >= 1 && n_sp <= 2;
+    for (int k = 0; k < n_sp && fast; ++k)
+      fast = s->sp[k].type == SP_GEOM && s->sp[k].fill_mode == CHB_FILL_CONSTANT;
+    if (fast) {
+      const float* t = s->sp[n_sp - 1].t;
+      const bool row_id = (t[3] == 0.0f && t[4] == 1.0f && t[5] == 0.0f);
+      const bool col_id = (t[0] == 1.0f && t[1] == 0.0f && t[2] == 0.0f);
+      if (row_id) pull_affine<1>(dst, complete, identity, n_sp == 2);
+      else if (col_id) pull_affine<2>(dst, complete, identity, n_sp == 2);
+      else pull_affine<0>(dst, complete, identity, n_sp == 2);
+      return;
+    }
+    pull_generic(dst, complete, identity);
+  }
+
   // ---- histogram of the virtual image into s->hmap[c][256].
-  __device__ __forceinline__ void hist_add(int c, int v) {
-    atomicAdd(&big[c * HIST_WORDS_PER_CH + ((v >> 1) << 5) + lane], 1u << ((v & 1) << 4));
+  // Replica layout: word (v >> 1) * 32 + lane holds the u16 counts of bins v & ~1 and v | 1 for
+  // the pixels seen by lane `lane` of any warp: every lane always hits its own bank.
+  __device__ __forceinline__ void hist_add(uint8_t* hb, uint32_t v) {  // hb: channel base + lane * 4
+    atomicAdd(reinterpret_cast<unsigned int*>(hb + ((v & 0xFEu) << 6)), 1u << ((v & 1u) << 4));
   }
 
   __device__ void histogram(bool identity) {
-    using U = Unit<C>;
     const int n_sp = s->n_sp;
-    // A pending LUT and a pull pass both need the table, which aliases the histogram: when spatial
-    // ops are pending, count RAW values for resolved pixels and final colours separately, then map.
-    for (int i = tid; i < C * HIST_WORDS_PER_CH; i += nthreads) big[i] = 0;
-    for (int i = tid; i < MAXC * 256; i += nthreads) (&s->hmap[0][0])[i] = 0;
+    for (int i = tid; i < C * HIST_WORDS_PER_CH; i += NT) big[i] = 0;
+    for (int i = tid; i < MAXC * 256; i += NT) (&s->hmap[0][0])[i] = 0;
     tab_valid = false;
     __syncthreads();
+    uint8_t* hb = reinterpret_cast<uint8_t*>(big) + (lane << 2);
+    const uint8_t* src = img_src();
     if (n_sp == 0) {
-      const int n_units = img_bytes / U::BYTES;
-      for (int u = tid; u < n_units; u += nthreads) {
-        const uint4* src = reinterpret_cast<const uint4*>(img_src() + (size_t)u * U::BYTES);
+      const int n_units = img_bytes >> 4;
+      for (int u = tid; u < n_units; u += NT) {
+        const uint4 v = reinterpret_cast<const uint4*>(src)[u];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int ph = (C == 3) ? (u % 3) : 0;
+        uint8_t* h0 = hb + (size_t)((C == 3) ? ph : 0) * (HIST_WORDS_PER_CH * 4);
+        uint8_t* h1 = hb + (size_t)((C == 3) ? (ph == 2 ? 0 : ph + 1) : (1 % C)) * (HIST_WORDS_PER_CH * 4);
+        uint8_t* h2 = hb + (size_t)((C == 3) ? (ph == 0 ? 2 : ph - 1) : (2 % C)) * (HIST_WORDS_PER_CH * 4);
+        uint8_t* h3 = hb + (size_t)((C == 3) ? ph : (3 % C)) * (HIST_WORDS_PER_CH * 4);
 #pragma unroll
-        for (int q = 0; q < U::VECS; ++q) {
-          const uint4 v = src[q];
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int j = 0; j < 4; ++j) {
+          if (C == 3) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) hist_add((16 * q + 4 * j + b) % C, get_byte(w[j], b));
+            for (int b = 0; b < 4; ++b) {
+              const int r = (4 * j + b) % 3;
+              hist_add(r == 0 ? h0 : r == 1 ? h1 : h2, byte_of(w[j], b));
+            }
+          } else {
+            hist_add(h0, byte_of(w[j], 0));
+            hist_add(h1, byte_of(w[j], 1));
+            hist_add(h2, byte_of(w[j], 2));
+            hist_add(h3, byte_of(w[j], 3));
+          }
         }
       }
-      for (int i = n_units * U::BYTES + tid; i < img_bytes; i += nthreads) hist_add(i % C, raw_at(i));
+      for (int i = (n_units << 4) + tid; i < img_bytes; i += NT)
+        hist_add(hb + (size_t)(i % C) * (HIST_WORDS_PER_CH * 4), src[i]);
     } else {
-      for (int pix = tid; pix < HW; pix += nthreads) {
+      // spatial ops pending: count RAW values of resolved pixels (mapped through the LUT below) and
+      // the already-final colours of fill / mask pixels straight into the mapped histogram.
+      for (int pix = tid; pix < HW; pix += NT) {
         int y = pix / W;
         int x = pix - y * W;
         const int k = pull_resolve(s, n_sp, H, W, x, y);
         if (k < 0) {
-          const int base = (y * W + x) * C;
+          const uint8_t* px = src + (y * W + x) * C;
 #pragma unroll
-          for (int c = 0; c < C; ++c) hist_add(c, raw_at(base + c));
+          for (int c = 0; c < C; ++c) hist_add(hb + (size_t)c * (HIST_WORDS_PER_CH * 4), px[c]);
         } else {
-          // colours are already final values: count them straight into the mapped histogram.
 #pragma unroll
           for (int c = 0; c < C; ++c) atomicAdd(&s->hmap[c][s->sp[k].color[c]], 1u);
         }
@@ -486,7 +720,7 @@ struct Ctx {
     }
     __syncthreads();
     // reduce the 32 lane replicas, mapping raw values through the pending LUT.
-    for (int t = tid; t < C * 256; t += nthreads) {
+    for (int t = tid; t < C * 256; t += NT) {
       const int c = t >> 8, v = t & 255;
       const uint32_t* row = big + c * HIST_WORDS_PER_CH + ((v >> 1) << 5);
       const int sh = (v & 1) << 4;
@@ -558,75 +792,157 @@ struct Ctx {
       }
     }
     __syncthreads();
-    for (int t = tid; t < C * 256; t += nthreads) {
+    for (int t = tid; t < C * 256; t += NT) {
       const int c = t >> 8, v = t & 255;
       s->lut[c][v] = s->etab[c][s->lut[c][v]];
     }
-    for (int t = tid; t < s->n_sp * C; t += nthreads) {
+    for (int t = tid; t < s->n_sp * C; t += NT) {
       const int k = t / C, c = t - k * C;
       s->sp[k].color[c] = s->etab[c][s->sp[k].color[c]];
     }
+    if (tid == 0) s->lut_identity = 0;
+    tab_valid = false;
     __syncthreads();
   }
 
   // ---- Sharpness (tfa.image.sharpness; oracle/ops.py sharpness): raw holds the materialised input.
-  __device__ void sharpness_pass(uint8_t* dst, float f, int mode) {
+  // out = rint(clip(deg + f * (orig - deg))), deg = trunc(sum of the 9 float32 products in row-major
+  // order, starting from 0), border pixels keep deg = orig.
+  __device__ __forceinline__ uint32_t sharp_blend(float deg, float orig, float f) {
+    return rint_bits(clamp255(__fadd_rn(deg, __fmul_rn(f, __fsub_rn(orig, deg)))));
+  }
+
+  // Sliding-column form for rows that are a whole number of words: a thread owns one word column
+  // (4 bytes wide) of a strip of rows and walks down it, keeping the float32 products of the last
+  // two rows of its 4 + 2C-byte window in registers, so every input byte is converted and multiplied
+  // once per column instead of nine times.  A warp's 32 lanes own 32 adjacent word columns: loads
+  // are conflict-free and the 4-byte stores coalesce into full 128-byte lines.
+  __device__ void sharpness_columns(uint8_t* dst, float f) {
+    constexpr int NB = 4 + 2 * C;  // window bytes per row
     const int row = W * C;
+    const int wpr = row >> 2;      // words per row
     const float k1 = __int_as_float(0x3d9d89d9);  // float32(1)/float32(13)
     const float k5 = __int_as_float(0x3ec4ec4f);  // float32(5)/float32(13)
-    const int n16 = (img_bytes + 15) >> 4;
-    const bool dst_vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-    for (int u = tid; u < n16; u += nthreads) {
-      const int i0 = u << 4;
-      int y = i0 / row;
-      int xb = i0 - y * row;
-      uint32_t o[4] = {0, 0, 0, 0};
+    const uint8_t* src = img_src();
+    // first and last row: every pixel is border -> blend(orig, orig) == orig
+    for (int i = tid; i < wpr; i += NT) {
+      reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+      if (H > 1)
+        reinterpret_cast<uint32_t*>(dst)[(size_t)(H - 1) * wpr + i] =
+            reinterpret_cast<const uint32_t*>(src)[(size_t)(H - 1) * wpr + i];
+    }
+    const int inner = H - 2;
+    if (inner <= 0) return;
+    // split the inner rows into S strips so that (word columns x strips) keeps every thread busy:
+    // minimise rounds * (rows per strip + 2 halo rows) over a small range of S.
+    int best_s = 1;
+    long best_cost = 1L << 60;
+    for (int S = 1; S <= 64 && S <= inner; ++S) {
+      const long rounds = ((long)wpr * S + NT - 1) / NT;
+      const long cost = rounds * ((inner + S - 1) / S + 2);
+      if (cost < best_cost) { best_cost = cost; best_s = S; }
+    }
+    const int R = (inner + best_s - 1) / best_s;
+    const int n_strips = (inner + R - 1) / R;
+    const int n_items = wpr * n_strips;
+    for (int item = tid; item < n_items; item += NT) {
+      const int strip = item / wpr;
+      const int xw = item - strip * wpr;
+      const int y_begin = 1 + strip * R;
+      const int y_end = min(H - 1, y_begin + R);
+      const int xb0 = xw << 2;
+      // per byte of the word: is it in the first / last pixel of the row?
+      bool border[4];
 #pragma unroll
-      for (int b = 0; b < 16; ++b) {
-        const int i = i0 + b;
-        if (i < img_bytes) {
-          const int orig = raw_at(i);
-          int deg = orig;
-          const int x = xb / C;
-          if (y > 0 && y < H - 1 && x > 0 && x < W - 1) {
-            float acc = 0.0f;
+      for (int b = 0; b < 4; ++b) border[b] = (xb0 + b < C) || (xb0 + b >= row - C);
+      const bool has_prev = xw > 0, has_next = xw + 1 < wpr;
+      float pa[NB], pb[NB];  // products (x k1) of rows y-1 and y
+      float ctr[4];          // float values of the centre bytes of row y
+      auto load_row = [&](int yy, float* p, float* cvals) {
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(src) + (size_t)yy * wpr + xw;
+        const uint32_t w1 = rp[0];
+        const uint32_t w0 = has_prev ? rp[-1] : 0u;
+        const uint32_t w2 = has_next ? rp[1] : 0u;
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-              for (int dx = -1; dx <= 1; ++dx) {
-                const float kk = (dy == 0 && dx == 0) ? k5 : k1;
-                acc = __fadd_rn(acc, __fmul_rn((float)raw_at(i + dy * row + dx * C), kk));
-              }
-            deg = ((int)acc) & 0xFF;
-          }
-          int r;
-          if (mode == BLEND_IMAGE1) {
-            r = deg;
-          } else {
-            const float a = (float)deg;
-            float t = __fadd_rn(a, __fmul_rn(f, __fsub_rn((float)orig, a)));
-            t = rintf(fminf(fmaxf(t, 0.0f), 255.0f));  // TFA blend: clip, round half-to-even
-            r = (int)t;
-          }
-          o[b >> 2] |= (uint32_t)r << (8 * (b & 3));
+        for (int j = 0; j < NB; ++j) {
+          const int wb = 4 - C + j;  // byte index in the 12-byte (w0, w1, w2) window
+          const uint32_t wsel = (wb < 4) ? w0 : (wb < 8) ? w1 : w2;
+          const float fv = byte_to_float(wsel, wb & 3);
+          p[j] = __fmul_rn(fv, k1);
+          if (cvals != nullptr && j >= C && j < C + 4) cvals[j - C] = fv;
         }
-        if (++xb == row) { xb = 0; ++y; }
-      }
-      if (dst_vec && i0 + 16 <= img_bytes) {
-        st_stream(reinterpret_cast<uint4*>(dst + i0), make_uint4(o[0], o[1], o[2], o[3]));
-      } else {
-        const int nb = min(16, img_bytes - i0);
+      };
+      load_row(y_begin - 1, pa, nullptr);
+      load_row(y_begin, pb, ctr);
+#pragma unroll 3
+      for (int y = y_begin; y < y_end; ++y) {
+        float pc[NB], nctr[4];
+        load_row(y + 1, pc, nctr);
+        uint32_t o = 0;
 #pragma unroll
-        for (int b = 0; b < 16; ++b)
-          if (b < nb) dst[i0 + b] = (uint8_t)get_byte(o[b >> 2], b & 3);
+        for (int b = 0; b < 4; ++b) {
+          const float orig = ctr[b];
+          float deg = orig;
+          if (!border[b]) {
+            // window index b + C is the byte itself, b / b + 2C its left / right neighbours
+            float acc = pa[b];
+            acc = __fadd_rn(acc, pa[b + C]);
+            acc = __fadd_rn(acc, pa[b + 2 * C]);
+            acc = __fadd_rn(acc, pb[b]);
+            acc = __fadd_rn(acc, __fmul_rn(orig, k5));
+            acc = __fadd_rn(acc, pb[b + 2 * C]);
+            acc = __fadd_rn(acc, pc[b]);
+            acc = __fadd_rn(acc, pc[b + C]);
+            acc = __fadd_rn(acc, pc[b + 2 * C]);
+            deg = __fadd_rn(__fadd_rz(acc, 8388608.0f), -8388608.0f);  // float(trunc(acc))
+          }
+          const uint32_t r = sharp_blend(deg, orig, f);
+          o = (b == 0) ? (r & 0xFFu) : put_byte(o, r, b);
+        }
+        reinterpret_cast<uint32_t*>(dst)[(size_t)y * wpr + xw] = o;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) { pa[j] = pb[j]; pb[j] = pc[j]; }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) ctr[b] = nctr[b];
       }
+    }
+  }
+
+  __device__ void sharpness_pass(uint8_t* dst, float f, int mode) {
+    const int row = W * C;
+    if (mode == BLEND_IMAGE1) f = 0.0f;  // factor 0: deg + 0 * (orig - deg) == deg exactly
+    if ((row & 3) == 0 && H >= 1 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(img_src()) & 3) == 0) {
+      sharpness_columns(dst, f);
+      return;
+    }
+    const float k1 = __int_as_float(0x3d9d89d9);
+    const float k5 = __int_as_float(0x3ec4ec4f);
+    for (int i = tid; i < img_bytes; i += NT) {
+      const int y = i / row;
+      const int xb = i - y * row;
+      const int x = xb / C;
+      const int orig = raw_at(i);
+      float deg = (float)orig;
+      if (y > 0 && y < H - 1 && x > 0 && x < W - 1) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const float kk = (dy == 0 && dx == 0) ? k5 : k1;
+            acc = __fadd_rn(acc, __fmul_rn((float)raw_at(i + dy * row + dx * C), kk));
+          }
+        deg = (float)(((int)acc) & 0xFF);
+      }
+      dst[i] = (uint8_t)(sharp_blend(deg, (float)orig, f) & 0xFFu);
     }
   }
 
   // ---- bilinear warp (image_ops.h bilinear_interpolation; oracle/ops.py projective_transform).
   __device__ void bilinear_pass(uint8_t* dst, const float* t, int fill_mode, int fill, bool identity) {
     if (!identity && !tab_valid) build_table();
-    for (int pix = tid; pix < HW; pix += nthreads) {
+    for (int pix = tid; pix < HW; pix += NT) {
       const int y = pix / W, x = pix - y * W;
       float sx, sy;
       affine_source(t, x, y, sx, sy);
@@ -645,7 +961,7 @@ struct Ctx {
         auto tap = [&](bool in, int iy, int ix) -> float {
           if (!in) return (float)fill;
           const int v = raw_at((iy * W + ix) * C + c);
-          return (float)(identity ? v : lut_byte(c, v));
+          return (float)(identity ? v : (int)lut_byte(c, v));
         };
         const float v00 = tap(iny0 && inx0, iy0, ix0), v01 = tap(iny0 && inx1, iy0, ix1);
         const float v10 = tap(iny1 && inx0, iy1, ix0), v11 = tap(iny1 && inx1, iy1, ix1);
@@ -663,9 +979,9 @@ struct Ctx {
     __syncthreads();
     if (SMEM) {
       const int n16 = img_bytes >> 4;
-      for (int i = tid; i < n16; i += nthreads)
+      for (int i = tid; i < n16; i += NT)
         reinterpret_cast<uint4*>(simg)[i] = ld_cg(reinterpret_cast<const uint4*>(buf) + i);
-      for (int i = (n16 << 4) + tid; i < img_bytes; i += nthreads) simg[i] = __ldcg(buf + i);
+      for (int i = (n16 << 4) + tid; i < img_bytes; i += NT) simg[i] = __ldcg(buf + i);
       raw = simg;
     } else {
       raw = buf;
@@ -674,7 +990,7 @@ struct Ctx {
   }
 
   __device__ void reset_lut() {
-    for (int t = tid; t < C * 256; t += nthreads) s->lut[t >> 8][t & 255] = (uint8_t)(t & 255);
+    for (int t = tid; t < C * 256; t += NT) s->lut[t >> 8][t & 255] = (uint8_t)(t & 255);
     if (tid == 0) { s->lut_identity = 1; s->n_sp = 0; }
     tab_valid = false;
     __syncthreads();
@@ -684,83 +1000,92 @@ struct Ctx {
   __device__ void materialize() {
     uint8_t* dst = free_scratch();
     const bool identity = s->lut_identity != 0;
-    if (s->n_sp > 0) pull_pass(dst, identity); else map_pass(dst, identity);
+    if (s->n_sp > 0) pull_pass(dst, identity, true); else map_pass(dst, identity);
     adopt(dst);
     reset_lut();
   }
 };
 
 // ---------------------------------------------------------------------------- schedule decode
-// Twin of oracle/philox.py decode_schedule for ONE image; executed by one thread.
-__device__ void decode_image(const KParams& p, const DevOp* ops, Small* s, int img, int H, int W) {
+// Twin of oracle/philox.py decode_schedule for ONE image, executed by warp 0: every lane draws the
+// Philox block of one slot, lane 0 assembles the chain, the lanes then copy the chosen DevOps.
+__device__ void decode_image(const KParams& p, Small* s, int img, int H, int W, int lane) {
   const unsigned long long own = p.image_index_base + (unsigned long long)img;
   const unsigned long long stream_img = p.elementwise ? own : ~0ull;
   const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-  int n = 0;
-  for (int i = 0; i < p.n_draws; ++i) {
-    const uint32_t slot0 = (uint32_t)(i * (p.K + 1));
-    int choice;
-    const size_t rbase = ((size_t)img * p.n_draws + i) * p.K * CHB_SCHED_FIELDS;
-    if (p.replay) {
-      choice = p.replay[rbase];
-      if (choice < 0 || choice >= p.T) choice = 0;
-    } else {
-      const uint4 w = philox4x32_10(make_uint4((uint32_t)stream_img, (uint32_t)(stream_img >> 32), p.call_counter, slot0), key);
-      choice = (int)__umulhi(w.x, (uint32_t)p.T);
-    }
-    for (int j = 0; j < p.K; ++j) {
-      const int opi = choice * p.K + j;
-      const DevOp& op = ops[opi];
-      int applied, negate, cy, cx;
-      if (p.replay) {
-        const int32_t* r = p.replay + rbase + (size_t)j * CHB_SCHED_FIELDS;
-        applied = (r[1] != 0) && op.kind >= 0;
-        negate = r[2] != 0;
-        cy = r[3];
-        cx = r[4];
-      } else {
-        const uint32_t slot = slot0 + 1 + (uint32_t)j;
-        const uint4 w = philox4x32_10(make_uint4((uint32_t)stream_img, (uint32_t)(stream_img >> 32), p.call_counter, slot), key);
-        uint4 wc = w;
-        if (!p.elementwise) wc = philox4x32_10(make_uint4((uint32_t)own, (uint32_t)(own >> 32), p.call_counter, slot), key);
-        applied = (op.kind >= 0) && ((int)(w.x >> 8) < op.thr24);
-        negate = w.y < 0x80000000u;
-        cy = (int)__umulhi(wc.z, (uint32_t)H);
-        cx = (int)__umulhi(wc.w, (uint32_t)W);
-      }
-      if (p.record) {
-        int32_t* r = p.record + rbase + (size_t)j * CHB_SCHED_FIELDS;
-        r[0] = choice; r[1] = applied; r[2] = negate; r[3] = cy; r[4] = cx;
-      }
-      if (applied && n < CHB_MAX_CHAIN) {
-        s->prog[n].op = opi; s->prog[n].negate = negate; s->prog[n].cy = cy; s->prog[n].cx = cx;
-        ++n;
-      }
-    }
+  const int n_slots = p.n_draws * (p.K + 1);
+  if (!p.replay && lane < n_slots) {
+    const uint4 w = philox4x32_10(make_uint4((uint32_t)stream_img, (uint32_t)(stream_img >> 32), p.call_counter, (uint32_t)lane), key);
+    uint4 wc = w;
+    if (!p.elementwise) wc = philox4x32_10(make_uint4((uint32_t)own, (uint32_t)(own >> 32), p.call_counter, (uint32_t)lane), key);
+    s->rnd[lane][0] = w.x; s->rnd[lane][1] = w.y; s->rnd[lane][2] = w.z; s->rnd[lane][3] = w.w;
+    s->rndc[lane][2] = wc.z; s->rndc[lane][3] = wc.w;
   }
-  s->n_prog = n;
+  __syncwarp();
+  if (lane == 0) {
+    int n = 0;
+    for (int i = 0; i < p.n_draws; ++i) {
+      const int slot0 = i * (p.K + 1);
+      const size_t rbase = ((size_t)img * p.n_draws + i) * p.K * CHB_SCHED_FIELDS;
+      int choice;
+      if (p.replay) {
+        choice = p.replay[rbase];
+        if (choice < 0 || choice >= p.T) choice = 0;
+      } else {
+        choice = (int)__umulhi(s->rnd[slot0][0], (uint32_t)p.T);
+      }
+      for (int j = 0; j < p.K; ++j) {
+        const int opi = choice * p.K + j;
+        const int kind = __ldg(&p.ops[opi].kind);
+        int applied, negate, cy, cx;
+        if (p.replay) {
+          const int32_t* r = p.replay + rbase + (size_t)j * CHB_SCHED_FIELDS;
+          applied = (r[1] != 0) && kind >= 0;
+          negate = r[2] != 0;
+          cy = r[3];
+          cx = r[4];
+        } else {
+          const int slot = slot0 + 1 + j;
+          applied = (kind >= 0) && ((int)(s->rnd[slot][0] >> 8) < __ldg(&p.ops[opi].thr24));
+          negate = s->rnd[slot][1] < 0x80000000u;
+          cy = (int)__umulhi(s->rndc[slot][2], (uint32_t)H);
+          cx = (int)__umulhi(s->rndc[slot][3], (uint32_t)W);
+        }
+        if (p.record) {
+          int32_t* r = p.record + rbase + (size_t)j * CHB_SCHED_FIELDS;
+          r[0] = choice; r[1] = applied; r[2] = negate; r[3] = cy; r[4] = cx;
+        }
+        if (applied && n < CHB_MAX_CHAIN) {
+          s->prog[n].table_index = opi; s->prog[n].negate = negate; s->prog[n].cy = cy; s->prog[n].cx = cx;
+          ++n;
+        }
+      }
+    }
+    s->n_prog = n;
+  }
+  __syncwarp();
+  const int n = s->n_prog;
+  constexpr int OPW = (int)(sizeof(DevOp) / 4);
+  for (int e = 0; e < n; ++e)
+    if (lane < OPW)
+      reinterpret_cast<uint32_t*>(&s->prog[e].op)[lane] =
+          __ldg(reinterpret_cast<const uint32_t*>(&p.ops[s->prog[e].table_index]) + lane);
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------- kernel
 template <int C, bool SMEM>
-__global__ void __launch_bounds__(1024, 1) policy_kernel(const KParams p) {
+__global__ void __launch_bounds__(NT, 1) policy_kernel(const KParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int H = p.H, W = p.W;
   const int img_bytes = H * W * C;
   const size_t img_pad = SMEM ? align_up((size_t)img_bytes, 128) : 0;
   uint8_t* simg = smem_raw;
   uint32_t* big = reinterpret_cast<uint32_t*>(smem_raw + img_pad);
-  Small* s = reinterpret_cast<Small*>(smem_raw + img_pad + big_region_bytes(C));
+  uint8_t* stage = smem_raw + img_pad + big_region_bytes(C);
+  Small* s = reinterpret_cast<Small*>(smem_raw + img_pad + big_region_bytes(C) + 2 * stage_bytes(C));
 
-  const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int n_table = p.T * p.K;
-  const bool ops_in_smem = n_table <= CHB_MAX_TABLE_OPS;
-  if (ops_in_smem) {
-    const int nwords = n_table * (int)(sizeof(DevOp) / 4);
-    for (int i = tid; i < nwords; i += nthreads)
-      reinterpret_cast<uint32_t*>(s->ops)[i] = reinterpret_cast<const uint32_t*>(p.ops)[i];
-  }
-  const DevOp* ops = ops_in_smem ? s->ops : p.ops;
+  const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&s->mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -769,11 +1094,11 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(const KParams p) {
   __syncthreads();
 
   Ctx<C, SMEM> cx;
-  cx.s = s; cx.big = big; cx.simg = simg;
+  cx.s = s; cx.big = big; cx.stage = stage; cx.simg = simg;
   cx.scrA = p.scratch + (size_t)blockIdx.x * 2 * p.scratch_stride;
   cx.scrB = cx.scrA + p.scratch_stride;
   cx.H = H; cx.W = W; cx.HW = H * W; cx.img_bytes = img_bytes;
-  cx.tid = tid; cx.nthreads = nthreads; cx.lane = tid & 31;
+  cx.tid = tid; cx.lane = tid & 31; cx.stage_seq = 0;
   uint32_t phase = 0;
 
   int img = blockIdx.x;
@@ -795,25 +1120,28 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(const KParams p) {
         }
         tma_pending = true;
       } else {
-        for (int i = tid; i < img_bytes; i += nthreads) simg[i] = in_img[i];
+        for (int i = tid; i < img_bytes; i += NT) simg[i] = in_img[i];
       }
       cx.raw = simg;
     } else {
       if (in_vec) {
         cx.raw = in_img;
       } else {
-        for (int i = tid; i < img_bytes; i += nthreads) cx.scrA[i] = in_img[i];
+        for (int i = tid; i < img_bytes; i += NT) cx.scrA[i] = in_img[i];
         __threadfence();
         cx.raw = cx.scrA;
       }
     }
-    if (tid == 0) {
-      decode_image(p, ops, s, img, H, W);
-      s->next_img = (int)gridDim.x + (int)atomicAdd(p.work_counter, 1u);
-      s->n_sp = 0;
-      s->lut_identity = 1;
+    if (tid < 32) {
+      decode_image(p, s, img, H, W, tid);
+      if (tid == 0) {
+        s->next_img = (int)gridDim.x + (int)atomicAdd(p.work_counter, 1u);
+        s->n_sp = 0;
+        s->lut_identity = 1;
+      }
+    } else {
+      for (int t = tid - 32; t < C * 256; t += NT - 32) s->lut[t >> 8][t & 255] = (uint8_t)(t & 255);
     }
-    for (int t = tid; t < C * 256; t += nthreads) s->lut[t >> 8][t & 255] = (uint8_t)(t & 255);
     cx.tab_valid = false;
     __syncthreads();
 
@@ -829,22 +1157,21 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(const KParams p) {
 
     // 2. interpret the chain (uniform across the CTA).
     for (int pi = 0; pi < n_prog; ++pi) {
-      const ProgEntry pe = s->prog[pi];
-      const DevOp& op = ops[pe.op];
+      const ProgEntry& pe = s->prog[pi];
+      const DevOp& op = pe.op;
       const bool last = (pi == n_prog - 1);
       const int kind = op.kind;
       switch (kind) {
         case CHB_OP_INVERT: case CHB_OP_POSTERIZE: case CHB_OP_SOLARIZE: case CHB_OP_SOLARIZE_ADD:
         case CHB_OP_BRIGHTNESS: case CHB_OP_CONTRAST: {
-          for (int t = tid; t < C * 256; t += nthreads)
+          for (int t = tid; t < C * 256; t += NT)
             s->lut[t >> 8][t & 255] = (uint8_t)pointwise_value(op, s->lut[t >> 8][t & 255]);
-          for (int t = tid; t < s->n_sp * C; t += nthreads) {
+          for (int t = tid; t < s->n_sp * C; t += NT) {
             const int k = t / C, c = t - k * C;
             s->sp[k].color[c] = pointwise_value(op, s->sp[k].color[c]);
           }
-          cx.tab_valid = false;
-          __syncthreads();
           if (tid == 0) s->lut_identity = 0;
+          cx.tab_valid = false;
           __syncthreads();
         } break;
         case CHB_OP_COLOR: {
@@ -856,7 +1183,7 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(const KParams p) {
           if (!SMEM) { __threadfence(); cx.raw = dst; }
           __syncthreads();
           // the LUT is now baked in; spatial colours are pixels too.
-          for (int t = tid; t < C * 256; t += nthreads) s->lut[t >> 8][t & 255] = (uint8_t)(t & 255);
+          for (int t = tid; t < C * 256; t += NT) s->lut[t >> 8][t & 255] = (uint8_t)(t & 255);
           if (tid < s->n_sp) {
             int* col = s->sp[tid].color;
             color_pixel(col[0], col[1], col[2], op.factor, op.blend_mode);
@@ -868,9 +1195,6 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(const KParams p) {
         case CHB_OP_AUTOCONTRAST: case CHB_OP_EQUALIZE: {
           ensure_loaded();
           cx.stat_op(kind, s->lut_identity != 0);
-          if (tid == 0) s->lut_identity = 0;
-          cx.tab_valid = false;
-          __syncthreads();
         } break;
         case CHB_OP_CUTOUT: {
           const int h = op.ip0;
@@ -886,7 +1210,7 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(const KParams p) {
             }
             const int rw = (x1 - x0) * C, rh = y1 - y0;
             if (rw > 0 && rh > 0)
-              for (int i = tid; i < rw * rh; i += nthreads) {
+              for (int i = tid; i < rw * rh; i += NT) {
                 const int ry = i / rw, rb = i - ry * rw;
                 simg[((y0 + ry) * W + x0) * C + rb] = (uint8_t)op.ip1;
               }
@@ -949,7 +1273,7 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(const KParams p) {
     if (!emitted) {
       ensure_loaded();
       const bool identity = s->lut_identity != 0;
-      if (s->n_sp > 0) cx.pull_pass(out_img, identity); else cx.map_pass(out_img, identity);
+      if (s->n_sp > 0) cx.pull_pass(out_img, identity, false); else cx.map_pass(out_img, identity);
     }
     __syncthreads();
     img = s->next_img;
@@ -958,6 +1282,7 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(const KParams p) {
 
   // last CTA out re-arms the work counter for the next launch.
   if (tid == 0) {
+    bulk_wait_read<0>();  // staging buffers must outlive the stores that read them
     __threadfence();
     const unsigned int done = atomicAdd(p.work_counter + 1, 1u);
     if (done == gridDim.x - 1) {
@@ -971,9 +1296,9 @@ __global__ void __launch_bounds__(1024, 1) policy_kernel(const KParams p) {
 template <int C>
 cudaError_t launch_c(const KParams& p, const LaunchInfo& li, cudaStream_t stream) {
   if (li.image_in_smem)
-    policy_kernel<C, true><<<li.grid, li.block, li.smem, stream>>>(p);
+    policy_kernel<C, true><<<li.grid, NT, li.smem, stream>>>(p);
   else
-    policy_kernel<C, false><<<li.grid, li.block, li.smem, stream>>>(p);
+    policy_kernel<C, false><<<li.grid, NT, li.smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -993,6 +1318,6 @@ cudaError_t configure_c(size_t smem_optin) {
     return launch_c<C>(p, li, stream);                                                               \
   }                                                                                                  \
   cudaError_t configure_c##C(size_t smem_optin) { return configure_c<C>(smem_optin); }               \
-  size_t smem_overhead_c##C() { return big_region_bytes(C) + align_up(sizeof(Small), 128) + 128; }
+  size_t smem_overhead_c##C() { return smem_overhead_bytes(C); }
 
 }  // namespace chb

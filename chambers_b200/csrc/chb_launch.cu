@@ -25,7 +25,7 @@ LaunchInfo plan_launch(int B, int H, int W, int C, int num_sms, size_t smem_opti
   const size_t over = smem_overhead(C);
   li.image_in_smem = img_pad + over <= smem_optin;
   li.smem = li.image_in_smem ? img_pad + over : over;
-  li.block = 1024;
+  li.block = 512;  // NT in chb_kernels.cuh (up to 128 registers per thread)
   // persistent CTAs, one per SM (the shared-memory carve-out allows no more), never more than images
   li.grid = B < num_sms ? B : num_sms;
   if (li.grid < 1) li.grid = 1;

@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "op_sweep.json"))
+    ap.add_argument("--only", default=None, help="run just this op (e.g. Rotate) -- for ncu captures")
     args = ap.parse_args()
     pk = peak()
     rows = []
@@ -80,6 +81,11 @@ def main():
     from oracle.policy import magnitude_kwargs  # parameters only (no pixels): same table as the layers use
     names = ["AutoContrast", "Equalize", "Invert", "Brightness", "Contrast", "Color", "Sharpness", "ShearX", "ShearY",
              "TranslateX", "TranslateY", "Posterize", "Solarize", "SolarizeAdd", "CutOut", "Rotate"]
+    if args.only:
+        layer = A.RandomChoice([getattr(A, args.only)(**magnitude_kwargs(args.only, 10))], 1)
+        ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), bufs, args.iters, warm=1)
+        report("op:" + args.only, B, 224, 224, ms)
+        return
     ident = A.RandomChoice([A.RandomChance(A.Invert(), 0.0)], 1)
     ms = time_layer(lambda i, x, y: ident(x, seed=0, call_counter=i, out=y), bufs, args.iters)
     report("identity(copy)", B, 224, 224, ms)
