@@ -89,7 +89,8 @@ SIGNATURES = {
                           _vp, _vp, _vp]),
     "chb_policy_apply_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChbPolicy), _i64, _i64,
                                    _u64, _u32, _vp, _vp]),
-    "chb_smem_image_limit": (_i64, [_vp, _i]),
+    "chb_set_debug": (_i, [_vp, _i]),
+    "chb_tile_plan": (_i, [_i, _i] + [ctypes.POINTER(_i)] * 4),
 }
 
 
@@ -140,5 +141,13 @@ def kernel_launches(device):
     return int(load().chb_kernel_launches(context(device)))
 
 
-def smem_image_limit(device, channels=3):
-    return int(load().chb_smem_image_limit(context(device), int(channels)))
+def tile_plan(H, W):
+    """(tiles_x, tiles_y, tile_width, tile_height) of an H x W image (pure function of the shape)."""
+    out = [_i() for _ in range(4)]
+    load().chb_tile_plan(int(H), int(W), *[ctypes.byref(o) for o in out])
+    return tuple(o.value for o in out)
+
+
+def set_debug(device, force_generic):
+    """Route every tile through the scalar executor (tests cross-check it against the fast ones)."""
+    check(context(device), load().chb_set_debug(context(device), 1 if force_generic else 0))

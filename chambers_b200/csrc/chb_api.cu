@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -19,11 +20,24 @@ using chb::DevOp;
 struct PolicyEntry {
   std::vector<DevOp> host;
   DevOp* dev = nullptr;
-  bool uploaded = false;
+  uint8_t* optab = nullptr;  // [n][256] value maps of the point-wise ops (built on device)
+};
+
+// Per-stream working memory: calls on one stream are ordered, calls on different streams are not.
+struct Workspace {
+  cudaStream_t stream = nullptr;
+  chb::ImgState* states = nullptr;
+  int* lists = nullptr;
+  unsigned int* counters = nullptr;
+  size_t cap_images = 0;
+  int cap_levels = 0;
+  uint8_t* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  uint8_t* inplace = nullptr;
+  size_t inplace_bytes = 0;
 };
 
 static const int kPipe = 3;         // e2e pipeline depth (streams / staging buffers)
-static const int kCounterSlots = 256;
 
 struct chb_ctx {
   int device = 0;
@@ -31,9 +45,8 @@ struct chb_ctx {
   size_t smem_optin = 0;
   std::string err;
   int64_t launches = 0;
-  unsigned int* d_counters = nullptr;  // kCounterSlots x {next, done}
-  uint8_t* d_scratch = nullptr;
-  size_t scratch_bytes = 0;
+  int force_generic = 0;  // CHB_FORCE_GENERIC=1: every tile through the scalar executor (debugging)
+  std::vector<Workspace*> workspaces;
   std::vector<PolicyEntry*> cache;
   // e2e pipeline
   cudaStream_t streams[kPipe] = {nullptr, nullptr, nullptr};
@@ -314,11 +327,10 @@ extern "C" int chb_init(int device, chb_ctx** out) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
-  e = chb::configure_kernels(ctx->smem_optin);
+  e = chb::configure_kernels();
   if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "configure_kernels"); delete ctx; return r; }
-  e = cudaMalloc(&ctx->d_counters, kCounterSlots * 2 * sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(ctx->d_counters, 0, kCounterSlots * 2 * sizeof(unsigned int));
-  if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "counter alloc"); delete ctx; return r; }
+  const char* fg = getenv("CHB_FORCE_GENERIC");
+  ctx->force_generic = (fg && fg[0] && fg[0] != '0') ? 1 : 0;
   *out = ctx;
   return CHB_OK;
 }
@@ -327,9 +339,11 @@ extern "C" void chb_destroy(chb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  for (PolicyEntry* pe : ctx->cache) { cudaFree(pe->dev); delete pe; }
-  cudaFree(ctx->d_counters);
-  cudaFree(ctx->d_scratch);
+  for (PolicyEntry* pe : ctx->cache) { cudaFree(pe->dev); cudaFree(pe->optab); delete pe; }
+  for (Workspace* ws : ctx->workspaces) {
+    cudaFree(ws->states); cudaFree(ws->lists); cudaFree(ws->counters); cudaFree(ws->scratch); cudaFree(ws->inplace);
+    delete ws;
+  }
   for (int i = 0; i < kPipe; ++i) {
     if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
     cudaFree(ctx->st_in[i]); cudaFree(ctx->st_out[i]);
@@ -338,10 +352,19 @@ extern "C" void chb_destroy(chb_ctx* ctx) {
   delete ctx;
 }
 
-extern "C" int64_t chb_smem_image_limit(const chb_ctx* ctx, int C) {
-  if (!ctx || C < 1 || C > 4) return 0;
-  const int64_t lim = (int64_t)ctx->smem_optin - (int64_t)chb::smem_overhead(C);
-  return lim > 0 ? (lim / 128) * 128 : 0;
+extern "C" int chb_set_debug(chb_ctx* ctx, int force_generic) {
+  if (!ctx) return CHB_ERR_INVALID;
+  ctx->force_generic = force_generic ? 1 : 0;
+  return CHB_OK;
+}
+
+extern "C" int chb_tile_plan(int H, int W, int* tiles_x, int* tiles_y, int* tw, int* th) {
+  const chb::TilePlan t = chb::plan_tiles(H, W);
+  if (tiles_x) *tiles_x = t.tiles_x;
+  if (tiles_y) *tiles_y = t.tiles_y;
+  if (tw) *tw = t.tw;
+  if (th) *th = t.th;
+  return t.n_tiles;
 }
 
 // ------------------------------------------------------------------------------------- launch
@@ -386,7 +409,7 @@ static int get_policy(chb_ctx* ctx, const chb_policy* pol, int K, int H, int W, 
   if (!hit) {
     if (ctx->cache.size() >= 64) {  // bounded cache: drop everything once nothing can be in flight
       CHB_CUDA(ctx, cudaDeviceSynchronize());
-      for (PolicyEntry* pe : ctx->cache) { cudaFree(pe->dev); delete pe; }
+      for (PolicyEntry* pe : ctx->cache) { cudaFree(pe->dev); cudaFree(pe->optab); delete pe; }
       ctx->cache.clear();
     }
     hit = new PolicyEntry();
@@ -394,24 +417,61 @@ static int get_policy(chb_ctx* ctx, const chb_policy* pol, int K, int H, int W, 
     cudaError_t e = cudaMalloc(&hit->dev, host.size() * sizeof(DevOp));
     if (e != cudaSuccess) { delete hit; return cuda_fail(ctx, e, "policy table alloc"); }
     // pageable source: the runtime stages the bytes before returning, so `host` may go away.
+    e = cudaMalloc(&hit->optab, host.size() * 256);
+    if (e != cudaSuccess) { cudaFree(hit->dev); delete hit; return cuda_fail(ctx, e, "policy value-map alloc"); }
     e = cudaMemcpyAsync(hit->dev, hit->host.data(), host.size() * sizeof(DevOp), cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) { cudaFree(hit->dev); delete hit; return cuda_fail(ctx, e, "policy table upload"); }
+    if (e == cudaSuccess) {
+      e = chb::launch_optab(hit->dev, hit->optab, (int)host.size(), stream);
+      ctx->launches += 1;
+    }
     // other streams may use this entry later: make the upload visible to them too.
-    e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) { cudaFree(hit->dev); delete hit; return cuda_fail(ctx, e, "policy table upload sync"); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { cudaFree(hit->dev); cudaFree(hit->optab); delete hit; return cuda_fail(ctx, e, "policy table upload"); }
     ctx->cache.push_back(hit);
   }
   *out = hit;
   return CHB_OK;
 }
 
-static int ensure_scratch(chb_ctx* ctx, size_t bytes) {
-  if (bytes <= ctx->scratch_bytes) return CHB_OK;
-  if (ctx->d_scratch) CHB_CUDA(ctx, cudaFree(ctx->d_scratch));  // cudaFree synchronises the device
-  ctx->d_scratch = nullptr;
-  ctx->scratch_bytes = 0;
-  CHB_CUDA(ctx, cudaMalloc(&ctx->d_scratch, bytes));
-  ctx->scratch_bytes = bytes;
+static int grow(chb_ctx* ctx, void** ptr, size_t* have, size_t want) {
+  if (want <= *have) return CHB_OK;
+  if (*ptr) CHB_CUDA(ctx, cudaFree(*ptr));  // cudaFree synchronises the device
+  *ptr = nullptr;
+  *have = 0;
+  CHB_CUDA(ctx, cudaMalloc(ptr, want));
+  *have = want;
+  return CHB_OK;
+}
+
+static int get_workspace(chb_ctx* ctx, cudaStream_t stream, int B, int max_levels, size_t scratch_bytes,
+                         size_t inplace_bytes, Workspace** out) {
+  Workspace* ws = nullptr;
+  for (Workspace* w : ctx->workspaces)
+    if (w->stream == stream) ws = w;
+  if (!ws) {
+    ws = new Workspace();
+    ws->stream = stream;
+    ctx->workspaces.push_back(ws);
+  }
+  if ((size_t)B > ws->cap_images || max_levels > ws->cap_levels) {
+    const size_t nb = (size_t)B > ws->cap_images ? (size_t)B : ws->cap_images;
+    const int nl = max_levels > ws->cap_levels ? max_levels : ws->cap_levels;
+    if (ws->states) CHB_CUDA(ctx, cudaFree(ws->states));
+    if (ws->lists) CHB_CUDA(ctx, cudaFree(ws->lists));
+    if (ws->counters) CHB_CUDA(ctx, cudaFree(ws->counters));
+    ws->states = nullptr; ws->lists = nullptr; ws->counters = nullptr;
+    ws->cap_images = 0; ws->cap_levels = 0;
+    CHB_CUDA(ctx, cudaMalloc(&ws->states, nb * sizeof(chb::ImgState)));
+    CHB_CUDA(ctx, cudaMalloc(&ws->lists, nb * nl * sizeof(int)));
+    CHB_CUDA(ctx, cudaMalloc(&ws->counters, 2 * (size_t)nl * sizeof(unsigned int)));
+    ws->cap_images = nb;
+    ws->cap_levels = nl;
+  }
+  int r = grow(ctx, (void**)&ws->scratch, &ws->scratch_bytes, scratch_bytes);
+  if (r != CHB_OK) return r;
+  r = grow(ctx, (void**)&ws->inplace, &ws->inplace_bytes, inplace_bytes);
+  if (r != CHB_OK) return r;
+  *out = ws;
   return CHB_OK;
 }
 
@@ -426,32 +486,52 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   int r = validate_policy(ctx, pol, K);
   if (r != CHB_OK) return r;
   if ((long long)H * W * C > 0x3FFFFFFFll) return fail(ctx, CHB_ERR_UNSUPPORTED, "image larger than 1 GiB");
-  if ((long long)H * W > 32ll * 65535) return fail(ctx, CHB_ERR_UNSUPPORTED, "image larger than 2M pixels (16-bit histogram replicas)");
+  if (H >= (1 << 22) || W >= (1 << 22)) return fail(ctx, CHB_ERR_UNSUPPORTED, "image side of 4M pixels or more");
   CHB_CUDA(ctx, cudaSetDevice(ctx->device));
   PolicyEntry* pe = nullptr;
   r = get_policy(ctx, pol, K, H, W, C, batch_total, stream, &pe);  // validates ops even when B == 0
   if (r != CHB_OK) return r;
   if (B == 0 || H == 0 || W == 0) return CHB_OK;
   if (!d_in || !d_out) return fail(ctx, CHB_ERR_INVALID, "NULL image pointer");
-  const chb::LaunchInfo li = chb::plan_launch(B, H, W, C, ctx->num_sms, ctx->smem_optin);
-  if (!li.image_in_smem && d_in == d_out)
-    return fail(ctx, CHB_ERR_INVALID, "in-place call needs an image that fits in shared memory");
-  const size_t stride = ((size_t)H * W * C + 255) / 256 * 256;
-  r = ensure_scratch(ctx, (size_t)ctx->num_sms * 2 * stride);
+  const size_t img_bytes = (size_t)H * W * C;
+  const chb::TilePlan tp = chb::plan_tiles(H, W);
+  if ((unsigned long long)B * (unsigned long long)tp.n_tiles >= 0xFFFF0000ull)
+    return fail(ctx, CHB_ERR_UNSUPPORTED, "batch * tiles exceeds the 32-bit work counter");
+  const int chain = pol->n_draws * K;
+  const int max_levels = chain + 1;  // every op adds at most one pass before the final write
+  // tiles read neighbours of their own region: an in-place call goes through a temporary.
+  const bool overlap = (d_in < d_out + (size_t)B * img_bytes) && (d_out < d_in + (size_t)B * img_bytes);
+  const size_t stride = (img_bytes + 255) / 256 * 256;
+  Workspace* ws = nullptr;
+  r = get_workspace(ctx, stream, B, max_levels, chain >= 2 ? (size_t)B * 2 * stride : 0,
+                    overlap ? (size_t)B * img_bytes : 0, &ws);
   if (r != CHB_OK) return r;
 
   chb::KParams p;
   memset(&p, 0, sizeof(p));
-  p.in = d_in; p.out = d_out; p.B = B; p.H = H; p.W = W;
-  p.ops = pe->dev; p.T = pol->n_table; p.n_draws = pol->n_draws; p.K = K;
+  p.in = d_in; p.out = overlap ? ws->inplace : d_out; p.B = B; p.H = H; p.W = W;
+  p.ops = pe->dev; p.optab = pe->optab; p.T = pol->n_table; p.n_draws = pol->n_draws; p.K = K;
   p.elementwise = pol->elementwise ? 1 : 0;
   p.seed = seed; p.call_counter = call_counter; p.image_index_base = (unsigned long long)image_index_base;
   p.replay = d_replay; p.record = d_record;
-  p.scratch = ctx->d_scratch; p.scratch_stride = stride;
-  p.work_counter = ctx->d_counters + 2 * (size_t)(ctx->launches % kCounterSlots);
-  cudaError_t e = chb::launch_policy(p, C, li, stream);
-  if (e != cudaSuccess) return cuda_fail(ctx, e, "policy kernel launch");
+  p.scratch = ws->scratch; p.scratch_stride = stride;
+  p.states = ws->states; p.lists = ws->lists; p.counters = ws->counters;
+  p.max_levels = max_levels;
+  p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y; p.tw = tp.tw; p.th = tp.th; p.n_tiles = tp.n_tiles;
+  p.force_generic = ctx->force_generic;
+  cudaError_t e = chb::launch_plan(p, C, stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "plan kernel launch");
   ctx->launches += 1;
+  const long long slots = (long long)ctx->num_sms * chb::pass_ctas_per_sm(C);
+  for (int level = 0; level < max_levels; ++level) {
+    p.level = level;
+    long long grid = slots;
+    if (level == 0 && (long long)B * tp.n_tiles < grid) grid = (long long)B * tp.n_tiles;
+    e = chb::launch_pass(p, C, (int)grid, stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "pass kernel launch");
+    ctx->launches += 1;
+  }
+  if (overlap) CHB_CUDA(ctx, cudaMemcpyAsync(d_out, ws->inplace, (size_t)B * img_bytes, cudaMemcpyDeviceToDevice, stream));
   return CHB_OK;
 }
 

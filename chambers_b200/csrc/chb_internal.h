@@ -1,4 +1,4 @@
-// Internal (non-ABI) declarations shared by chb_api.cu (host) and chb_kernels.cu (device).
+// Internal (non-ABI) declarations shared by chb_api.cu (host) and the kernel translation units.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,35 +27,85 @@ static_assert(sizeof(DevOp) == 112, "DevOp layout");
 
 enum { BLEND_IMAGE2 = 0, BLEND_IMAGE1 = 1, BLEND_INTERP = 2, BLEND_EXTRAP = 3 };
 
+constexpr int MAXC = 4;
+
+// ---- per-image pass state (global memory; written by the plan kernel and by pass finalisers) ----
+// The chain of one image is evaluated lazily.  Between passes the "virtual image" is
+//     src bytes -> spatial list (nearest warps / CutOut masks, each carrying the final colour it
+//     contributes) -> LUT l1 -> optional kernel K (Color | Sharpness | bilinear warp) -> LUT l2
+// and every op only edits that state; a pass over the pixels happens only when an op needs the
+// pixels themselves (a histogram, or a materialised neighbourhood).
+enum { PASS_WRITE_OUT = 0, PASS_COUNT = 1, PASS_WRITE_SCRATCH = 2 };
+enum { K_NONE = 0, K_COLOR = 1, K_SHARP = 2, K_BILINEAR = 3 };
+enum { SP_GEOM = 0, SP_MASK = 1 };
+
+struct Spatial {  // 72 bytes
+  int32_t type, fill_mode;
+  float t[8];
+  int32_t y0, y1, x0, x1;
+  int32_t color[MAXC];
+};
+
+struct alignas(16) TileState {  // what a tile needs; loaded whole by every tile CTA
+  int32_t pass_kind, src_sel, dst_sel, n_sp;
+  int32_t kmode, l1_id, l2_id, sp_fast;  // sp_fast: every entry is constant-fill (bbox staging is valid)
+  float kfactor;
+  int32_t _pad[3];
+  Spatial sp[CHB_MAX_CHAIN];
+  Spatial kgeo;  // K_BILINEAR: the warp (t, fill_mode, color[0] = fill)
+  uint8_t l1[MAXC][256];
+  uint8_t l2[MAXC][256];
+  int32_t _pad2[2];
+};
+static_assert(sizeof(TileState) % 16 == 0, "TileState must be a whole number of 16-byte units");
+
+struct ProgRec {
+  int32_t table_index, negate, cy, cx;
+};
+
+struct alignas(16) ImgState {
+  TileState t;
+  // finaliser-only part
+  int32_t next_op, n_prog, hist_valid, _pad0;
+  ProgRec prog[CHB_MAX_CHAIN];
+  uint32_t tiles_done, _pad1[3];
+  uint32_t color_cnt[CHB_MAX_CHAIN];  // COUNT passes: pixels that resolved to spatial entry k
+  uint32_t hist[MAXC][256];           // COUNT passes: values entering the last LUT
+};
+static_assert(sizeof(ImgState) % 16 == 0, "ImgState must be a whole number of 16-byte units");
+
 struct KParams {
   const uint8_t* in;
   uint8_t* out;
   int B, H, W;
-  const DevOp* ops;  // [T][K]
+  const DevOp* ops;      // [T][K]
+  const uint8_t* optab;  // [T*K][256]: the value map of every point-wise table op
   int T, n_draws, K, elementwise;
   unsigned long long seed;
   unsigned int call_counter;
   unsigned long long image_index_base;
   const int32_t* replay;
   int32_t* record;
-  uint8_t* scratch;               // gridDim.x * 2 * scratch_stride bytes
+  uint8_t* scratch;                   // image i, buffer s in {1, 2}: scratch + (2 i + s - 1) * stride
   unsigned long long scratch_stride;
-  unsigned int* work_counter;     // dynamic image scheduler (zeroed before launch)
+  ImgState* states;                   // [B]
+  int* lists;                         // [max_levels][B]: images that have a pass at that level
+  unsigned int* counters;             // [0, max_levels): list lengths; [max_levels, 2 max_levels): work counters
+  int level, max_levels;
+  int tiles_x, tiles_y, tw, th, n_tiles;
+  int force_generic;                  // debugging: route every tile through the scalar executor
 };
 
-struct LaunchInfo {
-  int grid, block;
-  size_t smem;
-  bool image_in_smem;
+struct TilePlan {
+  int tiles_x, tiles_y, tw, th, n_tiles;
 };
+TilePlan plan_tiles(int H, int W);
 
-// Decides grid / block / smem for a (H, W, C) image on this device.
-LaunchInfo plan_launch(int B, int H, int W, int C, int num_sms, size_t smem_optin);
-// Launches the fused policy kernel.  Returns cudaGetLastError().
-cudaError_t launch_policy(const KParams& p, int C, const LaunchInfo& li, cudaStream_t stream);
-// Opt in to the large dynamic shared memory carve-out for every kernel instantiation.
-cudaError_t configure_kernels(size_t smem_optin);
-// Shared-memory bytes the kernel needs besides the image itself.
-size_t smem_overhead(int C);
+// Launchers (chb_kernels_c<N>.cu / chb_launch.cu).  Each returns cudaGetLastError().
+cudaError_t launch_optab(const DevOp* ops, uint8_t* optab, int n_ops, cudaStream_t stream);
+cudaError_t launch_plan(const KParams& p, int C, cudaStream_t stream);
+cudaError_t launch_pass(const KParams& p, int C, int grid, cudaStream_t stream);
+cudaError_t configure_kernels();
+int pass_ctas_per_sm(int C);
 
 }  // namespace chb

@@ -1,4 +1,4 @@
-// policy_kernel<3, *> instantiations (see chb_kernels.cuh).
+// pass_kernel<3> instantiation (see chb_kernels.cuh).
 #include "chb_kernels.cuh"
 namespace chb {
 CHB_DEFINE_CHANNEL_ENTRY(3)

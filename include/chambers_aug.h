@@ -15,6 +15,8 @@
  *     Nothing throws across the ABI.  Device calls are stream-ordered and never synchronise.
  *   - one chb_ctx per (host thread, device); a ctx is not re-entrant.
  *   - there is NO CPU fallback: without a CUDA device chb_init fails.
+ *   - working memory (per-image pass state, scratch images) is owned by the ctx, keyed by stream and
+ *     grown on demand; a call that grows it synchronises the device once.
  */
 #ifndef CHAMBERS_AUG_H_
 #define CHAMBERS_AUG_H_
@@ -129,7 +131,8 @@ int chb_autoaugment_table(chb_transform* out25);
  *   seed, call_counter  Philox4x32-10 key / call index (see oracle/philox.py for the layout).
  *   d_replay          NULL, or device int32 [B][n_draws][K][5] schedule to use instead of the RNG.
  *   d_record          NULL, or device int32 buffer of the same shape receiving the schedule used.
- * d_in may equal d_out only when one image fits in shared memory (H*W*C <= chb_smem_image_limit). */
+ * d_in may equal d_out (or overlap it): tiles read neighbours of their own region, so such a call
+ * is routed through a library-owned temporary and one extra device-to-device copy. */
 int chb_policy_apply(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int B, int H, int W, int C,
                      const chb_policy* policy, int64_t batch_total, int64_t image_index_base,
                      uint64_t seed, uint32_t call_counter, const int32_t* d_replay,
@@ -162,10 +165,14 @@ int chb_policy_apply_host(chb_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, int
                           int64_t image_index_base, uint64_t seed, uint32_t call_counter,
                           const int32_t* h_replay, int32_t* h_record);
 
-/* Largest H*W*C (bytes) for which one image is staged whole in one CTA's shared memory (the
- * one-HBM-read-one-HBM-write path) for a C-channel image; larger images run from global memory
- * through L2. */
-int64_t chb_smem_image_limit(const chb_ctx* ctx, int C);
+/* Debugging switch: force_generic != 0 routes every tile through the scalar executor instead of
+ * the vectorised ones (same results, used by the tests to cross-check the two on the device). */
+int chb_set_debug(chb_ctx* ctx, int force_generic);
+
+/* How an H x W image is cut into work items: tiles_x * tiles_y tiles of at most tw x th pixels
+ * (the same count cuts the image into flat runs / row strips for passes without a spatial op).
+ * Pure function of the shape; any of the out pointers may be NULL.  Returns the tile count. */
+int chb_tile_plan(int H, int W, int* tiles_x, int* tiles_y, int* tw, int* th);
 
 #ifdef __cplusplus
 }

@@ -167,10 +167,11 @@ def test_autoaugment_every_subpolicy(A, c1_batch):
 
 
 @pytest.mark.parametrize("shape", [(6, 256, 256, 3), (3, 512, 512, 3), (4, 301, 299, 3)])
-def test_large_images_global_path(A, shape):
-    """Images that do not fit in shared memory run from global memory (config 4's 512x512)."""
+def test_large_images_many_tiles(A, shape):
+    """Images cut into many tiles, aligned (config 4's 512x512) and ragged (301x299: scalar executor)."""
     from chambers_b200 import _lib
-    assert shape[1] * shape[2] * 3 > _lib.smem_image_limit(torch.cuda.current_device(), 3)
+    tx, ty, _, _ = _lib.tile_plan(shape[1], shape[2])
+    assert tx * ty >= 16
     x = random_images(*shape, seed=9, kind="smooth")
     layer = A.RandAugment(3, 15, elementwise=True)
     for call in range(3):
@@ -284,3 +285,35 @@ def test_full_size_batches_sampled_against_oracle(A):
     cut = A.CutOut(80, 128)(big, seed=2, call_counter=0)
     changed = (cut != big).any(dim=3).sum(dim=(1, 2))
     assert int(changed.max()) <= 80 * 80 and int(((cut != big) & (cut != 128)).sum()) == 0
+
+
+@pytest.mark.parametrize("shape", [(224, 224), (512, 512), (96, 160)])
+def test_fast_executors_match_scalar_executor(A, shape):
+    """Every ordered op pair at the BASELINE image sizes: the vectorised tile executors (flat /
+    gather / sharpness) against the scalar executor of the same library, bit for bit, plus a sample
+    of the pairs against the oracle."""
+    from chambers_b200 import _lib
+    H, W = shape
+    s, rng = _replay_all_pairs()
+    s[..., 3] = rng.integers(0, H, size=s.shape[:3])
+    s[..., 4] = rng.integers(0, W, size=s.shape[:3])
+    g = torch.Generator().manual_seed(H)
+    x = torch.randint(0, 256, (256, H, W, 3), dtype=torch.uint8, generator=g)
+    xg = x.cuda()
+    dev = torch.cuda.current_device()
+    for magnitude in (10, 15):
+        layer = A.RandAugment(2, magnitude, elementwise=True)
+        fast = layer(xg, training=True, replay=s)
+        _lib.set_debug(dev, True)
+        try:
+            slow = layer(xg, training=True, replay=s)
+        finally:
+            _lib.set_debug(dev, False)
+        torch.cuda.synchronize()
+        same = (fast == slow).flatten(1).all(dim=1).cpu().numpy()
+        bad = [(oracle.OP_NAMES[s[b, 0, 0, 0]], oracle.OP_NAMES[s[b, 1, 0, 0]]) for b in np.nonzero(~same)[0]]
+        assert not bad, "fast != scalar executor for pairs %r" % (bad[:12],)
+        if H <= 224:
+            idx = list(range(3, 256, 37))
+            want = oracle.apply_schedule(x.numpy()[idx], policy_of(layer), s[idx], elementwise=True)
+            assert_same(fast[idx].cpu().numpy(), want, "oracle sample M=%d" % magnitude)

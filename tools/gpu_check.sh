@@ -1,8 +1,9 @@
 #!/bin/bash
-# One GPU visit: parity tests, headline bench, per-op sweep.  Usage: tools/gpu_check.sh [sweep-batch]
+# One GPU visit: parity tests, headline bench, per-op sweep.  Usage: tools/gpu_check.sh [sweep-batch] [pytest-args]
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 -p no:cacheprovider > gpurun_out/pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest.log)
-tail -12 gpurun_out/pytest.log
+nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/gpu.txt 2>&1
+(timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider ${2:-} > gpurun_out/pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest.log)
+grep -E "^(FAILED|ERROR)|passed|failed|exit" gpurun_out/pytest.log | cut -c1-300 | head -60
 (timeout 400 python bench.py --steps 200 --warmup 10 > gpurun_out/bench.log 2>&1; echo "bench exit $?" >> gpurun_out/bench.log)
 python - <<PY
 import json
