@@ -44,6 +44,53 @@ __device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
 __device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) {  // fire-and-forget shared atomic add
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+// ---- mbarrier + TMA (1-D bulk copies; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "CHB_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra CHB_DONE_%=;\n\t"
+      "bra CHB_WAIT_%=;\n\t"
+      "CHB_DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared, completion (bytes) signalled on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src_gmem), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-groups
+__device__ __forceinline__ void bulk_store(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {  // this thread's stores have finished reading shared memory
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all0() {  // this thread's stores are complete
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {  // generic-proxy smem writes -> visible to the async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// Barrier of the NCONS consumer threads of a pass CTA (the producer warp never joins it).
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 // Streaming global accesses: image bytes are touched once per pass, keep them out of L1.
 __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 

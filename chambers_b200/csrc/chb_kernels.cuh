@@ -5,7 +5,10 @@
 //                 replayed schedule) and folds the chain into a per-image pass state (ImgState).
 //   pass_kernel   persistent CTAs pull (image, tile) items of one *level* from an atomic counter.
 //                 A tile is ~10 KB of the image; level 0 is every image's first pass, level n the
-//                 n-th extra pass of the few images that need one.
+//                 n-th extra pass of the few images that need one.  Each CTA is a two-slot
+//                 producer / consumer pipeline: one warp claims items and drives the TMA loads
+//                 (cp.async.bulk + mbarrier), eight warps compute from shared memory and hand the
+//                 finished tile back to the TMA (bulk stores).
 //
 // The chain is evaluated lazily (chb_internal.h: ImgState).  Point-wise ops compose into 256-entry
 // LUTs, nearest-neighbour warps and CutOut go on a spatial list, Color / Sharpness / a bilinear warp
@@ -22,10 +25,9 @@
 // pair.
 //
 // Tile executors (all bit-exact twins of each other; the scalar one is the fallback for odd shapes):
-//   exec_flat     no spatial op: 48-byte (16-pixel) units, LDG.128 -> LUT/Color in registers -> STG.128
+//   exec_flat     no spatial op: 48-byte (16-pixel) units, LDS.128 -> LUT/Color in registers -> STS.128
 //   exec_gather   spatial list: the source bounding box of a 64 x 56 tile is staged in shared memory
-//                 with 16-byte loads, pixels are gathered from it, results leave through a staged
-//                 tile with 16-byte stores
+//                 (one TMA copy per row), pixels are gathered from it into the output tile
 //   exec_sharp    Sharpness: row strip + halo staged in shared memory, sliding 3x3 window per word column
 //   exec_generic  anything, one pixel per thread straight from global memory
 #pragma once
@@ -34,17 +36,20 @@
 namespace chb {
 namespace {
 
-constexpr int NT = 256;        // threads per pass CTA
-constexpr int PLAN_NT = 128;   // threads per plan CTA
-constexpr int PASS_MIN_CTAS = 4;
-constexpr int BIG_BYTES = 48 * 1024;             // staging / histogram region of a pass CTA
+constexpr int NCONS = 256;                       // consumer threads of a pass CTA (8 warps)
+constexpr int NT = NCONS + 32;                   // + one producer warp
+constexpr int PLAN_NT = 128;                     // threads per plan CTA
+constexpr int PASS_MIN_CTAS = 2;
+constexpr int DATA_BYTES = 32 * 1024;            // staged source bytes of one pipeline slot
+constexpr int OSTAGE_BYTES = 16 * 1024 + 256;    // one output staging tile (64 x 64 x 4 bytes + one unit)
+constexpr int R_BYTES = 2 * OSTAGE_BYTES;        // two output tiles | lane-private histograms | finaliser scratch
 constexpr int LHIST_CH_BYTES = 64 * 32 * 4;      // lane-private u8x4 histogram of one channel
-constexpr int CTL_BYTES = 16;
-constexpr size_t PASS_SMEM = sizeof(ImgState) + CTL_BYTES + BIG_BYTES;
 constexpr int STATE_VECS = (int)(offsetof(ImgState, hist) / 16);   // everything but the histogram
 constexpr int TILE_VECS = (int)(sizeof(TileState) / 16);
 static_assert(offsetof(ImgState, hist) % 16 == 0, "hist must start on a 16-byte boundary");
 static_assert(offsetof(ImgState, next_op) == sizeof(TileState), "finaliser part follows the tile part");
+static_assert(MAXC * LHIST_CH_BYTES <= R_BYTES, "lane-private histograms must fit the R region");
+static_assert(sizeof(ImgState) + MAXC * 256 * 5 <= R_BYTES, "finaliser scratch must fit the R region");
 
 struct Rect {
   int x0, x1, y0, y1;
@@ -150,11 +155,12 @@ __device__ __forceinline__ void reset_view(ImgState* s, int tid, int nt) {  // a
 // CTA-cooperative chain walk.  *s lives in shared memory; starting at s->next_op every op is folded
 // into the view until one needs the pixels.  On return s->t.pass_kind names the pass to run now; the
 // walk resumes at the same op once that pass has finished.  hmap: MAXC*256 words, etab: MAXC*256
-// bytes of shared scratch.  Needs nt >= 32 * C.
+// bytes of shared scratch.  Needs nt >= 32 * C; `sync` is the barrier of the nt participating threads.
+template <class Sync>
 __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H, int W, uint32_t* hmap,
-                        uint8_t* etab, int tid, int nt) {
+                        uint8_t* etab, int tid, int nt, Sync sync) {
   for (;;) {
-    __syncthreads();
+    sync();
     const int pi = s->next_op;
     const int n_prog = s->n_prog;
     const int kmode = s->t.kmode;
@@ -163,7 +169,7 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
     const int src_sel = s->t.src_sel;
     ProgRec pe = {0, 0, 0, 0};
     if (pi < n_prog) pe = s->prog[pi];
-    __syncthreads();
+    sync();
     if (pi >= n_prog) {
       if (tid == 0) s->t.pass_kind = PASS_WRITE_OUT;
       break;
@@ -196,7 +202,7 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
       }
       // s->hist counts the values entering the last LUT; map them through it, add the spatial colours.
       for (int t = tid; t < MAXC * 256; t += nt) hmap[t] = 0u;
-      __syncthreads();
+      sync();
       for (int t = tid; t < C * 256; t += nt) {
         const uint32_t cnt = s->hist[t >> 8][t & 255];
         if (cnt) atomicAdd(&hmap[(t & ~255) + last_lut[t >> 8][t & 255]], cnt);
@@ -207,9 +213,9 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
           const uint32_t cnt = s->color_cnt[k];
           if (cnt) atomicAdd(&hmap[c * 256 + s->t.sp[k].color[c]], cnt);
         }
-      __syncthreads();
+      sync();
       stat_tables(kind, C, hmap, etab, tid);
-      __syncthreads();
+      sync();
       for (int t = tid; t < C * 256; t += nt) last_lut[t >> 8][t & 255] = etab[(t & ~255) + last_lut[t >> 8][t & 255]];
       if (!frozen)
         for (int t = tid; t < n_sp * C; t += nt) {
@@ -301,7 +307,7 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
       break;
     }
   }
-  __syncthreads();
+  sync();
 }
 
 // Twin of oracle/philox.py decode_schedule for ONE image, executed by warp 0: every lane draws the
@@ -385,46 +391,104 @@ __global__ void __launch_bounds__(PLAN_NT) plan_kernel(const KParams p, int C) {
   if (tid < 32) decode_image(p, &s, rnd, rndc, img, p.H, p.W, tid);
   reset_view(&s, tid, PLAN_NT);
   __syncthreads();
-  advance(&s, p.states + img, p, C, p.H, p.W, hmap, etab, tid, PLAN_NT);
+  advance(&s, p.states + img, p, C, p.H, p.W, hmap, etab, tid, PLAN_NT, [] { __syncthreads(); });
   for (int i = tid; i < STATE_VECS; i += PLAN_NT)
     reinterpret_cast<uint4*>(p.states + img)[i] = reinterpret_cast<const uint4*>(&s)[i];
 }
 
 #endif  // CHB_WITH_PLAN
 
-// ================================================================================ tile context
+// ============================================================================== pipeline slots
+// A pass CTA is a two-slot producer / consumer pipeline.  The producer warp claims the next
+// (image, tile) item, pulls the image's TileState into the slot with a TMA bulk copy, decides how
+// the tile will be executed, and issues the TMA loads of the tile's source bytes (one bulk copy
+// for a flat run or a row strip, one per row for a gather bounding box); all of it completes on the
+// slot's `full` mbarrier.  The 8 consumer warps wait on `full`, compute from shared memory into an
+// output staging tile and hand that to the TMA again (bulk stores), then release the slot through
+// its `empty` mbarrier.  While the consumers work on one slot the loads of the other are in flight.
+enum { CLS_END = 0, CLS_FLAT = 1, CLS_GATHER = 2, CLS_SHARP = 3, CLS_GENERIC = 4, CLS_GATHER_SHARP = 5 };
+
+struct alignas(16) SlotInfo {  // written by the producer, read by the consumers
+  int32_t cls, img, tile, pass_kind;
+  int32_t bx0, bx1, by0, by1;        // GATHER: source bounding box (inclusive); SHARP: by0 = first staged row
+  int32_t bxb0, rowb, pitch, rows;   // GATHER: first staged byte of a row, staged bytes per row, pitch, rows
+  int32_t x0, x1, y0, y1;            // region of the tile (box or strip); FLAT: x0 / x1 = first / last unit
+  uint32_t fill;                     // GATHER: the colour bytes of spatial entry 0
+  int32_t paint;                     // FLAT: the spatial list is masks only; paint them over the result
+  int32_t _pad[2];
+};
+
+struct alignas(128) Slot {
+  SlotInfo info;
+  TileState st;
+  uint8_t _pad[128 - (sizeof(SlotInfo) + sizeof(TileState)) % 128];
+  uint8_t data[DATA_BYTES];
+};
+
+struct alignas(128) PassSmem {
+  unsigned long long full[2], empty[2], stbar;
+  int32_t ctl[6];
+  uint32_t color_cnt[CHB_MAX_CHAIN];
+  uint32_t hist[MAXC][256];  // tile-local counts of a COUNT pass
+  Slot slot[2];
+  uint8_t r[R_BYTES];        // two output staging tiles | lane-private histograms | finaliser scratch
+};
+
 template <int C>
 struct TC {
   const KParams* p;
-  ImgState* s;
-  uint32_t big;        // shared address of the staging region
+  PassSmem* sm;
+  const TileState* t;
+  const SlotInfo* info;
+  uint32_t data;       // shared address of the slot's staged source bytes
+  uint32_t ostage;     // shared address of this tile's output staging tile
+  uint32_t* nstore;    // stores issued so far by this CTA's consumers (staging tiles alternate per store)
+  uint32_t r;          // shared address of the R region
   const uint8_t* src;  // source image of this pass
   uint8_t* dst;        // destination image (unused by COUNT passes)
   int H, W, HW, img_bytes, tid, lane, tile;
   uint32_t l1a, l2a;   // shared addresses of the two LUTs
 };
 
-__device__ __forceinline__ void count_value(ImgState* s, int c, uint32_t v) { atomicAdd(&s->hist[c][v & 255u], 1u); }
+template <int C>
+__device__ __forceinline__ void count_value(const TC<C>& c, int ch, uint32_t v) { atomicAdd(&c.sm->hist[ch][v & 255u], 1u); }
+
+// Every consumer thread that issues bulk stores (warp 0) calls this before the barrier that
+// precedes its next store: the previous store has then finished reading its staging tile, and
+// since staging tiles alternate per store, the tile the next storing item writes is free once that
+// barrier is passed.
+__device__ __forceinline__ void stores_drained(int tid) {
+  if (tid < 32) bulk_wait_read0();
+}
+// The barrier in front of a store: drain, sync, flip the staging tile for the next storing item.
+template <int C>
+__device__ __forceinline__ void store_barrier(const TC<C>& c) {
+  fence_proxy_async();  // this thread's shared-memory writes -> visible to the TMA
+  stores_drained(c.tid);
+  cons_sync();
+  ++(*c.nstore);
+}
 
 // =========================================================================== scalar executor
 template <int C, bool COUNT>
-__device__ void exec_generic(const TC<C>& c, const Rect r) {
-  const TileState& t = c.s->t;
+__device__ void exec_generic(const TC<C>& c) {
+  const TileState& t = *c.t;
   const int H = c.H, W = c.W;
-  const int rw = r.x1 - r.x0;
-  const int n = rw * (r.y1 - r.y0);
+  const int rx0 = c.info->x0, ry0 = c.info->y0;
+  const int rw = c.info->x1 - rx0;
+  const int n = rw * (c.info->y1 - ry0);
   const int kmode = t.kmode;
   const float f = t.kfactor;
   const uint8_t* src = c.src;
-  for (int i = c.tid; i < n; i += NT) {
+  for (int i = c.tid; i < n; i += NCONS) {
     const int ry = i / rw;
-    const int y = r.y0 + ry, x = r.x0 + (i - ry * rw);
+    const int y = ry0 + ry, x = rx0 + (i - ry * rw);
     int v[C];
     if (kmode == K_NONE || kmode == K_COLOR) {
       int sx = x, sy = y;
       const int k = resolve(t.sp, t.n_sp, H, W, sx, sy);
       if (k >= 0) {
-        if (COUNT) { atomicAdd(&c.s->color_cnt[k], 1u); continue; }
+        if (COUNT) { atomicAdd(&c.sm->color_cnt[k], 1u); continue; }
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) v[ch] = t.sp[k].color[ch];
       } else {
@@ -449,7 +513,7 @@ __device__ void exec_generic(const TC<C>& c, const Rect r) {
         }
         if (COUNT) {
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) count_value(c.s, ch, (uint32_t)v[ch]);
+          for (int ch = 0; ch < C; ++ch) count_value(c, ch, (uint32_t)v[ch]);
           continue;
         }
       }
@@ -480,7 +544,7 @@ __device__ void exec_generic(const TC<C>& c, const Rect r) {
       }
       if (COUNT) {
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) count_value(c.s, ch, (uint32_t)v[ch]);
+        for (int ch = 0; ch < C; ++ch) count_value(c, ch, (uint32_t)v[ch]);
         continue;
       }
 #pragma unroll
@@ -516,7 +580,7 @@ __device__ void exec_generic(const TC<C>& c, const Rect r) {
       }
       if (COUNT) {
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) count_value(c.s, ch, (uint32_t)v[ch]);
+        for (int ch = 0; ch < C; ++ch) count_value(c, ch, (uint32_t)v[ch]);
         continue;
       }
 #pragma unroll
@@ -572,16 +636,16 @@ __device__ __forceinline__ void lhist_add(uint32_t ch_lane_base, uint32_t v) {
   reds_add(ch_lane_base + ((v & 0xFCu) << 5), 1u << ((v & 3u) << 3));
 }
 template <int C>
-__device__ __forceinline__ void lhist_zero(uint32_t big, int tid) {
-  for (int i = tid; i < C * LHIST_CH_BYTES / 16; i += NT) sts_v4(big + i * 16, make_uint4(0u, 0u, 0u, 0u));
+__device__ __forceinline__ void lhist_zero(uint32_t r, int tid) {
+  for (int i = tid; i < C * LHIST_CH_BYTES / 16; i += NCONS) sts_v4(r + i * 16, make_uint4(0u, 0u, 0u, 0u));
 }
-// Adds the lane-private counters into s->hist (shared u32 bins).
+// Adds the lane-private counters into sm->hist (shared u32 bins).
 template <int C>
-__device__ __forceinline__ void lhist_reduce(ImgState* s, uint32_t big, int tid) {
+__device__ __forceinline__ void lhist_reduce(PassSmem* sm, uint32_t r, int tid) {
   const int lane = tid & 31;
-  for (int t = tid; t < C * 64; t += NT) {
+  for (int t = tid; t < C * 64; t += NCONS) {
     const int ch = t >> 6, row = t & 63;
-    const uint32_t base = big + ch * LHIST_CH_BYTES + row * 128;
+    const uint32_t base = r + ch * LHIST_CH_BYTES + row * 128;
     uint32_t lo = 0, hi = 0;
 #pragma unroll 8
     for (int l = 0; l < 32; ++l) {
@@ -589,40 +653,43 @@ __device__ __forceinline__ void lhist_reduce(ImgState* s, uint32_t big, int tid)
       lo += w & 0x00FF00FFu;
       hi += (w >> 8) & 0x00FF00FFu;
     }
-    uint32_t* h = &s->hist[ch][row * 4];
+    uint32_t* h = &sm->hist[ch][row * 4];
     h[0] += lo & 0xFFFFu; h[1] += hi & 0xFFFFu; h[2] += lo >> 16; h[3] += hi >> 16;
   }
 }
 
 // =============================================================================== flat executor
 // No spatial op pending, K in {none, Color}: the tile is a contiguous run of units (48 bytes = 16
-// pixels for C == 3, else 16 bytes) whose channel phase is a compile-time constant.
+// pixels for C == 3, else 16 bytes) whose channel phase is a compile-time constant.  The run sits in
+// the slot (one TMA load); every thread takes one unit per round with LDS.128 (a quarter-warp's
+// 48-byte-strided vectors fall into distinct 16-byte bank groups), transforms it in registers and
+// writes it to the output staging tile, which leaves as one TMA store.
 template <int C, bool COUNT>
 __device__ void exec_flat(const TC<C>& c) {
   constexpr int UW = (C == 3) ? 12 : 4;
   constexpr int UB = UW * 4;
-  const TileState& t = c.s->t;
-  const int n_tiles = c.p->n_tiles;
-  const int n_units = c.img_bytes / UB;
-  const int upt = (n_units + n_tiles - 1) / n_tiles;
-  const int u0 = min(n_units, c.tile * upt), u1 = min(n_units, u0 + upt);
+  const TileState& t = *c.t;
+  const int u0 = c.info->x0, u1 = c.info->x1;
+  const int nloc = u1 - u0;
   const int kmode = t.kmode;
   const bool use1 = !t.l1_id, use2 = !t.l2_id;
   const float f = t.kfactor;
-  const uint32_t hl = c.big + (c.lane << 2);
-
-  for (int base = u0; base < u1; base += NT) {  // one unit per thread per round
+  const uint32_t hl = c.r + (c.lane << 2);
+  if (COUNT) {
+    stores_drained(c.tid);  // the R region may still be feeding a store of the previous item
+    cons_sync();
+  }
+  for (int base = 0; base < nloc; base += NCONS) {  // one unit per thread per round
     const int u = base + c.tid;
     if (COUNT) {
-      lhist_zero<C>(c.big, c.tid);
-      __syncthreads();
+      lhist_zero<C>(c.r, c.tid);
+      cons_sync();
     }
-    if (u < u1) {
+    if (u < nloc) {
       uint32_t w[UW];
-      const uint8_t* sp = c.src + (size_t)u * UB;
 #pragma unroll
       for (int q = 0; q < UW / 4; ++q) {
-        const uint4 v = ldg_stream(sp + q * 16);
+        const uint4 v = lds_v4(c.data + u * UB + q * 16);
         w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
       }
       if (kmode == K_NONE) {
@@ -650,23 +717,54 @@ __device__ void exec_flat(const TC<C>& c) {
 #pragma unroll
           for (int b = 0; b < 4; ++b) lhist_add(hl + ((4 * j + b) % C) * LHIST_CH_BYTES, byte_of(w[j], b));
       } else {
-        uint8_t* dp = c.dst + (size_t)u * UB;
 #pragma unroll
         for (int q = 0; q < UW / 4; ++q)
-          *reinterpret_cast<uint4*>(dp + q * 16) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          sts_v4(c.ostage + u * UB + q * 16, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
       }
     }
     if (COUNT) {
-      __syncthreads();
-      lhist_reduce<C>(c.s, c.big, c.tid);
-      __syncthreads();
+      cons_sync();
+      lhist_reduce<C>(c.sm, c.r, c.tid);
+      cons_sync();
+    }
+  }
+  if (!COUNT) {
+    // CutOut rectangles (the spatial list holds nothing else in this class), in list order
+    const int P0 = u0 * (UB / C), P1 = u1 * (UB / C);  // pixel range of this tile
+    for (int k = 0; k < c.info->paint; ++k) {
+      cons_sync();
+      const Spatial& e = t.sp[k];
+      const int rw = (e.x1 - e.x0) * C;
+      if (rw <= 0 || nloc <= 0) continue;
+      const int ylo = max(e.y0, P0 / c.W), yhi = min(e.y1, (P1 - 1) / c.W + 1);
+      const int n = (yhi - ylo) * rw;
+      for (int i = c.tid; i < n; i += NCONS) {
+        const int ry = i / rw, rb = i - ry * rw;
+        const int bidx = ((ylo + ry) * c.W + e.x0) * C + rb - P0 * C;  // byte index within the tile
+        if (bidx >= 0 && bidx < nloc * UB)
+          asm volatile("st.shared.u8 [%0], %1;" ::"r"(c.ostage + (uint32_t)bidx), "r"(e.color[rb % C]) : "memory");
+      }
+    }
+    store_barrier(c);
+    if (c.tid == 0 && nloc > 0) {
+      bulk_store(c.dst + (size_t)u0 * UB, c.ostage, (uint32_t)nloc * UB);
+      bulk_commit();
     }
   }
   // ragged tail of the image (whole pixels, fewer than one unit): last tile, one pixel per thread
-  if (c.tile == n_tiles - 1) {
-    const int p0 = n_units * UB / C;
-    for (int pix = p0 + c.tid; pix < c.HW; pix += NT) {
+  if (c.tile == c.p->n_tiles - 1) {
+    const int p0 = (c.img_bytes / UB) * UB / C;
+    for (int pix = p0 + c.tid; pix < c.HW; pix += NCONS) {
       int v[C];
+      if (!COUNT && c.info->paint) {
+        int sx = pix % c.W, sy = pix / c.W;
+        const int k = resolve(t.sp, t.n_sp, c.H, c.W, sx, sy);
+        if (k >= 0) {
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) c.dst[(size_t)pix * C + ch] = (uint8_t)t.sp[k].color[ch];
+          continue;
+        }
+      }
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) v[ch] = c.src[(size_t)pix * C + ch];
       if (kmode == K_NONE) {
@@ -687,7 +785,7 @@ __device__ void exec_flat(const TC<C>& c) {
       }
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) {
-        if (COUNT) count_value(c.s, ch, (uint32_t)v[ch]);
+        if (COUNT) count_value(c, ch, (uint32_t)v[ch]);
         else c.dst[(size_t)pix * C + ch] = (uint8_t)v[ch];
       }
     }
@@ -695,102 +793,164 @@ __device__ void exec_flat(const TC<C>& c) {
 }
 
 // ============================================================================= gather executor
-// Spatial list pending (constant-fill nearest warps and masks), K in {none, Color}.  Returns false
-// (nothing done) when the tile's source bounding box does not fit the staging region.
-// Requires W * C % 16 == 0 (rows are whole 16-byte units) and 16-byte aligned images.
+// round(v) (half away from zero) as a source index, together with its bounds test 0 <= round(v) < n,
+// in five instructions.  fl_rz(v + (2^22 + 0.5)) lands in [2^22, 2^23) exactly when v + 0.5 is in
+// [0, 2^22); the ulp there is 0.5 and round-toward-zero cuts v + 0.5 down to a multiple of 0.5, so
+// the mantissa >> 1 is floor(v + 0.5) = round(v) for v >= 0.  -0.5 < v < 0 rounds to -0 (index 0,
+// like std::round); v == -0.5 rounds away to -1 and is excluded by the explicit test; anything
+// smaller or >= 2^22 (or NaN) produces an index >= n.  Needs n < 2^22 (checked on the host).
+__device__ __forceinline__ bool src_index(float v, int n, int& idx) {
+  const uint32_t u = __float_as_uint(__fadd_rz(v, 4194304.5f));
+  idx = (int)((u - 0x4A800000u) >> 1);
+  return (v > -0.5f) && ((uint32_t)idx < (uint32_t)n);
+}
+
+// Division-free walk over the 4-pixel quads of a tw x th tile: thread t starts at quad t and
+// advances by NCONS quads per round.
+struct QuadWalk {
+  int rq, ry, drq, dry, qpr;
+  __device__ __forceinline__ QuadWalk(int tid, int tw) {
+    qpr = tw >> 2;
+    ry = tid / qpr; rq = tid - ry * qpr;
+    dry = NCONS / qpr; drq = NCONS - dry * qpr;
+  }
+  __device__ __forceinline__ void next() {
+    rq += drq; ry += dry;
+    if (rq >= qpr) { rq -= qpr; ++ry; }
+  }
+};
+
+// Spatial list pending (constant-fill nearest warps and masks), K in {none, Color}.  The producer
+// has staged the source bounding box of the tile (info->bx0.., one TMA row copy per row); pixels are
+// gathered from it four at a time into the output staging tile, which leaves as one TMA store per row.
+//
+// Fast form: the list is ONE warp (by far the most common case).  The x-dependent products of the
+// four pixels of a thread's quad column stay in registers for the whole tile (a thread keeps its
+// column when the quads per row divide the thread count), so a pixel costs four float adds, the
+// 5-instruction index/bounds step per coordinate, an address and C byte loads.
 template <int C, bool COUNT>
-__device__ bool exec_gather(const TC<C>& c, const Rect r) {
-  const TileState& t = c.s->t;
+__device__ void gather_single(const TC<C>& c) {
+  const TileState& t = *c.t;
+  const SlotInfo& in = *c.info;
+  const int H = c.H, W = c.W;
+  const int tw = in.x1 - in.x0, th = in.y1 - in.y0;
+  const Spatial& e = t.sp[0];
+  const float t0 = e.t[0], t1 = e.t[1], t2 = e.t[2], t3 = e.t[3], t4 = e.t[4], t5 = e.t[5];
+  const int kmode = t.kmode;
+  const bool use1 = !t.l1_id, use2 = !t.l2_id;
+  const bool plain = (kmode == K_NONE) && (COUNT || !use1);  // staged bytes are the result
+  const float f = t.kfactor;
+  uint32_t fill = 0;
+#pragma unroll
+  for (int ch = 0; ch < C; ++ch) fill |= (uint32_t)(e.color[ch] & 255) << (8 * ch);
+  const uint32_t fill_a = smem_addr(&in.fill);  // the fill pixel, so that a miss is just another address
+  const int pitch = in.pitch;
+  // staged byte of source pixel (ix, iy), channel ch: base0 + iy * pitch + ix * C + ch
+  const uint32_t base0 = c.data - (uint32_t)(in.by0 * pitch + in.bxb0);
+  QuadWalk q(c.tid, tw);
+  const bool fixed_col = (q.drq == 0);
+  float ax[4], bx[4];
+  auto xterms = [&](int rq) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float fx = small_uint_to_float((uint32_t)(in.x0 + (rq << 2) + i));
+      ax[i] = __fmul_rn(t0, fx);
+      bx[i] = __fmul_rn(t3, fx);
+    }
+  };
+  xterms(q.rq);
+  uint32_t n_fill = 0;
+  for (; q.ry < th; q.next()) {
+    if (!fixed_col) xterms(q.rq);
+    const float fy = small_uint_to_float((uint32_t)(in.y0 + q.ry));
+    const float t1y = __fmul_rn(t1, fy), t4y = __fmul_rn(t4, fy);
+    uint32_t o[C];
+#pragma unroll
+    for (int w = 0; w < C; ++w) o[w] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int ix, iy;
+      const bool inx = src_index(__fadd_rn(__fadd_rn(ax[i], t1y), t2), W, ix);
+      const bool iny = src_index(__fadd_rn(__fadd_rn(bx[i], t4y), t5), H, iy);
+      const bool inside = inx && iny;
+      const uint32_t a = inside ? base0 + (uint32_t)(iy * pitch + ix * C) : fill_a;
+      uint32_t v[C];
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(a + ch);
+      if (!plain) {
+        if (kmode == K_NONE) {
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(c.l1a + ch * 256 + v[ch]);
+        } else if (C == 3) {
+          if (use1) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(c.l1a + ch * 256 + v[ch]);
+          }
+          color_pixel_f(small_uint_to_float(v[0]), small_uint_to_float(v[1]), small_uint_to_float(v[2]), f, v[0], v[1], v[2]);
+          if (!COUNT && use2) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(c.l2a + ch * 256 + v[ch]);
+          }
+        }
+        if (!COUNT) {
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) v[ch] = inside ? v[ch] : byte_of(fill, ch);
+        }
+      }
+      if (COUNT) {
+        if (inside) {
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) count_value(c, ch, v[ch]);
+        } else {
+          ++n_fill;
+        }
+      } else {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+          const int bi = i * C + ch;
+          o[bi >> 2] = ((bi & 3) == 0) ? (v[ch] & 255u) : put_byte(o[bi >> 2], v[ch], bi & 3);
+        }
+      }
+    }
+    if (!COUNT) {
+      const uint32_t oa = c.ostage + (uint32_t)((q.ry * tw + (q.rq << 2)) * C);
+#pragma unroll
+      for (int w = 0; w < C; ++w) sts_u32(oa + 4 * w, o[w]);
+    }
+  }
+  if (COUNT && n_fill) atomicAdd(&c.sm->color_cnt[0], n_fill);
+}
+
+// General form: any list of constant-fill warps and masks.
+template <int C, bool COUNT>
+__device__ void gather_list(const TC<C>& c) {
+  const TileState& t = *c.t;
+  const SlotInfo& in = *c.info;
   const int H = c.H, W = c.W;
   const int n_sp = t.n_sp;
-  // ---- source bounding box: push the tile's corners back through every warp of the list.  Affine
-  // maps take extremes at corners; one pixel of margin per stage covers the rounding of that stage.
-  float minx = (float)r.x0, maxx = (float)(r.x1 - 1), miny = (float)r.y0, maxy = (float)(r.y1 - 1);
-  bool empty = false;
-  for (int k = n_sp - 1; k >= 0; --k) {
-    const Spatial& e = t.sp[k];
-    if (e.type != SP_GEOM || empty) continue;
-    float lx = 3.0e38f, hx = -3.0e38f, ly = 3.0e38f, hy = -3.0e38f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float px = (j & 1) ? maxx : minx, py = (j & 2) ? maxy : miny;
-      const float sx = e.t[0] * px + e.t[1] * py + e.t[2];
-      const float sy = e.t[3] * px + e.t[4] * py + e.t[5];
-      lx = fminf(lx, sx); hx = fmaxf(hx, sx); ly = fminf(ly, sy); hy = fmaxf(hy, sy);
-    }
-    minx = fmaxf(lx - 1.0f, 0.0f); maxx = fminf(hx + 1.0f, (float)(W - 1));
-    miny = fmaxf(ly - 1.0f, 0.0f); maxy = fminf(hy + 1.0f, (float)(H - 1));
-    if (!(minx <= maxx && miny <= maxy)) empty = true;  // also catches NaN
-  }
-  int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;  // inclusive
-  if (!empty) {
-    bx0 = max(0, (int)floorf(minx)); bx1 = min(W - 1, (int)ceilf(maxx));
-    by0 = max(0, (int)floorf(miny)); by1 = min(H - 1, (int)ceilf(maxy));
-  }
-  const int rows = by1 - by0 + 1;
-  const int rowbytes = W * C;
-  const int bxb0 = (bx0 * C) & ~15;
-  const int bxb1 = min(rowbytes, ((bx1 + 1) * C + 15) & ~15);
-  const int rowb = rows > 0 ? bxb1 - bxb0 : 0;
-  const int pitch = rowb + 16;  // consecutive rows start 4 banks apart
-  const int tw = r.x1 - r.x0, th = r.y1 - r.y0;
-  const int out_bytes = COUNT ? 0 : tw * th * C;
-  if ((long long)max(rows, 0) * pitch + out_bytes > BIG_BYTES) return false;
-  const uint32_t ostage = c.big;
-  const uint32_t stage = c.big + out_bytes;
-
-  // ---- stage the bounding box
-  if (rows > 0) {
-    const int n16 = rowb >> 4;
-    const int total = rows * n16;
-    const uint8_t* sbase = c.src + (size_t)by0 * rowbytes + bxb0;
-    for (int i = c.tid; i < total; i += NT) {
-      const int rr = i / n16, q = i - rr * n16;
-      sts_v4(stage + rr * pitch + (q << 4), ldg_stream(sbase + (size_t)rr * rowbytes + (q << 4)));
-    }
-  }
-  __syncthreads();
-
-  // ---- gather: one item = 4 consecutive pixels of a tile row
+  const int bx0 = in.bx0, by0 = in.by0;
+  const uint32_t box_w = (uint32_t)(in.bx1 - bx0), box_h = (uint32_t)(in.by1 - by0);
+  const bool box_empty = in.rows <= 0;
+  const int tw = in.x1 - in.x0, th = in.y1 - in.y0;
+  const int pitch = in.pitch;
+  const uint32_t base0 = c.data - (uint32_t)(by0 * pitch + in.bxb0);
   const int kmode = t.kmode;
   const bool use1 = !t.l1_id, use2 = !t.l2_id;
   const float f = t.kfactor;
-  const bool single = (n_sp == 1 && t.sp[0].type == SP_GEOM);
-  float t0 = 1.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 1.f, t5 = 0.f;
-  uint32_t fill0 = 0;
-  if (single) {
-    const Spatial& e = t.sp[0];
-    t0 = e.t[0]; t1 = e.t[1]; t2 = e.t[2]; t3 = e.t[3]; t4 = e.t[4]; t5 = e.t[5];
-#pragma unroll
-    for (int ch = 0; ch < C; ++ch) fill0 |= (uint32_t)(e.color[ch] & 255) << (8 * ch);
-  }
-  const int qpr = tw >> 2;
-  const int n_items = qpr * th;
-  const uint32_t box_w = (uint32_t)(bx1 - bx0), box_h = (uint32_t)(by1 - by0);
-  for (int it = c.tid; it < n_items; it += NT) {
-    const int ry = it / qpr, rq = it - ry * qpr;
-    const int y = r.y0 + ry;
-    int x = r.x0 + (rq << 2);
+  for (QuadWalk q(c.tid, tw); q.ry < th; q.next()) {
+    const int y = in.y0 + q.ry;
+    int x = in.x0 + (q.rq << 2);
     uint32_t o[C];
 #pragma unroll
-    for (int q = 0; q < C; ++q) o[q] = 0;
-    const float fy = small_uint_to_float((uint32_t)y);
-    const float t1y = __fmul_rn(t1, fy), t4y = __fmul_rn(t4, fy);
+    for (int w = 0; w < C; ++w) o[w] = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i, ++x) {
-      int sx = x, sy = y, k = -1;
-      if (single) {
-        const float fx = small_uint_to_float((uint32_t)x);
-        sx = round_half_away_i(__fadd_rn(__fadd_rn(__fmul_rn(t0, fx), t1y), t2));
-        sy = round_half_away_i(__fadd_rn(__fadd_rn(__fmul_rn(t3, fx), t4y), t5));
-        if (!((unsigned)sx < (unsigned)W && (unsigned)sy < (unsigned)H)) k = 0;
-      } else {
-        k = resolve(t.sp, n_sp, H, W, sx, sy);
-      }
+      int sx = x, sy = y;
+      const int k = resolve(t.sp, n_sp, H, W, sx, sy);
       uint32_t v[C];
       if (k < 0) {
-        if ((uint32_t)(sx - bx0) <= box_w && (uint32_t)(sy - by0) <= box_h) {
-          const uint32_t a = stage + (uint32_t)((sy - by0) * pitch + sx * C - bxb0);
+        if (!box_empty && (uint32_t)(sx - bx0) <= box_w && (uint32_t)(sy - by0) <= box_h) {
+          const uint32_t a = base0 + (uint32_t)(sy * pitch + sx * C);
 #pragma unroll
           for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(a + ch);
         } else {  // never taken if the box is right; keeps a box error from becoming a wrong pixel
@@ -816,14 +976,11 @@ __device__ bool exec_gather(const TC<C>& c, const Rect r) {
         }
         if (COUNT) {
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) count_value(c.s, ch, v[ch]);
+          for (int ch = 0; ch < C; ++ch) count_value(c, ch, v[ch]);
         }
       } else {
         if (COUNT) {
-          atomicAdd(&c.s->color_cnt[k], 1u);
-        } else if (single) {
-#pragma unroll
-          for (int ch = 0; ch < C; ++ch) v[ch] = byte_of(fill0, ch);
+          atomicAdd(&c.sm->color_cnt[k], 1u);
         } else {
 #pragma unroll
           for (int ch = 0; ch < C; ++ch) v[ch] = (uint32_t)t.sp[k].color[ch];
@@ -838,290 +995,567 @@ __device__ bool exec_gather(const TC<C>& c, const Rect r) {
       }
     }
     if (!COUNT) {
-      const uint32_t oa = ostage + (uint32_t)((ry * tw + (rq << 2)) * C);
+      const uint32_t oa = c.ostage + (uint32_t)((q.ry * tw + (q.rq << 2)) * C);
 #pragma unroll
-      for (int q = 0; q < C; ++q) sts_u32(oa + 4 * q, o[q]);
+      for (int w = 0; w < C; ++w) sts_u32(oa + 4 * w, o[w]);
+    }
+  }
+}
+
+// One TMA store per row of a tw x th output staging tile whose top-left pixel is (x0, y0).
+template <int C>
+__device__ __forceinline__ void store_tile_rows(const TC<C>& c, uint32_t ostage, int x0, int y0, int tw, int th) {
+  if (c.tid < 32) {
+    const int rowbytes = c.W * C;
+    uint8_t* dbase = c.dst + ((size_t)y0 * c.W + x0) * C;
+    const uint32_t rb = (uint32_t)(tw * C);
+    for (int rr = c.tid; rr < th; rr += 32) bulk_store(dbase + (size_t)rr * rowbytes, ostage + rr * rb, rb);
+    bulk_commit();
+  }
+}
+
+template <int C, bool COUNT>
+__device__ void exec_gather(const TC<C>& c) {
+  const TileState& t = *c.t;
+  const SlotInfo& in = *c.info;
+  if (t.n_sp == 1 && t.sp[0].type == SP_GEOM) gather_single<C, COUNT>(c);
+  else gather_list<C, COUNT>(c);
+  if (!COUNT) {
+    store_barrier(c);
+    store_tile_rows(c, c.ostage, in.x0, in.y0, in.x1 - in.x0, in.y1 - in.y0);
+  }
+}
+
+// Sharpness of a gathered image (K == Sharpness with a spatial list pending): the tile's virtual
+// pre-image (spatial list -> l1) is gathered with a one-pixel halo into shared memory, half a tile
+// at a time, and sharpened from there.  Rare (a warp or CutOut followed by Sharpness), so the 3x3
+// window is evaluated per pixel; what matters is that it no longer runs on the scalar executor.
+// R region: [halo tile | output half 0 | output half 1].
+template <int C, bool COUNT>
+__device__ void exec_gather_sharp(const TC<C>& c) {
+  const TileState& t = *c.t;
+  const SlotInfo& in = *c.info;
+  const int H = c.H, W = c.W;
+  const int n_sp = t.n_sp;
+  const int bx0 = in.bx0, by0 = in.by0;
+  const uint32_t box_w = (uint32_t)(in.bx1 - bx0), box_h = (uint32_t)(in.by1 - by0);
+  const bool box_empty = in.rows <= 0;
+  const int pitch = in.pitch;
+  const uint32_t base0 = c.data - (uint32_t)(by0 * pitch + in.bxb0);
+  const bool use2 = !t.l2_id;
+  const float f = t.kfactor;
+  const float k1 = __int_as_float(0x3d9d89d9);  // float32(1)/float32(13)
+  const float k5 = __int_as_float(0x3ec4ec4f);  // float32(5)/float32(13)
+  const int tw = in.x1 - in.x0, th = in.y1 - in.y0;
+  const int hh = (th + 1) >> 1;              // rows per half
+  const int vw = tw + 2;                     // halo tile width in pixels
+  const uint32_t vbuf = c.r;
+  const uint32_t vbytes = (uint32_t)(((hh + 2) * vw * C + 15) & ~15);
+  const uint32_t obytes = (uint32_t)(hh * tw * C);
+  stores_drained(c.tid);  // the whole R region is used here
+  cons_sync();
+  for (int half = 0; half < 2; ++half) {
+    const int ya = in.y0 + half * hh, yb = min(in.y1, ya + hh);
+    if (yb <= ya) break;
+    // phase 1: virtual pre-image on [x0-1, x1] x [ya-1, yb]
+    const int nv = (yb - ya + 2) * vw;
+    for (int i = c.tid; i < nv; i += NCONS) {
+      const int vy = i / vw, vx = i - vy * vw;
+      const int y = ya - 1 + vy, x = in.x0 - 1 + vx;
+      uint32_t v[C];
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) v[ch] = 0;
+      if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) {
+        int sx = x, sy = y;
+        const int k = resolve(t.sp, n_sp, H, W, sx, sy);
+        if (k < 0) {
+          if (!box_empty && (uint32_t)(sx - bx0) <= box_w && (uint32_t)(sy - by0) <= box_h) {
+            const uint32_t a = base0 + (uint32_t)(sy * pitch + sx * C);
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(a + ch);
+          } else {
+            const uint8_t* px = c.src + ((size_t)sy * W + sx) * C;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) v[ch] = __ldg(px + ch);
+          }
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(c.l1a + ch * 256 + v[ch]);
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) v[ch] = (uint32_t)t.sp[k].color[ch];
+        }
+      }
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch)
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(vbuf + (uint32_t)(i * C + ch)), "r"(v[ch]) : "memory");
+    }
+    cons_sync();
+    // phase 2: sharpen tw x (yb - ya) pixels out of the halo tile
+    const uint32_t obuf = c.r + vbytes + half * obytes;
+    const int np = (yb - ya) * tw;
+    for (int i = c.tid; i < np; i += NCONS) {
+      const int ry = i / tw, rx = i - ry * tw;
+      const int y = ya + ry, x = in.x0 + rx;
+      const bool interior = y > 0 && y < H - 1 && x > 0 && x < W - 1;
+      const uint32_t ctr = vbuf + (uint32_t)(((ry + 1) * vw + rx + 1) * C);
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) {
+        const uint32_t orig = lds_u8(ctr + ch);
+        float deg = small_uint_to_float(orig);
+        if (interior) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              const float kk = (dy == 0 && dx == 0) ? k5 : k1;
+              acc = __fadd_rn(acc, __fmul_rn(small_uint_to_float(lds_u8(ctr + (uint32_t)((dy * vw + dx) * C + ch))), kk));
+            }
+          deg = __fadd_rn(__fadd_rz(acc, 8388608.0f), -8388608.0f);  // float(trunc(acc))
+        }
+        uint32_t res = sharp_blend(deg, small_uint_to_float(orig), f);
+        if (COUNT) {
+          count_value(c, ch, res);
+        } else {
+          if (use2) res = lds_u8(c.l2a + ch * 256 + res);
+          asm volatile("st.shared.u8 [%0], %1;" ::"r"(obuf + (uint32_t)(i * C + ch)), "r"(res) : "memory");
+        }
+      }
+    }
+    if (!COUNT) {
+      fence_proxy_async();
+      cons_sync();
+      store_tile_rows(c, obuf, in.x0, ya, tw, yb - ya);
+    } else {
+      cons_sync();
     }
   }
   if (!COUNT) {
-    __syncthreads();
-    const int n16 = (tw * C) >> 4;
-    const int total = th * n16;
-    uint8_t* dbase = c.dst + ((size_t)r.y0 * W + r.x0) * C;
-    for (int i = c.tid; i < total; i += NT) {
-      const int rr = i / n16, q = i - rr * n16;
-      *reinterpret_cast<uint4*>(dbase + (size_t)rr * rowbytes + (q << 4)) = lds_v4(ostage + rr * (tw * C) + (q << 4));
-    }
+    stores_drained(c.tid);  // the next item's staging tile overlaps these buffers
+    cons_sync();
   }
-  return true;
 }
 
 // ========================================================================== sharpness executor
-// K == Sharpness with no spatial op pending: the tile is a strip of whole rows.  The strip plus one
-// halo row each side is staged in shared memory with l1 already applied; a thread then owns one word
-// column (4 bytes wide) of a sub-strip and walks down it, keeping the float32 products of the last
-// two rows of its 4 + 2C-byte window in registers, so every input byte is converted and multiplied
-// once per column instead of nine times.  Requires W * C % 16 == 0.  Returns false if the strip does
-// not fit the staging region.
+// K == Sharpness with no spatial op pending: the tile is a strip of whole rows; the strip plus one
+// halo row each side sits in the slot (one TMA load).  l1 is applied to the staged rows in place; a
+// thread then owns one word column (4 bytes wide) of a sub-strip and walks down it, keeping the
+// float32 products of the last two rows of its 4 + 2C-byte window in registers, so every input byte
+// is converted and multiplied once per column instead of nine times.  Results go to the output
+// staging tile and leave as one TMA store (a strip is contiguous in the image).
 template <int C, bool COUNT>
-__device__ bool exec_sharp(const TC<C>& c, const Rect r) {
+__device__ void exec_sharp(const TC<C>& c) {
   constexpr int NB = 4 + 2 * C;  // window bytes per row
-  const TileState& t = c.s->t;
+  const TileState& t = *c.t;
+  const SlotInfo& in = *c.info;
   const int H = c.H;
   const int row = c.W * C;
-  const int sr0 = max(0, r.y0 - 1), sr1 = min(H, r.y1 + 1);
-  const int nrows = sr1 - sr0;
-  if (nrows <= 0) return true;
-  if ((long long)nrows * row > BIG_BYTES) return false;
-  const uint32_t stage = c.big;
+  const int sr0 = in.by0, nrows = in.rows;
+  const int y0 = in.y0, y1 = in.y1;
+  const uint32_t stage = c.data;
   const bool use1 = !t.l1_id, use2 = !t.l2_id;
   const float f = t.kfactor;
-  {  // stage rows [sr0, sr1) through l1; byte 16 i of the image has channel (16 i) % C
+  if (nrows <= 0 || y1 <= y0) return;
+  if (use1) {  // byte 16 i of the image has channel (16 i) % C
     const int total = (nrows * row) >> 4;
-    const uint8_t* sbase = c.src + (size_t)sr0 * row;
     const int i0 = (sr0 * row) >> 4;
-    for (int i = c.tid; i < total; i += NT) {
-      uint4 v = ldg_stream(sbase + ((size_t)i << 4));
-      if (use1) v = map_vec_phase<C>(v, c.l1a, (C == 3) ? ((i0 + i) % 3) : 0);
+    for (int i = c.tid; i < total; i += NCONS) {
+      const uint4 v = map_vec_phase<C>(lds_v4(stage + (i << 4)), c.l1a, (C == 3) ? ((i0 + i) % 3) : 0);
       sts_v4(stage + (i << 4), v);
     }
+    cons_sync();
   }
-  __syncthreads();
   const int wpr = row >> 2;  // words per row
   auto emit = [&](int y, int xw, uint32_t o) {
     const int ph = (C == 3) ? (xw % 3) : 0;  // channel of byte 0 of word xw (4 == 1 mod 3)
     if (COUNT) {
 #pragma unroll
-      for (int b = 0; b < 4; ++b) count_value(c.s, (ph + b) % C, byte_of(o, b));
+      for (int b = 0; b < 4; ++b) count_value(c, (ph + b) % C, byte_of(o, b));
     } else {
       if (use2)
         o = map_word(o, c.l2a + (uint32_t)((ph + 0) % C) * 256u, c.l2a + (uint32_t)((ph + 1) % C) * 256u,
                      c.l2a + (uint32_t)((ph + 2) % C) * 256u, c.l2a + (uint32_t)((ph + 3) % C) * 256u);
-      *reinterpret_cast<uint32_t*>(c.dst + (size_t)y * row + ((size_t)xw << 2)) = o;
+      sts_u32(c.ostage + (uint32_t)((y - y0) * row + (xw << 2)), o);
     }
   };
   // first and last image row: every pixel is border -> blend(orig, orig) == orig
-  if (r.y0 == 0 && r.y1 > 0)
-    for (int xw = c.tid; xw < wpr; xw += NT) emit(0, xw, lds_u32(stage + (uint32_t)((0 - sr0) * row + (xw << 2))));
-  if (H > 1 && r.y0 <= H - 1 && r.y1 > H - 1)
-    for (int xw = c.tid; xw < wpr; xw += NT) emit(H - 1, xw, lds_u32(stage + (uint32_t)((H - 1 - sr0) * row + (xw << 2))));
-  const int in0 = max(r.y0, 1), in1 = min(r.y1, H - 1);
+  if (y0 == 0)
+    for (int xw = c.tid; xw < wpr; xw += NCONS) emit(0, xw, lds_u32(stage + (uint32_t)((0 - sr0) * row + (xw << 2))));
+  if (H > 1 && y0 <= H - 1 && y1 > H - 1)
+    for (int xw = c.tid; xw < wpr; xw += NCONS) emit(H - 1, xw, lds_u32(stage + (uint32_t)((H - 1 - sr0) * row + (xw << 2))));
+  const int in0 = max(y0, 1), in1 = min(y1, H - 1);
   const int inner = in1 - in0;
-  if (inner <= 0) return true;
-  const float k1 = __int_as_float(0x3d9d89d9);  // float32(1)/float32(13)
-  const float k5 = __int_as_float(0x3ec4ec4f);  // float32(5)/float32(13)
-  // split the inner rows into S sub-strips so that (word columns x sub-strips) keeps every thread
-  // busy: minimise rounds * (rows per sub-strip + 2 halo rows).
-  int best_s = 1;
-  long best_cost = 1L << 60;
-  for (int S = 1; S <= 16 && S <= inner; ++S) {
-    const long rounds = ((long)wpr * S + NT - 1) / NT;
-    const long cost = rounds * ((inner + S - 1) / S + 2);
-    if (cost < best_cost) { best_cost = cost; best_s = S; }
-  }
-  const int R = (inner + best_s - 1) / best_s;
-  const int n_strips = (inner + R - 1) / R;
-  const int n_items = wpr * n_strips;
-  for (int item = c.tid; item < n_items; item += NT) {
-    const int strip = item / wpr;
-    const int xw = item - strip * wpr;
-    const int y_begin = in0 + strip * R;
-    const int y_end = min(in1, y_begin + R);
-    const int xb0 = xw << 2;
-    bool border[4];  // is the byte in the first / last pixel of the row?
+  if (inner > 0) {
+    const float k1 = __int_as_float(0x3d9d89d9);  // float32(1)/float32(13)
+    const float k5 = __int_as_float(0x3ec4ec4f);  // float32(5)/float32(13)
+    // split the inner rows into S sub-strips so that (word columns x sub-strips) keeps every thread
+    // busy: minimise rounds * (rows per sub-strip + 2 halo rows).
+    int best_s = 1;
+    long best_cost = 1L << 60;
+    for (int S = 1; S <= 16 && S <= inner; ++S) {
+      const long rounds = ((long)wpr * S + NCONS - 1) / NCONS;
+      const long cost = rounds * ((inner + S - 1) / S + 2);
+      if (cost < best_cost) { best_cost = cost; best_s = S; }
+    }
+    const int R = (inner + best_s - 1) / best_s;
+    const int n_strips = (inner + R - 1) / R;
+    const int n_items = wpr * n_strips;
+    for (int item = c.tid; item < n_items; item += NCONS) {
+      const int strip = item / wpr;
+      const int xw = item - strip * wpr;
+      const int y_begin = in0 + strip * R;
+      const int y_end = min(in1, y_begin + R);
+      const int xb0 = xw << 2;
+      bool border[4];  // is the byte in the first / last pixel of the row?
 #pragma unroll
-    for (int b = 0; b < 4; ++b) border[b] = (xb0 + b < C) || (xb0 + b >= row - C);
-    const bool has_prev = xw > 0, has_next = xw + 1 < wpr;
-    float pa[NB], pb[NB];  // products (x k1) of rows y-1 and y
-    float ctr[4];          // float values of the centre bytes of row y
-    auto load_row = [&](int yy, float* pr, float* cvals) {
-      const uint32_t ra = stage + (uint32_t)((yy - sr0) * row + xb0);
-      const uint32_t w1 = lds_u32(ra);
-      const uint32_t w0 = has_prev ? lds_u32(ra - 4) : 0u;
-      const uint32_t w2 = has_next ? lds_u32(ra + 4) : 0u;
+      for (int b = 0; b < 4; ++b) border[b] = (xb0 + b < C) || (xb0 + b >= row - C);
+      const bool has_prev = xw > 0, has_next = xw + 1 < wpr;
+      float pa[NB], pb[NB];  // products (x k1) of rows y-1 and y
+      float ctr[4];          // float values of the centre bytes of row y
+      auto load_row = [&](int yy, float* pr, float* cvals) {
+        const uint32_t ra = stage + (uint32_t)((yy - sr0) * row + xb0);
+        const uint32_t w1 = lds_u32(ra);
+        const uint32_t w0 = has_prev ? lds_u32(ra - 4) : 0u;
+        const uint32_t w2 = has_next ? lds_u32(ra + 4) : 0u;
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int wb = 4 - C + j;  // byte index in the 12-byte (w0, w1, w2) window
-        const uint32_t wsel = (wb < 4) ? w0 : (wb < 8) ? w1 : w2;
-        const float fv = byte_to_float(wsel, wb & 3);
-        pr[j] = __fmul_rn(fv, k1);
-        if (cvals != nullptr && j >= C && j < C + 4) cvals[j - C] = fv;
-      }
-    };
-    load_row(y_begin - 1, pa, nullptr);
-    load_row(y_begin, pb, ctr);
-    for (int y = y_begin; y < y_end; ++y) {
-      float pc[NB], nctr[4];
-      load_row(y + 1, pc, nctr);
-      uint32_t o = 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const float orig = ctr[b];
-        float deg = orig;
-        if (!border[b]) {
-          // window index b + C is the byte itself, b / b + 2C its left / right neighbours
-          float acc = pa[b];
-          acc = __fadd_rn(acc, pa[b + C]);
-          acc = __fadd_rn(acc, pa[b + 2 * C]);
-          acc = __fadd_rn(acc, pb[b]);
-          acc = __fadd_rn(acc, __fmul_rn(orig, k5));
-          acc = __fadd_rn(acc, pb[b + 2 * C]);
-          acc = __fadd_rn(acc, pc[b]);
-          acc = __fadd_rn(acc, pc[b + C]);
-          acc = __fadd_rn(acc, pc[b + 2 * C]);
-          deg = __fadd_rn(__fadd_rz(acc, 8388608.0f), -8388608.0f);  // float(trunc(acc))
+        for (int j = 0; j < NB; ++j) {
+          const int wb = 4 - C + j;  // byte index in the 12-byte (w0, w1, w2) window
+          const uint32_t wsel = (wb < 4) ? w0 : (wb < 8) ? w1 : w2;
+          const float fv = byte_to_float(wsel, wb & 3);
+          pr[j] = __fmul_rn(fv, k1);
+          if (cvals != nullptr && j >= C && j < C + 4) cvals[j - C] = fv;
         }
-        const uint32_t res = sharp_blend(deg, orig, f);
-        o = (b == 0) ? res : put_byte(o, res, b);
+      };
+      load_row(y_begin - 1, pa, nullptr);
+      load_row(y_begin, pb, ctr);
+      for (int y = y_begin; y < y_end; ++y) {
+        float pc[NB], nctr[4];
+        load_row(y + 1, pc, nctr);
+        uint32_t o = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float orig = ctr[b];
+          float deg = orig;
+          if (!border[b]) {
+            // window index b + C is the byte itself, b / b + 2C its left / right neighbours
+            float acc = pa[b];
+            acc = __fadd_rn(acc, pa[b + C]);
+            acc = __fadd_rn(acc, pa[b + 2 * C]);
+            acc = __fadd_rn(acc, pb[b]);
+            acc = __fadd_rn(acc, __fmul_rn(orig, k5));
+            acc = __fadd_rn(acc, pb[b + 2 * C]);
+            acc = __fadd_rn(acc, pc[b]);
+            acc = __fadd_rn(acc, pc[b + C]);
+            acc = __fadd_rn(acc, pc[b + 2 * C]);
+            deg = __fadd_rn(__fadd_rz(acc, 8388608.0f), -8388608.0f);  // float(trunc(acc))
+          }
+          const uint32_t res = sharp_blend(deg, orig, f);
+          o = (b == 0) ? res : put_byte(o, res, b);
+        }
+        emit(y, xw, o);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) { pa[j] = pb[j]; pb[j] = pc[j]; }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) ctr[b] = nctr[b];
       }
-      emit(y, xw, o);
-#pragma unroll
-      for (int j = 0; j < NB; ++j) { pa[j] = pb[j]; pb[j] = pc[j]; }
-#pragma unroll
-      for (int b = 0; b < 4; ++b) ctr[b] = nctr[b];
     }
   }
-  return true;
+  if (!COUNT) {
+    store_barrier(c);
+    if (c.tid == 0) {
+      bulk_store(c.dst + (size_t)y0 * row, c.ostage, (uint32_t)((y1 - y0) * row));
+      bulk_commit();
+    }
+  } else if (use1) {
+    fence_proxy_async();  // the slot was written through the generic proxy; the TMA refills it next
+  }
 }
 
-// ================================================================================ pass kernel
-template <int C, bool COUNT>
-__device__ void run_tile(const TC<C>& c) {
-  const KParams& p = *c.p;
-  const TileState& t = c.s->t;
-  const int H = c.H, W = c.W;
-  const int kmode = t.kmode;
-  const bool rows16 = ((W * C) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.src) & 15) == 0 &&
-                      (COUNT || (reinterpret_cast<uintptr_t>(c.dst) & 15) == 0);
+// =================================================================================== producer
+// Decides how a tile is executed and issues its loads.  Runs on the producer warp; every lane
+// computes the same plan, lane 0 writes it, all lanes issue row copies.
+template <int C>
+__device__ void produce_tile(const KParams& p, Slot& S, uint32_t full_bar, int img, int tile, int lane) {
+  const TileState& t = S.st;
+  const int H = p.H, W = p.W;
+  const int img_bytes = H * W * C;
+  const int pass_kind = t.pass_kind;
+  const bool count = pass_kind == PASS_COUNT;
+  const size_t img_off = (size_t)img * img_bytes;
+  const uint8_t* src = (t.src_sel == 0) ? p.in + img_off
+                                       : p.scratch + (size_t)(2 * (size_t)img + (t.src_sel - 1)) * p.scratch_stride;
+  const uint8_t* dst = (pass_kind == PASS_WRITE_OUT)
+                           ? p.out + img_off
+                           : p.scratch + (size_t)(2 * (size_t)img + (t.dst_sel - 1)) * p.scratch_stride;
+  const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (count || (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  const bool rows16 = ((W * C) & 15) == 0 && aligned;
   const bool fast = !p.force_generic;
-  const int tile = c.tile;
+  const int kmode = t.kmode, n_sp = t.n_sp;
+  const int rowbytes = W * C;
   // tile -> region.  The partition depends only on per-image state, so all tiles of a pass agree.
-  Rect strip;
+  Rect strip, box;
   {
     const int R = (H + p.n_tiles - 1) / p.n_tiles;
     strip.x0 = 0; strip.x1 = W; strip.y0 = min(H, tile * R); strip.y1 = min(H, strip.y0 + R);
-  }
-  Rect box;
-  {
     const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
     box.x0 = min(W, tx * p.tw); box.x1 = min(W, box.x0 + p.tw);
     box.y0 = min(H, ty * p.th); box.y1 = min(H, box.y0 + p.th);
   }
-  if (kmode == K_NONE || kmode == K_COLOR) {
-    if (t.n_sp == 0) {
-      const bool ok = fast && (c.img_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(c.src) & 15) == 0 &&
-                      (COUNT || (reinterpret_cast<uintptr_t>(c.dst) & 15) == 0);
-      if (ok) exec_flat<C, COUNT>(c);
-      else exec_generic<C, COUNT>(c, strip);
-    } else {
-      bool done = false;
-      if (fast && rows16 && t.sp_fast) done = exec_gather<C, COUNT>(c, box);
-      if (!done) exec_generic<C, COUNT>(c, box);
+  SlotInfo in;
+  in.cls = CLS_GENERIC; in.img = img; in.tile = tile; in.pass_kind = pass_kind;
+  in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0; in.rowb = 0; in.pitch = 16; in.rows = 0;
+  Rect reg = (n_sp > 0) ? box : strip;
+  uint32_t tx_bytes = 0;
+  const uint32_t data = smem_addr(S.data);
+
+  bool masks_only = n_sp > 0;
+  for (int k = 0; k < n_sp; ++k) masks_only = masks_only && (t.sp[k].type == SP_MASK);
+  in.fill = 0; in.paint = 0;
+  for (int ch = 0; ch < C; ++ch) in.fill |= (uint32_t)(t.sp[0].color[ch] & 255) << (8 * ch);
+
+  // Source bounding box of output rectangle q: push its corners back through every warp of the
+  // list.  Affine maps take extremes at corners; one pixel of margin per stage covers the rounding
+  // of that stage.  Returns false if the box does not fit the slot.
+  auto source_box = [&](const Rect q) -> bool {
+    float minx = (float)q.x0, maxx = (float)(q.x1 - 1), miny = (float)q.y0, maxy = (float)(q.y1 - 1);
+    bool empty = (q.x1 <= q.x0 || q.y1 <= q.y0);
+    for (int k = n_sp - 1; k >= 0; --k) {
+      const Spatial& e = t.sp[k];
+      if (e.type != SP_GEOM || empty) continue;
+      float lx = 3.0e38f, hx = -3.0e38f, ly = 3.0e38f, hy = -3.0e38f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float px = (j & 1) ? maxx : minx, py = (j & 2) ? maxy : miny;
+        const float sx = e.t[0] * px + e.t[1] * py + e.t[2];
+        const float sy = e.t[3] * px + e.t[4] * py + e.t[5];
+        lx = fminf(lx, sx); hx = fmaxf(hx, sx); ly = fminf(ly, sy); hy = fmaxf(hy, sy);
+      }
+      minx = fmaxf(lx - 1.0f, 0.0f); maxx = fminf(hx + 1.0f, (float)(W - 1));
+      miny = fmaxf(ly - 1.0f, 0.0f); maxy = fminf(hy + 1.0f, (float)(H - 1));
+      if (!(minx <= maxx && miny <= maxy)) empty = true;  // also catches NaN
     }
-  } else if (kmode == K_SHARP) {
-    if (t.n_sp == 0) {
-      bool done = false;
-      if (fast && rows16) done = exec_sharp<C, COUNT>(c, strip);
-      if (!done) exec_generic<C, COUNT>(c, strip);
-    } else {
-      exec_generic<C, COUNT>(c, box);
+    if (!empty) {
+      in.bx0 = max(0, (int)floorf(minx)); in.bx1 = min(W - 1, (int)ceilf(maxx));
+      in.by0 = max(0, (int)floorf(miny)); in.by1 = min(H - 1, (int)ceilf(maxy));
+      in.rows = in.by1 - in.by0 + 1;
+      in.bxb0 = (in.bx0 * C) & ~15;
+      in.rowb = min(rowbytes, ((in.bx1 + 1) * C + 15) & ~15) - in.bxb0;
+      in.pitch = in.rowb + 16;  // consecutive rows start 4 banks apart
     }
+    if ((long long)in.rows * in.pitch > DATA_BYTES) {
+      in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0; in.rowb = 0; in.pitch = 16; in.rows = 0;
+      return false;
+    }
+    return true;
+  };
+
+  if ((kmode == K_NONE || kmode == K_COLOR) && (n_sp == 0 || (masks_only && !count))) {
+    if (fast && (img_bytes & 15) == 0 && aligned) {
+      constexpr int UB = (C == 3) ? 48 : 16;
+      const int n_units = img_bytes / UB;
+      const int upt = (n_units + p.n_tiles - 1) / p.n_tiles;
+      const int u0 = min(n_units, tile * upt), u1 = min(n_units, u0 + upt);
+      in.cls = CLS_FLAT;
+      in.paint = n_sp;
+      reg.x0 = u0; reg.x1 = u1; reg.y0 = 0; reg.y1 = 0;
+      tx_bytes = (uint32_t)(u1 - u0) * UB;
+    } else {
+      reg = strip;  // all tiles of the pass take this branch together
+    }
+  } else if ((kmode == K_NONE || kmode == K_COLOR) && fast && rows16 && t.sp_fast) {
+    if (source_box(box)) {
+      in.cls = CLS_GATHER;
+      tx_bytes = (uint32_t)(in.rows * in.rowb);
+    }
+  } else if (kmode == K_SHARP && n_sp == 0 && fast && rows16) {
+    const int sr0 = max(0, strip.y0 - 1), sr1 = min(H, strip.y1 + 1);
+    const int nrows = (strip.y1 > strip.y0) ? sr1 - sr0 : 0;
+    if ((long long)nrows * rowbytes <= DATA_BYTES && (long long)(strip.y1 - strip.y0) * rowbytes <= OSTAGE_BYTES) {
+      in.cls = CLS_SHARP;
+      in.by0 = sr0; in.rows = nrows;
+      tx_bytes = (uint32_t)(nrows * rowbytes);
+    }
+  } else if (kmode == K_SHARP && n_sp > 0 && fast && rows16 && t.sp_fast) {
+    Rect halo = box;
+    halo.x0 = max(0, box.x0 - 1); halo.x1 = min(W, box.x1 + 1);
+    halo.y0 = max(0, box.y0 - 1); halo.y1 = min(H, box.y1 + 1);
+    if (box.x1 > box.x0 && box.y1 > box.y0 && source_box(halo)) {
+      in.cls = CLS_GATHER_SHARP;
+      tx_bytes = (uint32_t)(in.rows * in.rowb);
+    }
+  }
+  in.x0 = reg.x0; in.x1 = reg.x1; in.y0 = reg.y0; in.y1 = reg.y1;
+  if (lane == 0) {
+    S.info = in;
+    if (tx_bytes) mbar_arrive_expect_tx(full_bar, tx_bytes);
+    else mbar_arrive(full_bar);
+  }
+  __syncwarp();
+  if (tx_bytes == 0) return;
+  if (in.cls == CLS_FLAT) {
+    constexpr int UB = (C == 3) ? 48 : 16;
+    if (lane == 0) bulk_load(data, src + (size_t)in.x0 * UB, tx_bytes, full_bar);
+  } else if (in.cls == CLS_SHARP) {
+    if (lane == 0) bulk_load(data, src + (size_t)in.by0 * rowbytes, tx_bytes, full_bar);
   } else {
-    exec_generic<C, COUNT>(c, strip);
+    const uint8_t* sbase = src + (size_t)in.by0 * rowbytes + in.bxb0;
+    for (int rr = lane; rr < in.rows; rr += 32)
+      bulk_load(data + rr * in.pitch, sbase + (size_t)rr * rowbytes, (uint32_t)in.rowb, full_bar);
+  }
+}
+
+// ================================================================================ pass kernel
+template <int C, bool COUNT>
+__device__ __forceinline__ void run_tile(const TC<C>& c) {
+  switch (c.info->cls) {
+    case CLS_FLAT: exec_flat<C, COUNT>(c); break;
+    case CLS_GATHER: exec_gather<C, COUNT>(c); break;
+    case CLS_SHARP: exec_sharp<C, COUNT>(c); break;
+    case CLS_GATHER_SHARP: exec_gather_sharp<C, COUNT>(c); break;
+    default: exec_generic<C, COUNT>(c); break;
   }
 }
 
 template <int C>
 __global__ void __launch_bounds__(NT, PASS_MIN_CTAS) pass_kernel(const KParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  ImgState* s = reinterpret_cast<ImgState*>(smem_raw);
-  volatile int* ctl = reinterpret_cast<volatile int*>(smem_raw + sizeof(ImgState));
-  uint8_t* bigp = smem_raw + sizeof(ImgState) + CTL_BYTES;
+  PassSmem* sm = reinterpret_cast<PassSmem*>(smem_raw);
   const int tid = threadIdx.x;
   const int L = p.level;
   const int H = p.H, W = p.W;
   const int img_bytes = H * W * C;
   const unsigned n_entries = (L == 0) ? (unsigned)p.B : __ldcg(p.counters + L);
-  const unsigned long long n_items = (unsigned long long)n_entries * (unsigned)p.n_tiles;
+  const unsigned n_items = n_entries * (unsigned)p.n_tiles;
+  uint32_t full[2], empty[2];
+  full[0] = smem_addr(&sm->full[0]); full[1] = smem_addr(&sm->full[1]);
+  empty[0] = smem_addr(&sm->empty[0]); empty[1] = smem_addr(&sm->empty[1]);
+  const uint32_t stbar = smem_addr(&sm->stbar);
+  if (tid == 0) {
+    mbar_init(full[0], 1); mbar_init(full[1], 1);
+    mbar_init(empty[0], NCONS); mbar_init(empty[1], NCONS);
+    mbar_init(stbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
 
+  if (tid >= NCONS) {
+    // ------------------------------------------------------------------ producer warp
+    const int lane = tid - NCONS;
+    unsigned* work = p.counters + p.max_levels + L;
+    unsigned next_item = 0;
+    if (lane == 0) next_item = atomicAdd(work, 1u);
+    for (uint32_t it = 0;; ++it) {
+      const int sl = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const unsigned item = __shfl_sync(0xFFFFFFFFu, next_item, 0);
+      mbar_wait(empty[sl], ph ^ 1);  // the consumers have released this slot
+      Slot& S = sm->slot[sl];
+      if (item >= n_items) {
+        if (lane == 0) { S.info.cls = CLS_END; mbar_arrive(full[sl]); }
+        break;
+      }
+      if (lane == 0) next_item = atomicAdd(work, 1u);  // claim the next item while this one loads
+      const int entry = (int)(item / (unsigned)p.n_tiles);
+      const int tile = (int)(item - (unsigned)entry * (unsigned)p.n_tiles);
+      const int img = (L == 0) ? entry : __ldcg(p.lists + (size_t)L * p.B + entry);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(stbar, (uint32_t)sizeof(TileState));
+        bulk_load(smem_addr(&S.st), p.states + img, (uint32_t)sizeof(TileState), stbar);
+      }
+      mbar_wait(stbar, it & 1);
+      produce_tile<C>(p, S, full[sl], img, tile, lane);
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer warps
   TC<C> c;
-  c.p = &p; c.s = s; c.big = smem_addr(bigp);
+  uint32_t nstore = 0;
+  c.nstore = &nstore;
+  c.p = &p; c.sm = sm; c.r = smem_addr(sm->r);
   c.H = H; c.W = W; c.HW = H * W; c.img_bytes = img_bytes; c.tid = tid; c.lane = tid & 31;
-  c.l1a = smem_addr(&s->t.l1[0][0]); c.l2a = smem_addr(&s->t.l2[0][0]);
-
-  for (;;) {
-    __syncthreads();  // the previous item is completely done with shared memory
-    if (tid == 0) ctl[0] = (int)atomicAdd(p.counters + p.max_levels + L, 1u);
-    __syncthreads();
-    const unsigned item = (unsigned)ctl[0];
-    if (item >= n_items) break;
-    const int entry = (int)(item / (unsigned)p.n_tiles);
-    const int tile = (int)(item - (unsigned)entry * (unsigned)p.n_tiles);
-    const int img = (L == 0) ? entry : __ldcg(p.lists + (size_t)L * p.B + entry);
-    ImgState* g = p.states + img;
-    for (int i = tid; i < TILE_VECS; i += NT)
-      reinterpret_cast<uint4*>(s)[i] = __ldcg(reinterpret_cast<const uint4*>(g) + i);
-    __syncthreads();
-    const int pass_kind = s->t.pass_kind;
+  for (uint32_t it = 0;; ++it) {
+    const int sl = it & 1;
+    const uint32_t ph = (it >> 1) & 1;
+    mbar_wait(full[sl], ph);
+    Slot& S = sm->slot[sl];
+    if (S.info.cls == CLS_END) break;
+    const int img = S.info.img, pass_kind = S.info.pass_kind;
     const size_t img_off = (size_t)img * img_bytes;
-    const int src_sel = s->t.src_sel;
-    c.src = (src_sel == 0) ? p.in + img_off : p.scratch + (size_t)(2 * (size_t)img + (src_sel - 1)) * p.scratch_stride;
+    c.t = &S.st; c.info = &S.info; c.tile = S.info.tile;
+    c.data = smem_addr(S.data);
+    c.ostage = c.r + (nstore & 1u) * OSTAGE_BYTES;
+    c.l1a = smem_addr(&S.st.l1[0][0]); c.l2a = smem_addr(&S.st.l2[0][0]);
+    c.src = (S.st.src_sel == 0) ? p.in + img_off
+                                : p.scratch + (size_t)(2 * (size_t)img + (S.st.src_sel - 1)) * p.scratch_stride;
     c.dst = (pass_kind == PASS_WRITE_OUT)
                 ? p.out + img_off
-                : p.scratch + (size_t)(2 * (size_t)img + (s->t.dst_sel - 1)) * p.scratch_stride;
-    c.tile = tile;
+                : p.scratch + (size_t)(2 * (size_t)img + (S.st.dst_sel - 1)) * p.scratch_stride;
+    ImgState* g = p.states + img;
     if (pass_kind == PASS_COUNT) {
-      for (int i = tid; i < MAXC * 256; i += NT) (&s->hist[0][0])[i] = 0u;
-      if (tid < CHB_MAX_CHAIN) s->color_cnt[tid] = 0u;
-      __syncthreads();
+      for (int i = tid; i < MAXC * 256; i += NCONS) (&sm->hist[0][0])[i] = 0u;
+      if (tid < CHB_MAX_CHAIN) sm->color_cnt[tid] = 0u;
+      cons_sync();
       run_tile<C, true>(c);
-      __syncthreads();
-      for (int i = tid; i < C * 256; i += NT) {
-        const uint32_t v = (&s->hist[0][0])[i];
+      cons_sync();
+      for (int i = tid; i < C * 256; i += NCONS) {
+        const uint32_t v = (&sm->hist[0][0])[i];
         if (v) atomicAdd(&g->hist[0][0] + i, v);
       }
-      if (tid < CHB_MAX_CHAIN && s->color_cnt[tid]) atomicAdd(&g->color_cnt[tid], s->color_cnt[tid]);
+      if (tid < CHB_MAX_CHAIN && sm->color_cnt[tid]) atomicAdd(&g->color_cnt[tid], sm->color_cnt[tid]);
     } else {
       run_tile<C, false>(c);
     }
+    mbar_arrive(empty[sl]);  // done with the slot (state, info and staged bytes)
     if (pass_kind == PASS_WRITE_OUT) continue;
 
     // ---- COUNT / WRITE_SCRATCH: the last tile of the image resumes the chain walk
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) ctl[1] = (atomicAdd(&g->tiles_done, 1u) == (unsigned)p.n_tiles - 1u) ? 1 : 0;
-    __syncthreads();
-    if (!ctl[1]) continue;
-    __threadfence();
-    for (int i = tid; i < (int)(sizeof(ImgState) / 16) - TILE_VECS; i += NT)
-      reinterpret_cast<uint4*>(s)[TILE_VECS + i] = __ldcg(reinterpret_cast<const uint4*>(g) + TILE_VECS + i);
-    __syncthreads();
-    if (pass_kind == PASS_COUNT) {
-      if (tid == 0) s->hist_valid = 1;
-    } else {
-      if (tid == 0) s->t.src_sel = s->t.dst_sel;
-      reset_view(s, tid, NT);
+    stores_drained(tid);  // the finaliser scratch below aliases the output staging tiles
+    cons_sync();
+    if (tid == 0) {
+      __threadfence();  // cumulative: publishes the histogram atomics of the whole CTA (ordered by the barrier)
+      sm->ctl[1] = (atomicAdd(&g->tiles_done, 1u) == (unsigned)p.n_tiles - 1u) ? 1 : 0;
+      __threadfence();
     }
-    __syncthreads();
-    advance(s, g, p, C, H, W, reinterpret_cast<uint32_t*>(bigp), bigp + MAXC * 256 * 4, tid, NT);
-    for (int i = tid; i < STATE_VECS; i += NT)
-      reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(s)[i];
+    cons_sync();
+    if (!sm->ctl[1]) continue;
+    ImgState* fs = reinterpret_cast<ImgState*>(sm->r);
+    uint32_t* hmap = reinterpret_cast<uint32_t*>(sm->r + sizeof(ImgState));
+    uint8_t* etab = sm->r + sizeof(ImgState) + MAXC * 256 * 4;
+    for (int i = tid; i < (int)(sizeof(ImgState) / 16); i += NCONS)
+      reinterpret_cast<uint4*>(fs)[i] = __ldcg(reinterpret_cast<const uint4*>(g) + i);
+    cons_sync();
+    if (pass_kind == PASS_COUNT) {
+      if (tid == 0) fs->hist_valid = 1;
+    } else {
+      if (tid == 0) fs->t.src_sel = fs->t.dst_sel;
+      reset_view(fs, tid, NCONS);
+    }
+    cons_sync();
+    advance(fs, g, p, C, H, W, hmap, etab, tid, NCONS, [] { cons_sync(); });
+    for (int i = tid; i < STATE_VECS; i += NCONS)
+      reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(fs)[i];
     if (tid == 0 && L + 1 < p.max_levels) {
       const unsigned pos = atomicAdd(p.counters + L + 1, 1u);
       p.lists[(size_t)(L + 1) * p.B + pos] = img;
     }
+    cons_sync();  // the R region is free again
   }
+  if (tid < 32) bulk_wait_all0();  // every store of this CTA has landed before the grid retires
 }
 
 template <int C>
 cudaError_t launch_pass_c(const KParams& p, int grid, cudaStream_t stream) {
-  pass_kernel<C><<<grid, NT, PASS_SMEM, stream>>>(p);
+  pass_kernel<C><<<grid, NT, sizeof(PassSmem), stream>>>(p);
   return cudaGetLastError();
 }
 
 template <int C>
 cudaError_t configure_c() {
-  return cudaFuncSetAttribute(pass_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PASS_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(pass_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(pass_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 }  // namespace

@@ -9,15 +9,16 @@ namespace chb {
 CHB_DECL(1) CHB_DECL(2) CHB_DECL(3) CHB_DECL(4)
 #undef CHB_DECL
 
-// 2-D tiles of at most 64 x 64 pixels (64-pixel columns keep every tile row a whole number of
-// 16-byte units for C = 1..4); the same tile count cuts an image into flat runs or row strips for
-// the passes that have no spatial op.  224 x 224 -> 4 x 4 tiles of 64 x 56; 512 x 512 -> 8 x 8 of 64 x 64.
+// 2-D tiles of 64 x 64 pixels, ragged at the right / bottom edge (64-pixel columns keep every tile
+// row a whole number of 16-byte units for C = 1..4, and 64 x 64, 64 x 32 and 32 x 32 tiles are all
+// whole rounds of 256 threads x 4 pixels); the same tile count cuts an image into flat runs or row
+// strips for the passes that have no spatial op.  224 x 224 -> 4 x 4 tiles; 512 x 512 -> 8 x 8.
 TilePlan plan_tiles(int H, int W) {
   TilePlan t;
   t.tw = 64;
   t.tiles_x = W > 0 ? (W + 63) / 64 : 1;
   t.tiles_y = H > 0 ? (H + 63) / 64 : 1;
-  t.th = H > 0 ? (H + t.tiles_y - 1) / t.tiles_y : 1;
+  t.th = 64;
   t.n_tiles = t.tiles_x * t.tiles_y;
   return t;
 }
@@ -30,7 +31,7 @@ cudaError_t configure_kernels() {
   return configure_c4();
 }
 
-int pass_ctas_per_sm(int) { return 4; }  // __launch_bounds__(256, 4) and 55 KB of shared memory per CTA
+int pass_ctas_per_sm(int) { return 2; }  // __launch_bounds__(288, 2) and ~98 KB of shared memory per CTA
 
 cudaError_t launch_pass(const KParams& p, int C, int grid, cudaStream_t stream) {
   switch (C) {
