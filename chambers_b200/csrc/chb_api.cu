@@ -4,6 +4,7 @@
 // augmentation_schemes.py:42-128) or per call on the host (float32 conversion of the signed
 // parameters, the projective coefficients, image_augmentations.py:135-146, :334-341, :420-427) is
 // resolved here into a DevOp table; the pixels are only ever touched by chb_kernels.cu.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -58,6 +59,37 @@ struct chb_ctx {
 };
 
 static std::string g_init_error;
+
+// cuTensorMapEncodeTiled is a driver entry point; fetch it through the runtime so that the library
+// does not link against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+
+static const int kBoxRows = 96;    // 64 x 64 tile rotated by 45 degrees + margins
+static const int kBoxBytes = 304;  // 76 words: consecutive staged rows start 12 banks apart
+
+// Tensor map over `images` images of H rows of W*C bytes (uint32 elements), `stride` bytes apart,
+// with a box of at most kBoxRows x kBoxBytes.  Returns the box actually encoded.
+static bool encode_image_map(chb::TMap* out, const void* base, int H, int rowbytes, size_t stride, size_t images,
+                             int* box_rows, int* box_bytes) {
+  static_assert(sizeof(CUtensorMap) == sizeof(chb::TMap), "CUtensorMap size");
+  if (!g_encode_tiled || !base || images == 0) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)(rowbytes / 4), (cuuint64_t)H, (cuuint64_t)images};
+  const cuuint64_t strides[2] = {(cuuint64_t)rowbytes, (cuuint64_t)stride};
+  const int bw = kBoxBytes < rowbytes ? kBoxBytes : rowbytes;
+  const int bh = kBoxRows < H ? kBoxRows : H;
+  const cuuint32_t box[3] = {(cuuint32_t)(bw / 4), (cuuint32_t)bh, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = g_encode_tiled(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT32, 3,
+                                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  *box_rows = bh;
+  *box_bytes = bw;
+  return r == CUDA_SUCCESS;
+}
 
 static int fail(chb_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg; else g_init_error = msg;
@@ -329,6 +361,13 @@ extern "C" int chb_init(int device, chb_ctx** out) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   e = chb::configure_kernels();
   if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "configure_kernels"); delete ctx; return r; }
+  if (!g_encode_tiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode_tiled = (EncodeTiledFn)fn;
+  }
   const char* fg = getenv("CHB_FORCE_GENERIC");
   ctx->force_generic = (fg && fg[0] && fg[0] != '0') ? 1 : 0;
   *out = ctx;
@@ -519,6 +558,16 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   p.max_levels = max_levels;
   p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y; p.tw = tp.tw; p.th = tp.th; p.n_tiles = tp.n_tiles;
   p.force_generic = ctx->force_generic;
+  // gather tiles fetch their source bounding box as one 3-D tensor-map box (rows must be whole 16-byte units)
+  chb::TMap tm_in, tm_scr;
+  memset(&tm_in, 0, sizeof(tm_in));
+  memset(&tm_scr, 0, sizeof(tm_scr));
+  if ((((size_t)W * C) & 15) == 0 && ((uintptr_t)d_in & 15) == 0) {
+    int br = 0, bb = 0;
+    bool ok = encode_image_map(&tm_in, d_in, H, W * C, img_bytes, (size_t)B, &br, &bb);
+    if (ok && ws->scratch) ok = encode_image_map(&tm_scr, ws->scratch, H, W * C, stride, (size_t)B * 2, &br, &bb);
+    if (ok) { p.use_tmap = 1; p.box_rows = br; p.box_bytes = bb; }
+  }
   cudaError_t e = chb::launch_plan(p, C, stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "plan kernel launch");
   ctx->launches += 1;
@@ -527,7 +576,7 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     p.level = level;
     long long grid = slots;
     if (level == 0 && (long long)B * tp.n_tiles < grid) grid = (long long)B * tp.n_tiles;
-    e = chb::launch_pass(p, C, (int)grid, stream);
+    e = chb::launch_pass(p, tm_in, tm_scr, C, (int)grid, stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "pass kernel launch");
     ctx->launches += 1;
   }

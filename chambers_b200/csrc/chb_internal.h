@@ -94,6 +94,12 @@ struct KParams {
   int level, max_levels;
   int tiles_x, tiles_y, tw, th, n_tiles;
   int force_generic;                  // debugging: route every tile through the scalar executor
+  int use_tmap, box_rows, box_bytes;  // gather tiles: one tensor-map box of box_rows x box_bytes per tile
+};
+
+// Opaque copy of a CUtensorMap (cuda.h), passed to the pass kernel as a __grid_constant__ parameter.
+struct alignas(64) TMap {
+  unsigned char bytes[128];
 };
 
 struct TilePlan {
@@ -104,7 +110,7 @@ TilePlan plan_tiles(int H, int W);
 // Launchers (chb_kernels_c<N>.cu / chb_launch.cu).  Each returns cudaGetLastError().
 cudaError_t launch_optab(const DevOp* ops, uint8_t* optab, int n_ops, cudaStream_t stream);
 cudaError_t launch_plan(const KParams& p, int C, cudaStream_t stream);
-cudaError_t launch_pass(const KParams& p, int C, int grid, cudaStream_t stream);
+cudaError_t launch_pass(const KParams& p, const TMap& tm_in, const TMap& tm_scr, int C, int grid, cudaStream_t stream);
 cudaError_t configure_kernels();
 int pass_ctas_per_sm(int C);
 

@@ -39,17 +39,20 @@ namespace {
 constexpr int NCONS = 256;                       // consumer threads of a pass CTA (8 warps)
 constexpr int NT = NCONS + 32;                   // + one producer warp
 constexpr int PLAN_NT = 128;                     // threads per plan CTA
-constexpr int PASS_MIN_CTAS = 2;
-constexpr int DATA_BYTES = 32 * 1024;            // staged source bytes of one pipeline slot
-constexpr int OSTAGE_BYTES = 16 * 1024 + 256;    // one output staging tile (64 x 64 x 4 bytes + one unit)
-constexpr int R_BYTES = 2 * OSTAGE_BYTES;        // two output tiles | lane-private histograms | finaliser scratch
+constexpr int NU = 4;                            // pipeline units per CTA; a tile occupies one or two
+constexpr int UNIT_BYTES = 16 * 1024;            // staged source bytes of one unit
 constexpr int LHIST_CH_BYTES = 64 * 32 * 4;      // lane-private u8x4 histogram of one channel
 constexpr int STATE_VECS = (int)(offsetof(ImgState, hist) / 16);   // everything but the histogram
 constexpr int TILE_VECS = (int)(sizeof(TileState) / 16);
+constexpr int FIN_BYTES = (int)sizeof(ImgState) + MAXC * 256 * 5;  // finaliser: state + hmap + etab
+// one output staging tile: 64 x 64 pixels (a flat run never exceeds that either)
+__host__ __device__ constexpr int ostage_bytes(int C) { return 4096 * C + 256; }
+// R region: two output tiles | lane-private histograms | finaliser scratch
+__host__ __device__ constexpr int r_bytes(int C) {
+  return (2 * ostage_bytes(C) > FIN_BYTES ? 2 * ostage_bytes(C) : FIN_BYTES + 127) / 128 * 128;
+}
 static_assert(offsetof(ImgState, hist) % 16 == 0, "hist must start on a 16-byte boundary");
 static_assert(offsetof(ImgState, next_op) == sizeof(TileState), "finaliser part follows the tile part");
-static_assert(MAXC * LHIST_CH_BYTES <= R_BYTES, "lane-private histograms must fit the R region");
-static_assert(sizeof(ImgState) + MAXC * 256 * 5 <= R_BYTES, "finaliser scratch must fit the R region");
 
 struct Rect {
   int x0, x1, y0, y1;
@@ -398,15 +401,17 @@ __global__ void __launch_bounds__(PLAN_NT) plan_kernel(const KParams p, int C) {
 
 #endif  // CHB_WITH_PLAN
 
-// ============================================================================== pipeline slots
-// A pass CTA is a two-slot producer / consumer pipeline.  The producer warp claims the next
-// (image, tile) item, pulls the image's TileState into the slot with a TMA bulk copy, decides how
-// the tile will be executed, and issues the TMA loads of the tile's source bytes (one bulk copy
-// for a flat run or a row strip, one per row for a gather bounding box); all of it completes on the
-// slot's `full` mbarrier.  The 8 consumer warps wait on `full`, compute from shared memory into an
-// output staging tile and hand that to the TMA again (bulk stores), then release the slot through
-// its `empty` mbarrier.  While the consumers work on one slot the loads of the other are in flight.
-enum { CLS_END = 0, CLS_FLAT = 1, CLS_GATHER = 2, CLS_SHARP = 3, CLS_GENERIC = 4, CLS_GATHER_SHARP = 5 };
+// ============================================================================== pipeline units
+// A pass CTA is a producer / consumer pipeline over a ring of NU units of 16 KB.  The producer warp
+// claims (image, tile) items two ahead, prefetches each image's TileState with a TMA bulk copy,
+// decides how the tile will be executed, takes one or two consecutive units for it and issues the
+// TMA loads of the tile's source bytes -- one bulk copy for a flat run or a row strip, one 3-D
+// tensor-map box (cp.async.bulk.tensor) for the bounding box of a gather tile -- all completing on
+// the first unit's `full` mbarrier.  The 8 consumer warps wait on `full`, compute from shared
+// memory into an output staging tile and hand that to the TMA again (bulk stores), then release the
+// units through their `empty` mbarriers.  Up to four flat tiles or two gather tiles are in flight
+// per CTA, two CTAs per SM.
+enum { CLS_END = 0, CLS_FLAT = 1, CLS_GATHER = 2, CLS_SHARP = 3, CLS_GENERIC = 4, CLS_GATHER_SHARP = 5, CLS_SKIP = 6 };
 
 struct alignas(16) SlotInfo {  // written by the producer, read by the consumers
   int32_t cls, img, tile, pass_kind;
@@ -415,29 +420,27 @@ struct alignas(16) SlotInfo {  // written by the producer, read by the consumers
   int32_t x0, x1, y0, y1;            // region of the tile (box or strip); FLAT: x0 / x1 = first / last unit
   uint32_t fill;                     // GATHER: the colour bytes of spatial entry 0
   int32_t paint;                     // FLAT: the spatial list is masks only; paint them over the result
-  int32_t _pad[2];
+  int32_t span;                      // units this tile occupies (1 or 2)
+  int32_t _pad;
 };
 
-struct alignas(128) Slot {
-  SlotInfo info;
-  TileState st;
-  uint8_t _pad[128 - (sizeof(SlotInfo) + sizeof(TileState)) % 128];
-  uint8_t data[DATA_BYTES];
-};
-
+template <int C>
 struct alignas(128) PassSmem {
-  unsigned long long full[2], empty[2], stbar;
-  int32_t ctl[6];
+  unsigned long long full[NU], empty[NU], stbar[2];
+  int32_t ctl[4];
   uint32_t color_cnt[CHB_MAX_CHAIN];
   uint32_t hist[MAXC][256];  // tile-local counts of a COUNT pass
-  Slot slot[2];
-  uint8_t r[R_BYTES];        // two output staging tiles | lane-private histograms | finaliser scratch
+  SlotInfo info[NU];
+  TileState ust[NU];         // the TileState of the tile whose first unit this is
+  TileState stg[2];          // producer-private prefetch buffers
+  alignas(128) uint8_t data[NU][UNIT_BYTES];
+  alignas(128) uint8_t r[r_bytes(C)];
 };
 
 template <int C>
 struct TC {
   const KParams* p;
-  PassSmem* sm;
+  PassSmem<C>* sm;
   const TileState* t;
   const SlotInfo* info;
   uint32_t data;       // shared address of the slot's staged source bytes
@@ -641,7 +644,7 @@ __device__ __forceinline__ void lhist_zero(uint32_t r, int tid) {
 }
 // Adds the lane-private counters into sm->hist (shared u32 bins).
 template <int C>
-__device__ __forceinline__ void lhist_reduce(PassSmem* sm, uint32_t r, int tid) {
+__device__ __forceinline__ void lhist_reduce(PassSmem<C>* sm, uint32_t r, int tid) {
   const int lane = tid & 31;
   for (int t = tid; t < C * 64; t += NCONS) {
     const int ch = t >> 6, row = t & 63;
@@ -1272,11 +1275,24 @@ __device__ void exec_sharp(const TC<C>& c) {
 }
 
 // =================================================================================== producer
-// Decides how a tile is executed and issues its loads.  Runs on the producer warp; every lane
-// computes the same plan, lane 0 writes it, all lanes issue row copies.
+// 3-D tensor-map load (box of W*C/4 x H x images uint32 elements) completing on an mbarrier.
+__device__ __forceinline__ void tensor_load_3d(uint32_t dst_smem, const TMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+// What the producer decides for one tile.
+struct TilePlanD {
+  SlotInfo in;
+  uint32_t tx_bytes;
+  int src_sel;
+};
+
+// Decides how a tile is executed.  Every lane of the producer warp computes the same plan.
 template <int C>
-__device__ void produce_tile(const KParams& p, Slot& S, uint32_t full_bar, int img, int tile, int lane) {
-  const TileState& t = S.st;
+__device__ void plan_tile(const KParams& p, const TileState& t, int img, int tile, TilePlanD& d) {
   const int H = p.H, W = p.W;
   const int img_bytes = H * W * C;
   const int pass_kind = t.pass_kind;
@@ -1301,12 +1317,13 @@ __device__ void produce_tile(const KParams& p, Slot& S, uint32_t full_bar, int i
     box.x0 = min(W, tx * p.tw); box.x1 = min(W, box.x0 + p.tw);
     box.y0 = min(H, ty * p.th); box.y1 = min(H, box.y0 + p.th);
   }
-  SlotInfo in;
+  SlotInfo& in = d.in;
   in.cls = CLS_GENERIC; in.img = img; in.tile = tile; in.pass_kind = pass_kind;
   in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0; in.rowb = 0; in.pitch = 16; in.rows = 0;
+  in.span = 1; in._pad = 0;
   Rect reg = (n_sp > 0) ? box : strip;
-  uint32_t tx_bytes = 0;
-  const uint32_t data = smem_addr(S.data);
+  d.tx_bytes = 0;
+  d.src_sel = t.src_sel;
 
   bool masks_only = n_sp > 0;
   for (int k = 0; k < n_sp; ++k) masks_only = masks_only && (t.sp[k].type == SP_MASK);
@@ -1315,8 +1332,10 @@ __device__ void produce_tile(const KParams& p, Slot& S, uint32_t full_bar, int i
 
   // Source bounding box of output rectangle q: push its corners back through every warp of the
   // list.  Affine maps take extremes at corners; one pixel of margin per stage covers the rounding
-  // of that stage.  Returns false if the box does not fit the slot.
+  // of that stage.  The box is fetched as ONE tensor-map box of p.box_rows x p.box_bytes starting at
+  // word (bx0 * C) / 4 of row by0; returns false if the bounding box does not fit in it.
   auto source_box = [&](const Rect q) -> bool {
+    if (!p.use_tmap) return false;
     float minx = (float)q.x0, maxx = (float)(q.x1 - 1), miny = (float)q.y0, maxy = (float)(q.y1 - 1);
     bool empty = (q.x1 <= q.x0 || q.y1 <= q.y0);
     for (int k = n_sp - 1; k >= 0; --k) {
@@ -1334,18 +1353,15 @@ __device__ void produce_tile(const KParams& p, Slot& S, uint32_t full_bar, int i
       miny = fmaxf(ly - 1.0f, 0.0f); maxy = fminf(hy + 1.0f, (float)(H - 1));
       if (!(minx <= maxx && miny <= maxy)) empty = true;  // also catches NaN
     }
-    if (!empty) {
-      in.bx0 = max(0, (int)floorf(minx)); in.bx1 = min(W - 1, (int)ceilf(maxx));
-      in.by0 = max(0, (int)floorf(miny)); in.by1 = min(H - 1, (int)ceilf(maxy));
-      in.rows = in.by1 - in.by0 + 1;
-      in.bxb0 = (in.bx0 * C) & ~15;
-      in.rowb = min(rowbytes, ((in.bx1 + 1) * C + 15) & ~15) - in.bxb0;
-      in.pitch = in.rowb + 16;  // consecutive rows start 4 banks apart
-    }
-    if ((long long)in.rows * in.pitch > DATA_BYTES) {
-      in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0; in.rowb = 0; in.pitch = 16; in.rows = 0;
+    if (empty) return true;  // every pixel of the tile shows a fill colour: nothing to stage
+    in.bx0 = max(0, (int)floorf(minx)); in.bx1 = min(W - 1, (int)ceilf(maxx));
+    in.by0 = max(0, (int)floorf(miny)); in.by1 = min(H - 1, (int)ceilf(maxy));
+    in.bxb0 = (in.bx0 * C) & ~15;  // the TMA wants a 16-byte aligned box start
+    if (in.by1 - in.by0 + 1 > p.box_rows || (in.bx1 + 1) * C - in.bxb0 > p.box_bytes) {
+      in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0;
       return false;
     }
+    in.rows = p.box_rows; in.rowb = p.box_bytes; in.pitch = p.box_bytes;
     return true;
   };
 
@@ -1358,22 +1374,22 @@ __device__ void produce_tile(const KParams& p, Slot& S, uint32_t full_bar, int i
       in.cls = CLS_FLAT;
       in.paint = n_sp;
       reg.x0 = u0; reg.x1 = u1; reg.y0 = 0; reg.y1 = 0;
-      tx_bytes = (uint32_t)(u1 - u0) * UB;
+      d.tx_bytes = (uint32_t)(u1 - u0) * UB;  // <= 4096 * C <= one unit
     } else {
       reg = strip;  // all tiles of the pass take this branch together
     }
   } else if ((kmode == K_NONE || kmode == K_COLOR) && fast && rows16 && t.sp_fast) {
     if (source_box(box)) {
       in.cls = CLS_GATHER;
-      tx_bytes = (uint32_t)(in.rows * in.rowb);
+      d.tx_bytes = (uint32_t)(in.rows * in.rowb);
     }
   } else if (kmode == K_SHARP && n_sp == 0 && fast && rows16) {
     const int sr0 = max(0, strip.y0 - 1), sr1 = min(H, strip.y1 + 1);
     const int nrows = (strip.y1 > strip.y0) ? sr1 - sr0 : 0;
-    if ((long long)nrows * rowbytes <= DATA_BYTES && (long long)(strip.y1 - strip.y0) * rowbytes <= OSTAGE_BYTES) {
+    if ((long long)nrows * rowbytes <= 2 * UNIT_BYTES && (long long)(strip.y1 - strip.y0) * rowbytes <= ostage_bytes(C)) {
       in.cls = CLS_SHARP;
       in.by0 = sr0; in.rows = nrows;
-      tx_bytes = (uint32_t)(nrows * rowbytes);
+      d.tx_bytes = (uint32_t)(nrows * rowbytes);
     }
   } else if (kmode == K_SHARP && n_sp > 0 && fast && rows16 && t.sp_fast) {
     Rect halo = box;
@@ -1381,27 +1397,11 @@ __device__ void produce_tile(const KParams& p, Slot& S, uint32_t full_bar, int i
     halo.y0 = max(0, box.y0 - 1); halo.y1 = min(H, box.y1 + 1);
     if (box.x1 > box.x0 && box.y1 > box.y0 && source_box(halo)) {
       in.cls = CLS_GATHER_SHARP;
-      tx_bytes = (uint32_t)(in.rows * in.rowb);
+      d.tx_bytes = (uint32_t)(in.rows * in.rowb);
     }
   }
   in.x0 = reg.x0; in.x1 = reg.x1; in.y0 = reg.y0; in.y1 = reg.y1;
-  if (lane == 0) {
-    S.info = in;
-    if (tx_bytes) mbar_arrive_expect_tx(full_bar, tx_bytes);
-    else mbar_arrive(full_bar);
-  }
-  __syncwarp();
-  if (tx_bytes == 0) return;
-  if (in.cls == CLS_FLAT) {
-    constexpr int UB = (C == 3) ? 48 : 16;
-    if (lane == 0) bulk_load(data, src + (size_t)in.x0 * UB, tx_bytes, full_bar);
-  } else if (in.cls == CLS_SHARP) {
-    if (lane == 0) bulk_load(data, src + (size_t)in.by0 * rowbytes, tx_bytes, full_bar);
-  } else {
-    const uint8_t* sbase = src + (size_t)in.by0 * rowbytes + in.bxb0;
-    for (int rr = lane; rr < in.rows; rr += 32)
-      bulk_load(data + rr * in.pitch, sbase + (size_t)rr * rowbytes, (uint32_t)in.rowb, full_bar);
-  }
+  in.span = (d.tx_bytes > (uint32_t)UNIT_BYTES) ? 2 : 1;
 }
 
 // ================================================================================ pass kernel
@@ -1417,23 +1417,21 @@ __device__ __forceinline__ void run_tile(const TC<C>& c) {
 }
 
 template <int C>
-__global__ void __launch_bounds__(NT, PASS_MIN_CTAS) pass_kernel(const KParams p) {
+__global__ void __launch_bounds__(NT, (sizeof(PassSmem<C>) + 1024) * 2 <= 227 * 1024 ? 2 : 1)
+pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_constant__ TMap tm_scr) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  PassSmem* sm = reinterpret_cast<PassSmem*>(smem_raw);
+  PassSmem<C>* sm = reinterpret_cast<PassSmem<C>*>(smem_raw);
   const int tid = threadIdx.x;
   const int L = p.level;
   const int H = p.H, W = p.W;
   const int img_bytes = H * W * C;
   const unsigned n_entries = (L == 0) ? (unsigned)p.B : __ldcg(p.counters + L);
   const unsigned n_items = n_entries * (unsigned)p.n_tiles;
-  uint32_t full[2], empty[2];
-  full[0] = smem_addr(&sm->full[0]); full[1] = smem_addr(&sm->full[1]);
-  empty[0] = smem_addr(&sm->empty[0]); empty[1] = smem_addr(&sm->empty[1]);
-  const uint32_t stbar = smem_addr(&sm->stbar);
+  const uint32_t full0 = smem_addr(&sm->full[0]), empty0 = smem_addr(&sm->empty[0]);
+  const uint32_t stbar0 = smem_addr(&sm->stbar[0]);
   if (tid == 0) {
-    mbar_init(full[0], 1); mbar_init(full[1], 1);
-    mbar_init(empty[0], NCONS); mbar_init(empty[1], NCONS);
-    mbar_init(stbar, 1);
+    for (int u = 0; u < NU; ++u) { mbar_init(full0 + 8 * u, 1); mbar_init(empty0 + 8 * u, NCONS); }
+    mbar_init(stbar0, 1); mbar_init(stbar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -1443,28 +1441,86 @@ __global__ void __launch_bounds__(NT, PASS_MIN_CTAS) pass_kernel(const KParams p
     // ------------------------------------------------------------------ producer warp
     const int lane = tid - NCONS;
     unsigned* work = p.counters + p.max_levels + L;
-    unsigned next_item = 0;
-    if (lane == 0) next_item = atomicAdd(work, 1u);
-    for (uint32_t it = 0;; ++it) {
-      const int sl = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
-      const unsigned item = __shfl_sync(0xFFFFFFFFu, next_item, 0);
-      mbar_wait(empty[sl], ph ^ 1);  // the consumers have released this slot
-      Slot& S = sm->slot[sl];
-      if (item >= n_items) {
-        if (lane == 0) { S.info.cls = CLS_END; mbar_arrive(full[sl]); }
+    auto claim = [&]() -> unsigned {
+      unsigned v = 0;
+      if (lane == 0) v = atomicAdd(work, 1u);
+      return __shfl_sync(0xFFFFFFFFu, v, 0);
+    };
+    auto image_of = [&](unsigned item) -> int {
+      if (item >= n_items) return -1;
+      const int entry = (int)(item / (unsigned)p.n_tiles);
+      return (L == 0) ? entry : __ldcg(p.lists + (size_t)L * p.B + entry);
+    };
+    auto fetch_state = [&](int img, int buf) {
+      if (lane == 0 && img >= 0) {
+        mbar_arrive_expect_tx(stbar0 + 8 * buf, (uint32_t)sizeof(TileState));
+        bulk_load(smem_addr(&sm->stg[buf]), p.states + img, (uint32_t)sizeof(TileState), stbar0 + 8 * buf);
+      }
+    };
+    // items are claimed three ahead, image indices resolved two ahead, states fetched one ahead
+    unsigned item0 = claim(), item1 = claim(), item2 = claim();
+    int img0 = image_of(item0), img1 = image_of(item1);
+    fetch_state(img0, 0);
+    uint32_t pu = 0;          // next unit (monotonic)
+    uint32_t empty_par = 0xF; // parity to wait for on empty[u]: a fresh barrier passes parity 1
+    for (uint32_t k = 0;; ++k) {
+      auto take_unit = [&](uint32_t u) {  // wait until the consumers have released unit u
+        mbar_wait(empty0 + 8 * u, (empty_par >> u) & 1u);
+        empty_par ^= 1u << u;
+      };
+      if (img0 < 0) {
+        const uint32_t u = pu & (NU - 1);
+        take_unit(u);
+        if (lane == 0) { sm->info[u].cls = CLS_END; mbar_arrive(full0 + 8 * u); }
         break;
       }
-      if (lane == 0) next_item = atomicAdd(work, 1u);  // claim the next item while this one loads
-      const int entry = (int)(item / (unsigned)p.n_tiles);
-      const int tile = (int)(item - (unsigned)entry * (unsigned)p.n_tiles);
-      const int img = (L == 0) ? entry : __ldcg(p.lists + (size_t)L * p.B + entry);
-      if (lane == 0) {
-        mbar_arrive_expect_tx(stbar, (uint32_t)sizeof(TileState));
-        bulk_load(smem_addr(&S.st), p.states + img, (uint32_t)sizeof(TileState), stbar);
+      fetch_state(img1, (k + 1) & 1);
+      const int img2 = image_of(item2);
+      const unsigned item3 = claim();
+      mbar_wait(stbar0 + 8 * (k & 1), (k >> 1) & 1u);
+      const TileState& st = sm->stg[k & 1];
+      const int tile = (int)(item0 % (unsigned)p.n_tiles);
+      TilePlanD d;
+      plan_tile<C>(p, st, img0, tile, d);
+      if (d.in.span == 2 && (pu & (NU - 1)) == NU - 1) {  // a double tile may not wrap: pad the ring
+        const uint32_t u = pu & (NU - 1);
+        take_unit(u);
+        if (lane == 0) { sm->info[u].cls = CLS_SKIP; sm->info[u].span = 1; mbar_arrive(full0 + 8 * u); }
+        ++pu;
       }
-      mbar_wait(stbar, it & 1);
-      produce_tile<C>(p, S, full[sl], img, tile, lane);
+      const uint32_t u = pu & (NU - 1);
+      take_unit(u);
+      if (d.in.span == 2) take_unit(u + 1);
+      pu += d.in.span;
+      // hand the state to the consumers (the prefetch buffer is reused two items later)
+      for (int i = lane; i < TILE_VECS; i += 32)
+        reinterpret_cast<uint4*>(&sm->ust[u])[i] = reinterpret_cast<const uint4*>(&st)[i];
+      __syncwarp();
+      if (lane == 0) {
+        sm->info[u] = d.in;
+        const uint32_t fb = full0 + 8 * u;
+        const uint32_t dst = smem_addr(sm->data[u]);
+        if (d.tx_bytes == 0) {
+          mbar_arrive(fb);
+        } else {
+          mbar_arrive_expect_tx(fb, d.tx_bytes);
+          const size_t img_off = (size_t)img0 * img_bytes;
+          const uint8_t* src = (d.src_sel == 0) ? p.in + img_off
+                                               : p.scratch + (size_t)(2 * (size_t)img0 + (d.src_sel - 1)) * p.scratch_stride;
+          if (d.in.cls == CLS_FLAT) {
+            constexpr int UB = (C == 3) ? 48 : 16;
+            bulk_load(dst, src + (size_t)d.in.x0 * UB, d.tx_bytes, fb);
+          } else if (d.in.cls == CLS_SHARP) {
+            bulk_load(dst, src + (size_t)d.in.by0 * (W * C), d.tx_bytes, fb);
+          } else if (d.src_sel == 0) {
+            tensor_load_3d(dst, &tm_in, d.in.bxb0 >> 2, d.in.by0, img0, fb);
+          } else {
+            tensor_load_3d(dst, &tm_scr, d.in.bxb0 >> 2, d.in.by0, 2 * img0 + (d.src_sel - 1), fb);
+          }
+        }
+      }
+      __syncwarp();
+      item0 = item1; img0 = img1; item1 = item2; img1 = img2; item2 = item3;
     }
     return;
   }
@@ -1475,23 +1531,33 @@ __global__ void __launch_bounds__(NT, PASS_MIN_CTAS) pass_kernel(const KParams p
   c.nstore = &nstore;
   c.p = &p; c.sm = sm; c.r = smem_addr(sm->r);
   c.H = H; c.W = W; c.HW = H * W; c.img_bytes = img_bytes; c.tid = tid; c.lane = tid & 31;
-  for (uint32_t it = 0;; ++it) {
-    const int sl = it & 1;
-    const uint32_t ph = (it >> 1) & 1;
-    mbar_wait(full[sl], ph);
-    Slot& S = sm->slot[sl];
-    if (S.info.cls == CLS_END) break;
-    const int img = S.info.img, pass_kind = S.info.pass_kind;
+  uint32_t cu = 0;        // next unit (monotonic)
+  uint32_t full_par = 0;  // parity to wait for on full[u]
+  for (;;) {
+    const uint32_t u = cu & (NU - 1);
+    mbar_wait(full0 + 8 * u, (full_par >> u) & 1u);
+    full_par ^= 1u << u;
+    const SlotInfo& info = sm->info[u];
+    const int cls = info.cls;
+    if (cls == CLS_END) break;
+    if (cls == CLS_SKIP) {
+      mbar_arrive(empty0 + 8 * u);
+      ++cu;
+      continue;
+    }
+    const int span = info.span;
+    const int img = info.img, pass_kind = info.pass_kind;
     const size_t img_off = (size_t)img * img_bytes;
-    c.t = &S.st; c.info = &S.info; c.tile = S.info.tile;
-    c.data = smem_addr(S.data);
-    c.ostage = c.r + (nstore & 1u) * OSTAGE_BYTES;
-    c.l1a = smem_addr(&S.st.l1[0][0]); c.l2a = smem_addr(&S.st.l2[0][0]);
-    c.src = (S.st.src_sel == 0) ? p.in + img_off
-                                : p.scratch + (size_t)(2 * (size_t)img + (S.st.src_sel - 1)) * p.scratch_stride;
+    const TileState& st = sm->ust[u];
+    c.t = &st; c.info = &info; c.tile = info.tile;
+    c.data = smem_addr(sm->data[u]);
+    c.ostage = c.r + (nstore & 1u) * ostage_bytes(C);
+    c.l1a = smem_addr(&st.l1[0][0]); c.l2a = smem_addr(&st.l2[0][0]);
+    c.src = (st.src_sel == 0) ? p.in + img_off
+                              : p.scratch + (size_t)(2 * (size_t)img + (st.src_sel - 1)) * p.scratch_stride;
     c.dst = (pass_kind == PASS_WRITE_OUT)
                 ? p.out + img_off
-                : p.scratch + (size_t)(2 * (size_t)img + (S.st.dst_sel - 1)) * p.scratch_stride;
+                : p.scratch + (size_t)(2 * (size_t)img + (st.dst_sel - 1)) * p.scratch_stride;
     ImgState* g = p.states + img;
     if (pass_kind == PASS_COUNT) {
       for (int i = tid; i < MAXC * 256; i += NCONS) (&sm->hist[0][0])[i] = 0u;
@@ -1507,7 +1573,9 @@ __global__ void __launch_bounds__(NT, PASS_MIN_CTAS) pass_kernel(const KParams p
     } else {
       run_tile<C, false>(c);
     }
-    mbar_arrive(empty[sl]);  // done with the slot (state, info and staged bytes)
+    mbar_arrive(empty0 + 8 * u);  // done with the unit(s): state, info and staged bytes
+    if (span == 2) mbar_arrive(empty0 + 8 * (u + 1));
+    cu += span;
     if (pass_kind == PASS_WRITE_OUT) continue;
 
     // ---- COUNT / WRITE_SCRATCH: the last tile of the image resumes the chain walk
@@ -1546,26 +1614,30 @@ __global__ void __launch_bounds__(NT, PASS_MIN_CTAS) pass_kernel(const KParams p
 }
 
 template <int C>
-cudaError_t launch_pass_c(const KParams& p, int grid, cudaStream_t stream) {
-  pass_kernel<C><<<grid, NT, sizeof(PassSmem), stream>>>(p);
+cudaError_t launch_pass_c(const KParams& p, const TMap& tm_in, const TMap& tm_scr, int grid, cudaStream_t stream) {
+  pass_kernel<C><<<grid, NT, sizeof(PassSmem<C>), stream>>>(p, tm_in, tm_scr);
   return cudaGetLastError();
 }
 
 template <int C>
 cudaError_t configure_c() {
-  cudaError_t e = cudaFuncSetAttribute(pass_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+  cudaError_t e = cudaFuncSetAttribute(pass_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem<C>));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(pass_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
+
+template <int C>
+int ctas_per_sm_c() { return (sizeof(PassSmem<C>) + 1024) * 2 <= 227 * 1024 ? 2 : 1; }
 
 }  // namespace
 
 // Per-channel-count entry points, one translation unit each (chb_kernels_c<N>.cu) so the four
 // instantiations compile in parallel.
-#define CHB_DEFINE_CHANNEL_ENTRY(C)                                                                   \
-  cudaError_t launch_pass_c##C(const KParams& p, int grid, cudaStream_t stream) {                     \
-    return launch_pass_c<C>(p, grid, stream);                                                         \
-  }                                                                                                   \
-  cudaError_t configure_c##C() { return configure_c<C>(); }
+#define CHB_DEFINE_CHANNEL_ENTRY(C)                                                                           \
+  cudaError_t launch_pass_c##C(const KParams& p, const TMap& a, const TMap& b, int grid, cudaStream_t stream) { \
+    return launch_pass_c<C>(p, a, b, grid, stream);                                                           \
+  }                                                                                                           \
+  cudaError_t configure_c##C() { return configure_c<C>(); }                                                   \
+  int ctas_per_sm_c##C() { return ctas_per_sm_c<C>(); }
 
 }  // namespace chb

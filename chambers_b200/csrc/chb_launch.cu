@@ -3,9 +3,10 @@
 
 namespace chb {
 
-#define CHB_DECL(C)                                                         \
-  cudaError_t launch_pass_c##C(const KParams&, int, cudaStream_t);          \
-  cudaError_t configure_c##C();
+#define CHB_DECL(C)                                                                          \
+  cudaError_t launch_pass_c##C(const KParams&, const TMap&, const TMap&, int, cudaStream_t); \
+  cudaError_t configure_c##C();                                                              \
+  int ctas_per_sm_c##C();
 CHB_DECL(1) CHB_DECL(2) CHB_DECL(3) CHB_DECL(4)
 #undef CHB_DECL
 
@@ -31,14 +32,21 @@ cudaError_t configure_kernels() {
   return configure_c4();
 }
 
-int pass_ctas_per_sm(int) { return 2; }  // __launch_bounds__(288, 2) and ~98 KB of shared memory per CTA
-
-cudaError_t launch_pass(const KParams& p, int C, int grid, cudaStream_t stream) {
+int pass_ctas_per_sm(int C) {  // decided by the shared-memory footprint of pass_kernel<C>
   switch (C) {
-    case 1: return launch_pass_c1(p, grid, stream);
-    case 2: return launch_pass_c2(p, grid, stream);
-    case 3: return launch_pass_c3(p, grid, stream);
-    case 4: return launch_pass_c4(p, grid, stream);
+    case 1: return ctas_per_sm_c1();
+    case 2: return ctas_per_sm_c2();
+    case 3: return ctas_per_sm_c3();
+    default: return ctas_per_sm_c4();
+  }
+}
+
+cudaError_t launch_pass(const KParams& p, const TMap& a, const TMap& b, int C, int grid, cudaStream_t stream) {
+  switch (C) {
+    case 1: return launch_pass_c1(p, a, b, grid, stream);
+    case 2: return launch_pass_c2(p, a, b, grid, stream);
+    case 3: return launch_pass_c3(p, a, b, grid, stream);
+    case 4: return launch_pass_c4(p, a, b, grid, stream);
     default: return cudaErrorInvalidValue;
   }
 }
