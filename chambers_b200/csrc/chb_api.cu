@@ -534,7 +534,7 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   if (!d_in || !d_out) return fail(ctx, CHB_ERR_INVALID, "NULL image pointer");
   const size_t img_bytes = (size_t)H * W * C;
   const chb::TilePlan tp = chb::plan_tiles(H, W);
-  if ((unsigned long long)B * (unsigned long long)tp.n_tiles >= 0xFFFF0000ull)
+  if ((unsigned long long)B * 2ull * (unsigned long long)tp.n_tiles >= 0xFFFF0000ull)
     return fail(ctx, CHB_ERR_UNSUPPORTED, "batch * tiles exceeds the 32-bit work counter");
   const int chain = pol->n_draws * K;
   const int max_levels = chain + 1;  // every op adds at most one pass before the final write
@@ -558,6 +558,18 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   p.max_levels = max_levels;
   p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y; p.tw = tp.tw; p.th = tp.th; p.n_tiles = tp.n_tiles;
   p.force_generic = ctx->force_generic;
+  {
+    int shift = 0;
+    while ((1 << shift) < tp.n_tiles) ++shift;
+    p.tile_shift = shift;
+    p.strip_rows = (H + tp.n_tiles - 1) / tp.n_tiles;
+    const int ub = (C == 3) ? 48 : 16;
+    p.flat_units = (int)(img_bytes / ub);
+    p.flat_upt = (p.flat_units + tp.n_tiles - 1) / tp.n_tiles;
+    p.flags = ((((uintptr_t)d_in & 15) == 0) ? 1 : 0) | ((((uintptr_t)p.out & 15) == 0) ? 2 : 0) |
+              (((img_bytes & 15) == 0) ? 4 : 0) | (((((size_t)W * C) & 15) == 0) ? 8 : 0);
+    if (!(p.flags & 4)) p.flags &= ~3;  // images that are not whole 16-byte units are not aligned beyond the first
+  }
   // gather tiles fetch their source bounding box as one 3-D tensor-map box (rows must be whole 16-byte units)
   chb::TMap tm_in, tm_scr;
   memset(&tm_in, 0, sizeof(tm_in));

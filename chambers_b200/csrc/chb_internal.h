@@ -1,6 +1,7 @@
 // Internal (non-ABI) declarations shared by chb_api.cu (host) and the kernel translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "chambers_aug.h"
@@ -53,11 +54,12 @@ struct alignas(16) TileState {  // what a tile needs; loaded whole by every tile
   int32_t _pad[3];
   Spatial sp[CHB_MAX_CHAIN];
   Spatial kgeo;  // K_BILINEAR: the warp (t, fill_mode, color[0] = fill)
+  int32_t _pad2[2];
   uint8_t l1[MAXC][256];
   uint8_t l2[MAXC][256];
-  int32_t _pad2[2];
 };
 static_assert(sizeof(TileState) % 16 == 0, "TileState must be a whole number of 16-byte units");
+static_assert(offsetof(TileState, l1) % 16 == 0, "the LUTs must start on a 16-byte boundary");
 
 struct ProgRec {
   int32_t table_index, negate, cy, cx;
@@ -95,6 +97,11 @@ struct KParams {
   int tiles_x, tiles_y, tw, th, n_tiles;
   int force_generic;                  // debugging: route every tile through the scalar executor
   int use_tmap, box_rows, box_bytes;  // gather tiles: one tensor-map box of box_rows x box_bytes per tile
+  // per-launch constants of the tile planner
+  int tile_shift;                     // items are (entry << tile_shift) | tile
+  int strip_rows;                     // rows of a strip tile: ceil(H / n_tiles)
+  int flat_units, flat_upt;           // flat runs: units per image (48 bytes for C = 3, else 16) and per tile
+  int flags;                          // 1: in is 16-byte aligned, 2: out is, 4: images are whole 16-byte units, 8: rows are
 };
 
 // Opaque copy of a CUtensorMap (cuda.h), passed to the pass kernel as a __grid_constant__ parameter.

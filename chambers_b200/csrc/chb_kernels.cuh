@@ -776,12 +776,14 @@ __device__ void exec_flat(const TC<C>& c) {
           for (int ch = 0; ch < C; ++ch) v[ch] = t.l1[ch][v[ch]];
         }
       } else if (C == 3) {
+        if (use1) {
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) v[ch] = t.l1[ch][v[ch]];
+          for (int ch = 0; ch < C; ++ch) v[ch] = t.l1[ch][v[ch]];
+        }
         uint32_t R, G, B;
         color_pixel_f((float)v[0], (float)v[1], (float)v[2], f, R, G, B);
         v[0] = (int)R; v[1] = (int)G; v[2] = (int)B;
-        if (!COUNT) {
+        if (!COUNT && use2) {
 #pragma unroll
           for (int ch = 0; ch < C; ++ch) v[ch] = t.l2[ch][v[ch]];
         }
@@ -1005,15 +1007,22 @@ __device__ void gather_list(const TC<C>& c) {
   }
 }
 
-// One TMA store per row of a tw x th output staging tile whose top-left pixel is (x0, y0).
+// Copies a tw x th output staging tile (top-left pixel (x0, y0)) to the image with 16-byte vectors:
+// a row of the tile is a whole number of them, a warp writes 512 contiguous-by-row bytes per store.
+// (One TMA bulk store per row was measured first: 64 small stores per tile drained so slowly that
+// the wait before reusing the staging tile became the top stall, profiles/r01_v5.)
 template <int C>
 __device__ __forceinline__ void store_tile_rows(const TC<C>& c, uint32_t ostage, int x0, int y0, int tw, int th) {
-  if (c.tid < 32) {
-    const int rowbytes = c.W * C;
-    uint8_t* dbase = c.dst + ((size_t)y0 * c.W + x0) * C;
-    const uint32_t rb = (uint32_t)(tw * C);
-    for (int rr = c.tid; rr < th; rr += 32) bulk_store(dbase + (size_t)rr * rowbytes, ostage + rr * rb, rb);
-    bulk_commit();
+  const int rowbytes = c.W * C;
+  uint8_t* dbase = c.dst + ((size_t)y0 * c.W + x0) * C;
+  const int rb = tw * C;
+  const int n16 = rb >> 4;
+  int rr = c.tid / n16, q = c.tid - rr * n16;
+  const int drr = NCONS / n16, dq = NCONS - drr * n16;
+  for (; rr < th;) {
+    *reinterpret_cast<uint4*>(dbase + (size_t)rr * rowbytes + (q << 4)) = lds_v4(ostage + rr * rb + (q << 4));
+    q += dq; rr += drr;
+    if (q >= n16) { q -= n16; ++rr; }
   }
 }
 
@@ -1024,7 +1033,7 @@ __device__ void exec_gather(const TC<C>& c) {
   if (t.n_sp == 1 && t.sp[0].type == SP_GEOM) gather_single<C, COUNT>(c);
   else gather_list<C, COUNT>(c);
   if (!COUNT) {
-    store_barrier(c);
+    store_barrier(c);  // also flips the staging tile: the next item writes the other one
     store_tile_rows(c, c.ostage, in.x0, in.y0, in.x1 - in.x0, in.y1 - in.y0);
   }
 }
@@ -1045,7 +1054,7 @@ __device__ void exec_gather_sharp(const TC<C>& c) {
   const bool box_empty = in.rows <= 0;
   const int pitch = in.pitch;
   const uint32_t base0 = c.data - (uint32_t)(by0 * pitch + in.bxb0);
-  const bool use2 = !t.l2_id;
+  const bool use1 = !t.l1_id, use2 = !t.l2_id;  // identity LUTs are not even copied into the unit
   const float f = t.kfactor;
   const float k1 = __int_as_float(0x3d9d89d9);  // float32(1)/float32(13)
   const float k5 = __int_as_float(0x3ec4ec4f);  // float32(5)/float32(13)
@@ -1081,8 +1090,10 @@ __device__ void exec_gather_sharp(const TC<C>& c) {
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) v[ch] = __ldg(px + ch);
           }
+          if (use1) {
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(c.l1a + ch * 256 + v[ch]);
+            for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(c.l1a + ch * 256 + v[ch]);
+          }
         } else {
 #pragma unroll
           for (int ch = 0; ch < C; ++ch) v[ch] = (uint32_t)t.sp[k].color[ch];
@@ -1125,18 +1136,10 @@ __device__ void exec_gather_sharp(const TC<C>& c) {
         }
       }
     }
-    if (!COUNT) {
-      fence_proxy_async();
-      cons_sync();
-      store_tile_rows(c, obuf, in.x0, ya, tw, yb - ya);
-    } else {
-      cons_sync();
-    }
-  }
-  if (!COUNT) {
-    stores_drained(c.tid);  // the next item's staging tile overlaps these buffers
     cons_sync();
+    if (!COUNT) store_tile_rows(c, obuf, in.x0, ya, tw, yb - ya);
   }
+  cons_sync();  // the next item's staging tile overlaps these buffers
 }
 
 // ========================================================================== sharpness executor
@@ -1290,50 +1293,55 @@ struct TilePlanD {
   int src_sel;
 };
 
-// Decides how a tile is executed.  Every lane of the producer warp computes the same plan.
+// Decides how a tile is executed.  Every lane of the producer warp computes the same plan.  This
+// runs once per tile on a single warp, so everything that does not depend on the tile (strip
+// height, flat units per tile, alignment of the batch) comes precomputed in KParams.
 template <int C>
-__device__ void plan_tile(const KParams& p, const TileState& t, int img, int tile, TilePlanD& d) {
+__device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, int img, int tile, TilePlanD& d) {
+  constexpr int UB = (C == 3) ? 48 : 16;
   const int H = p.H, W = p.W;
-  const int img_bytes = H * W * C;
   const int pass_kind = t.pass_kind;
   const bool count = pass_kind == PASS_COUNT;
-  const size_t img_off = (size_t)img * img_bytes;
-  const uint8_t* src = (t.src_sel == 0) ? p.in + img_off
-                                       : p.scratch + (size_t)(2 * (size_t)img + (t.src_sel - 1)) * p.scratch_stride;
-  const uint8_t* dst = (pass_kind == PASS_WRITE_OUT)
-                           ? p.out + img_off
-                           : p.scratch + (size_t)(2 * (size_t)img + (t.dst_sel - 1)) * p.scratch_stride;
-  const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (count || (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-  const bool rows16 = ((W * C) & 15) == 0 && aligned;
-  const bool fast = !p.force_generic;
   const int kmode = t.kmode, n_sp = t.n_sp;
+  const bool src16 = (t.src_sel != 0) || (p.flags & 1);                       // scratch images are 256-byte aligned
+  const bool dst16 = count || (pass_kind != PASS_WRITE_OUT) || (p.flags & 2);
+  const bool fast = !p.force_generic;
+  SlotInfo& in = d.in;
+  in.cls = CLS_GENERIC; in.img = img; in.tile = tile; in.pass_kind = pass_kind;
+  in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0; in.rowb = 0; in.pitch = 16; in.rows = 0;
+  in.span = 1; in._pad = 0; in.fill = 0; in.paint = 0;
+  d.tx_bytes = 0;
+  d.src_sel = t.src_sel;
+  const bool plainK = (kmode == K_NONE || kmode == K_COLOR);
+
+  // ---- the common case first: no spatial op, a flat run of units
+  if (plainK && n_sp == 0 && fast && (p.flags & 4) && src16 && dst16) {
+    const int u0 = min(p.flat_units, tile * p.flat_upt), u1 = min(p.flat_units, u0 + p.flat_upt);
+    in.cls = CLS_FLAT;
+    in.x0 = u0; in.x1 = u1; in.y0 = 0; in.y1 = 0;
+    d.tx_bytes = (uint32_t)(u1 - u0) * UB;  // <= 4096 * C <= one unit
+    return;
+  }
+
   const int rowbytes = W * C;
+  const bool rows16 = (p.flags & 8) && src16 && dst16;
   // tile -> region.  The partition depends only on per-image state, so all tiles of a pass agree.
   Rect strip, box;
+  strip.x0 = 0; strip.x1 = W; strip.y0 = min(H, tile * p.strip_rows); strip.y1 = min(H, strip.y0 + p.strip_rows);
   {
-    const int R = (H + p.n_tiles - 1) / p.n_tiles;
-    strip.x0 = 0; strip.x1 = W; strip.y0 = min(H, tile * R); strip.y1 = min(H, strip.y0 + R);
     const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
     box.x0 = min(W, tx * p.tw); box.x1 = min(W, box.x0 + p.tw);
     box.y0 = min(H, ty * p.th); box.y1 = min(H, box.y0 + p.th);
   }
-  SlotInfo& in = d.in;
-  in.cls = CLS_GENERIC; in.img = img; in.tile = tile; in.pass_kind = pass_kind;
-  in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0; in.rowb = 0; in.pitch = 16; in.rows = 0;
-  in.span = 1; in._pad = 0;
   Rect reg = (n_sp > 0) ? box : strip;
-  d.tx_bytes = 0;
-  d.src_sel = t.src_sel;
-
   bool masks_only = n_sp > 0;
   for (int k = 0; k < n_sp; ++k) masks_only = masks_only && (t.sp[k].type == SP_MASK);
-  in.fill = 0; in.paint = 0;
   for (int ch = 0; ch < C; ++ch) in.fill |= (uint32_t)(t.sp[0].color[ch] & 255) << (8 * ch);
 
   // Source bounding box of output rectangle q: push its corners back through every warp of the
   // list.  Affine maps take extremes at corners; one pixel of margin per stage covers the rounding
   // of that stage.  The box is fetched as ONE tensor-map box of p.box_rows x p.box_bytes starting at
-  // word (bx0 * C) / 4 of row by0; returns false if the bounding box does not fit in it.
+  // the 16-byte aligned byte bxb0 of row by0; returns false if the bounding box does not fit in it.
   auto source_box = [&](const Rect q) -> bool {
     if (!p.use_tmap) return false;
     float minx = (float)q.x0, maxx = (float)(q.x1 - 1), miny = (float)q.y0, maxy = (float)(q.y1 - 1);
@@ -1365,20 +1373,17 @@ __device__ void plan_tile(const KParams& p, const TileState& t, int img, int til
     return true;
   };
 
-  if ((kmode == K_NONE || kmode == K_COLOR) && (n_sp == 0 || (masks_only && !count))) {
-    if (fast && (img_bytes & 15) == 0 && aligned) {
-      constexpr int UB = (C == 3) ? 48 : 16;
-      const int n_units = img_bytes / UB;
-      const int upt = (n_units + p.n_tiles - 1) / p.n_tiles;
-      const int u0 = min(n_units, tile * upt), u1 = min(n_units, u0 + upt);
+  if (plainK && (n_sp == 0 || (masks_only && !count))) {
+    if (fast && (p.flags & 4) && src16 && dst16) {  // CutOut only: a flat run with the rectangles painted over it
+      const int u0 = min(p.flat_units, tile * p.flat_upt), u1 = min(p.flat_units, u0 + p.flat_upt);
       in.cls = CLS_FLAT;
       in.paint = n_sp;
       reg.x0 = u0; reg.x1 = u1; reg.y0 = 0; reg.y1 = 0;
-      d.tx_bytes = (uint32_t)(u1 - u0) * UB;  // <= 4096 * C <= one unit
+      d.tx_bytes = (uint32_t)(u1 - u0) * UB;
     } else {
       reg = strip;  // all tiles of the pass take this branch together
     }
-  } else if ((kmode == K_NONE || kmode == K_COLOR) && fast && rows16 && t.sp_fast) {
+  } else if (plainK && fast && rows16 && t.sp_fast) {
     if (source_box(box)) {
       in.cls = CLS_GATHER;
       d.tx_bytes = (uint32_t)(in.rows * in.rowb);
@@ -1426,7 +1431,8 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   const int H = p.H, W = p.W;
   const int img_bytes = H * W * C;
   const unsigned n_entries = (L == 0) ? (unsigned)p.B : __ldcg(p.counters + L);
-  const unsigned n_items = n_entries * (unsigned)p.n_tiles;
+  // an item is (entry << tile_shift) | tile; tile indices >= n_tiles (padding to a power of two) are skipped
+  const unsigned n_items = n_entries << p.tile_shift;
   const uint32_t full0 = smem_addr(&sm->full[0]), empty0 = smem_addr(&sm->empty[0]);
   const uint32_t stbar0 = smem_addr(&sm->stbar[0]);
   if (tid == 0) {
@@ -1448,7 +1454,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     };
     auto image_of = [&](unsigned item) -> int {
       if (item >= n_items) return -1;
-      const int entry = (int)(item / (unsigned)p.n_tiles);
+      const int entry = (int)(item >> p.tile_shift);
       return (L == 0) ? entry : __ldcg(p.lists + (size_t)L * p.B + entry);
     };
     auto fetch_state = [&](int img, int buf) {
@@ -1479,7 +1485,11 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       const unsigned item3 = claim();
       mbar_wait(stbar0 + 8 * (k & 1), (k >> 1) & 1u);
       const TileState& st = sm->stg[k & 1];
-      const int tile = (int)(item0 % (unsigned)p.n_tiles);
+      const int tile = (int)(item0 & ((1u << p.tile_shift) - 1u));
+      if (tile >= p.n_tiles) {  // padding item
+        item0 = item1; img0 = img1; item1 = item2; img1 = img2; item2 = item3;
+        continue;
+      }
       TilePlanD d;
       plan_tile<C>(p, st, img0, tile, d);
       if (d.in.span == 2 && (pu & (NU - 1)) == NU - 1) {  // a double tile may not wrap: pad the ring
@@ -1492,9 +1502,21 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       take_unit(u);
       if (d.in.span == 2) take_unit(u + 1);
       pu += d.in.span;
-      // hand the state to the consumers (the prefetch buffer is reused two items later)
-      for (int i = lane; i < TILE_VECS; i += 32)
-        reinterpret_cast<uint4*>(&sm->ust[u])[i] = reinterpret_cast<const uint4*>(&st)[i];
+      // hand the state to the consumers (the prefetch buffer is reused two items later): the
+      // header and the spatial list always, a LUT only if it is not the identity or the scalar
+      // executor (which indexes the tables unconditionally) will run.
+      {
+        constexpr int HDR_VECS = (int)(offsetof(TileState, l1) / 16);
+        constexpr int LUT_VECS = MAXC * 256 / 16;
+        const uint4* sv = reinterpret_cast<const uint4*>(&st);
+        uint4* dv = reinterpret_cast<uint4*>(&sm->ust[u]);
+        for (int i = lane; i < HDR_VECS; i += 32) dv[i] = sv[i];
+        const bool all = d.in.cls == CLS_GENERIC;
+        if (all || !st.l1_id)
+          for (int i = lane; i < LUT_VECS; i += 32) dv[HDR_VECS + i] = sv[HDR_VECS + i];
+        if (all || !st.l2_id)
+          for (int i = lane; i < LUT_VECS; i += 32) dv[HDR_VECS + LUT_VECS + i] = sv[HDR_VECS + LUT_VECS + i];
+      }
       __syncwarp();
       if (lane == 0) {
         sm->info[u] = d.in;
