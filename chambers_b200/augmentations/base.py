@@ -197,7 +197,10 @@ def run_policy(inputs, transforms, n_draws, elementwise, seed, call_counter, bat
             raise ValueError("out must be a contiguous CUDA uint8 tensor of the input's shape")
         d_replay = d_record = None
         if replay is not None:
-            d_replay = torch.as_tensor(np.ascontiguousarray(replay, dtype=np.int32)).reshape(sched_shape).to(x.device)
+            if isinstance(replay, torch.Tensor) and replay.is_cuda:  # already resident: no host round trip
+                d_replay = replay.to(device=x.device, dtype=torch.int32).reshape(sched_shape).contiguous()
+            else:
+                d_replay = torch.as_tensor(np.ascontiguousarray(replay, dtype=np.int32)).reshape(sched_shape).to(x.device)
         if record:
             d_record = torch.zeros(sched_shape, dtype=torch.int32, device=x.device)
         with torch.cuda.device(dev):

@@ -41,6 +41,7 @@ constexpr int NT = NCONS + 32;                   // + one producer warp
 constexpr int PLAN_NT = 128;                     // threads per plan CTA
 constexpr int NU = 4;                            // pipeline units per CTA; a tile occupies one or two
 constexpr int UNIT_BYTES = 16 * 1024;            // staged source bytes of one unit
+constexpr int COUNT_GROUP = 4;                   // flat COUNT tiles per histogram flush (one item = 4 consecutive tiles)
 constexpr int LHIST_CH_BYTES = 64 * 32 * 4;      // lane-private u8x4 histogram of one channel
 constexpr int STATE_VECS = (int)(offsetof(ImgState, hist) / 16);   // everything but the histogram
 constexpr int TILE_VECS = (int)(sizeof(TileState) / 16);
@@ -418,9 +419,11 @@ struct alignas(16) SlotInfo {  // written by the producer, read by the consumers
   int32_t bx0, bx1, by0, by1;        // GATHER: source bounding box (inclusive); SHARP: by0 = first staged row
   int32_t bxb0, rowb, pitch, rows;   // GATHER: first staged byte of a row, staged bytes per row, pitch, rows
   int32_t x0, x1, y0, y1;            // region of the tile (box or strip); FLAT: x0 / x1 = first / last unit
-  uint32_t fill;                     // GATHER: the colour bytes of spatial entry 0
+  uint32_t fillc[2];                 // GATHER: the colour bytes of the last / last-but-one spatial entry
   int32_t paint;                     // FLAT: the spatial list is masks only; paint them over the result
   int32_t span;                      // units this tile occupies (1 or 2)
+  int32_t sharp_rows;                // SHARP classes: rows per sub-strip of the column walk
+  int32_t first, last;               // COUNT: first / last tile of a group that shares one histogram flush
   int32_t _pad;
 };
 
@@ -826,29 +829,37 @@ struct QuadWalk {
 };
 
 // Spatial list pending (constant-fill nearest warps and masks), K in {none, Color}.  The producer
-// has staged the source bounding box of the tile (info->bx0.., one TMA row copy per row); pixels are
-// gathered from it four at a time into the output staging tile, which leaves as one TMA store per row.
+// has staged the source bounding box of the tile (one tensor-map box); pixels are gathered from it
+// four at a time into the output staging tile.
 //
-// Fast form: the list is ONE warp (by far the most common case).  The x-dependent products of the
-// four pixels of a thread's quad column stay in registers for the whole tile (a thread keeps its
-// column when the quads per row divide the thread count), so a pixel costs four float adds, the
-// 5-instruction index/bounds step per coordinate, an address and C byte loads.
-template <int C, bool COUNT>
-__device__ void gather_single(const TC<C>& c) {
+// Fast form: the list holds ONE or TWO entries (all a RandAugment(N=2) chain can produce).  Entry
+// "a" = sp[n_sp-1] was applied last and is evaluated first on the output coordinate; if it is a warp,
+// the x-dependent products of the four pixels of a thread's quad column stay in registers for the
+// whole tile (a thread keeps its column when the quads per row divide the thread count), so its
+// coordinates cost four float adds plus the 5-instruction index/bounds step each.  Entry "b" =
+// sp[n_sp-2], if any, is evaluated on the integer coordinate that "a" produced.
+template <int C, bool COUNT, bool TWO>
+__device__ void gather_fast(const TC<C>& c) {
   const TileState& t = *c.t;
   const SlotInfo& in = *c.info;
   const int H = c.H, W = c.W;
   const int tw = in.x1 - in.x0, th = in.y1 - in.y0;
-  const Spatial& e = t.sp[0];
-  const float t0 = e.t[0], t1 = e.t[1], t2 = e.t[2], t3 = e.t[3], t4 = e.t[4], t5 = e.t[5];
+  const int n_sp = t.n_sp;
+  const Spatial& ea = t.sp[n_sp - 1];
+  const Spatial& eb = t.sp[TWO ? n_sp - 2 : 0];
+  constexpr bool two = TWO;
+  const bool a_geom = !TWO || ea.type == SP_GEOM;  // the one-entry form is only used for a warp
+  const bool b_geom = TWO && eb.type == SP_GEOM;
+  const float t0 = ea.t[0], t1 = ea.t[1], t2 = ea.t[2], t3 = ea.t[3], t4 = ea.t[4], t5 = ea.t[5];
+  const float u0 = eb.t[0], u1 = eb.t[1], u2 = eb.t[2], u3 = eb.t[3], u4 = eb.t[4], u5 = eb.t[5];
+  const int ay0 = ea.y0, ay1 = ea.y1, ax0 = ea.x0, ax1 = ea.x1;
+  const int by0m = eb.y0, by1m = eb.y1, bx0m = eb.x0, bx1m = eb.x1;
   const int kmode = t.kmode;
   const bool use1 = !t.l1_id, use2 = !t.l2_id;
   const bool plain = (kmode == K_NONE) && (COUNT || !use1);  // staged bytes are the result
   const float f = t.kfactor;
-  uint32_t fill = 0;
-#pragma unroll
-  for (int ch = 0; ch < C; ++ch) fill |= (uint32_t)(e.color[ch] & 255) << (8 * ch);
-  const uint32_t fill_a = smem_addr(&in.fill);  // the fill pixel, so that a miss is just another address
+  const uint32_t fill_a = in.fillc[0], fill_b = in.fillc[1];
+  const uint32_t fa_addr = smem_addr(&in.fillc[0]), fb_addr = smem_addr(&in.fillc[1]);  // a miss is just another address
   const int pitch = in.pitch;
   // staged byte of source pixel (ix, iy), channel ch: base0 + iy * pitch + ix * C + ch
   const uint32_t base0 = c.data - (uint32_t)(in.by0 * pitch + in.bxb0);
@@ -864,21 +875,43 @@ __device__ void gather_single(const TC<C>& c) {
     }
   };
   xterms(q.rq);
-  uint32_t n_fill = 0;
+  uint32_t n_fill_a = 0, n_fill_b = 0;
   for (; q.ry < th; q.next()) {
     if (!fixed_col) xterms(q.rq);
-    const float fy = small_uint_to_float((uint32_t)(in.y0 + q.ry));
+    const int y = in.y0 + q.ry;
+    const int xq = in.x0 + (q.rq << 2);
+    const float fy = small_uint_to_float((uint32_t)y);
     const float t1y = __fmul_rn(t1, fy), t4y = __fmul_rn(t4, fy);
     uint32_t o[C];
 #pragma unroll
     for (int w = 0; w < C; ++w) o[w] = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int ix, iy;
-      const bool inx = src_index(__fadd_rn(__fadd_rn(ax[i], t1y), t2), W, ix);
-      const bool iny = src_index(__fadd_rn(__fadd_rn(bx[i], t4y), t5), H, iy);
-      const bool inside = inx && iny;
-      const uint32_t a = inside ? base0 + (uint32_t)(iy * pitch + ix * C) : fill_a;
+      int ix = xq + i, iy = y;
+      bool hit_a, hit_b = false;  // the pixel shows the colour of entry a / b
+      if (a_geom) {
+        int jx, jy;
+        const bool inx = src_index(__fadd_rn(__fadd_rn(ax[i], t1y), t2), W, jx);
+        const bool iny = src_index(__fadd_rn(__fadd_rn(bx[i], t4y), t5), H, jy);
+        hit_a = !(inx && iny);
+        ix = jx; iy = jy;
+      } else {
+        hit_a = (iy >= ay0) && (iy < ay1) && (ix >= ax0) && (ix < ax1);
+      }
+      if (two && !hit_a) {
+        if (b_geom) {
+          const float gx = small_uint_to_float((uint32_t)ix), gy = small_uint_to_float((uint32_t)iy);
+          int jx, jy;
+          const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(u0, gx), __fmul_rn(u1, gy)), u2), W, jx);
+          const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(u3, gx), __fmul_rn(u4, gy)), u5), H, jy);
+          hit_b = !(inx && iny);
+          ix = jx; iy = jy;
+        } else {
+          hit_b = (iy >= by0m) && (iy < by1m) && (ix >= bx0m) && (ix < bx1m);
+        }
+      }
+      const bool inside = !(hit_a || hit_b);
+      const uint32_t a = inside ? base0 + (uint32_t)(iy * pitch + ix * C) : (hit_a ? fa_addr : fb_addr);
       uint32_t v[C];
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(a + ch);
@@ -898,16 +931,19 @@ __device__ void gather_single(const TC<C>& c) {
           }
         }
         if (!COUNT) {
+          const uint32_t fillv = hit_a ? fill_a : fill_b;
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) v[ch] = inside ? v[ch] : byte_of(fill, ch);
+          for (int ch = 0; ch < C; ++ch) v[ch] = inside ? v[ch] : byte_of(fillv, ch);
         }
       }
       if (COUNT) {
         if (inside) {
 #pragma unroll
           for (int ch = 0; ch < C; ++ch) count_value(c, ch, v[ch]);
+        } else if (hit_a) {
+          ++n_fill_a;
         } else {
-          ++n_fill;
+          ++n_fill_b;
         }
       } else {
 #pragma unroll
@@ -923,7 +959,10 @@ __device__ void gather_single(const TC<C>& c) {
       for (int w = 0; w < C; ++w) sts_u32(oa + 4 * w, o[w]);
     }
   }
-  if (COUNT && n_fill) atomicAdd(&c.sm->color_cnt[0], n_fill);
+  if (COUNT) {
+    if (n_fill_a) atomicAdd(&c.sm->color_cnt[n_sp - 1], n_fill_a);
+    if (TWO && n_fill_b) atomicAdd(&c.sm->color_cnt[n_sp - 2], n_fill_b);
+  }
 }
 
 // General form: any list of constant-fill warps and masks.
@@ -1030,7 +1069,8 @@ template <int C, bool COUNT>
 __device__ void exec_gather(const TC<C>& c) {
   const TileState& t = *c.t;
   const SlotInfo& in = *c.info;
-  if (t.n_sp == 1 && t.sp[0].type == SP_GEOM) gather_single<C, COUNT>(c);
+  if (t.n_sp == 1 && t.sp[0].type == SP_GEOM) gather_fast<C, COUNT, false>(c);
+  else if (t.n_sp == 2) gather_fast<C, COUNT, true>(c);
   else gather_list<C, COUNT>(c);
   if (!COUNT) {
     store_barrier(c);  // also flips the staging tile: the next item writes the other one
@@ -1038,11 +1078,98 @@ __device__ void exec_gather(const TC<C>& c) {
   }
 }
 
+// ========================================================================== sharpness executors
+// tfa.image.sharpness (oracle/ops.py sharpness) on rows held in shared memory.  One thread owns one
+// word column (4 output bytes) of a run of rows and walks down it with the float32 products
+// (value x 1/13) of the 4 + 2C-byte windows of the previous, current and next row in registers, so
+// every input byte is converted and multiplied once per column instead of nine times.  The row
+// loop is unrolled by three so that the three windows rotate by renaming, and border bytes are a
+// select, not a branch: the walk is straight-line float adds in the oracle's row-major order.
+//   col      shared address of this column's word in the row ABOVE the first output row
+//   pitch    bytes between rows
+//   n        output rows
+//   has_prev / has_next   the words left / right of the column exist (they hold the neighbours)
+//   bmask    bit b set: byte b of the column lies in the first / last pixel of the IMAGE row
+//   emit(r, word)         receives the sharpened word of output row r (0-based)
+template <int C, class Emit>
+__device__ __forceinline__ void sharp_walk(uint32_t col, int pitch, int n, bool has_prev, bool has_next, uint32_t bmask,
+                                           float f, Emit emit) {
+  constexpr int NB = 4 + 2 * C;  // window bytes per row
+  const float k1 = __int_as_float(0x3d9d89d9);  // float32(1)/float32(13)
+  const float k5 = __int_as_float(0x3ec4ec4f);  // float32(5)/float32(13)
+  float pa[NB], pb[NB], pc[NB];  // products of three consecutive rows
+  float ca[4], cb[4], cc[4];     // float values of their centre bytes
+  auto load_row = [&](uint32_t ra, float* pr, float* cv) {
+    const uint32_t w1 = lds_u32(ra);
+    const uint32_t w0 = has_prev ? lds_u32(ra - 4) : 0u;
+    const uint32_t w2 = has_next ? lds_u32(ra + 4) : 0u;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int wb = 4 - C + j;  // byte index in the 12-byte (w0, w1, w2) window
+      const uint32_t wsel = (wb < 4) ? w0 : (wb < 8) ? w1 : w2;
+      const float fv = byte_to_float(wsel, wb & 3);
+      pr[j] = __fmul_rn(fv, k1);
+      if (j >= C && j < C + 4) cv[j - C] = fv;
+    }
+  };
+  // rows above / at / below: window index b + C is the byte itself, b and b + 2C its left / right neighbours
+  auto step = [&](const float* up, const float* mid, const float* midc, const float* dn, int r) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const float orig = midc[b];
+      float acc = up[b];
+      acc = __fadd_rn(acc, up[b + C]);
+      acc = __fadd_rn(acc, up[b + 2 * C]);
+      acc = __fadd_rn(acc, mid[b]);
+      acc = __fadd_rn(acc, __fmul_rn(orig, k5));
+      acc = __fadd_rn(acc, mid[b + 2 * C]);
+      acc = __fadd_rn(acc, dn[b]);
+      acc = __fadd_rn(acc, dn[b + C]);
+      acc = __fadd_rn(acc, dn[b + 2 * C]);
+      float deg = __fadd_rn(__fadd_rz(acc, 8388608.0f), -8388608.0f);  // float(trunc(acc))
+      deg = ((bmask >> b) & 1u) ? orig : deg;                           // border pixels keep the original
+      const uint32_t res = sharp_blend(deg, orig, f);
+      o = (b == 0) ? res : put_byte(o, res, b);
+    }
+    emit(r, o);
+  };
+  load_row(col, pa, ca);
+  load_row(col + pitch, pb, cb);
+  uint32_t ra = col + 2 * pitch;
+  for (int r = 0; r < n; r += 3) {
+    load_row(ra, pc, cc);
+    step(pa, pb, cb, pc, r);
+    if (r + 1 < n) {
+      load_row(ra + pitch, pa, ca);
+      step(pb, pc, cc, pa, r + 1);
+    }
+    if (r + 2 < n) {
+      load_row(ra + 2 * pitch, pb, cb);
+      step(pc, pa, ca, pb, r + 2);
+    }
+    ra += 3 * pitch;
+  }
+}
+
+// Splits `inner` rows into sub-strips so that (columns x sub-strips) keeps every thread busy:
+// minimise rounds * (rows per sub-strip + 2 halo rows).  Returns rows per sub-strip.  Runs once per
+// tile on the producer warp (the result travels in SlotInfo::sharp_rows).
+__device__ __forceinline__ int sharp_split(int columns, int inner) {
+  int best_s = 1, best_cost = 0x7FFFFFFF;
+  for (int S = 1; S <= 8 && S <= inner; ++S) {
+    const int rounds = (columns * S + NCONS - 1) / NCONS;
+    const int cost = rounds * ((inner + S - 1) / S + 2);
+    if (cost < best_cost) { best_cost = cost; best_s = S; }
+  }
+  return (inner + best_s - 1) / best_s;
+}
+
 // Sharpness of a gathered image (K == Sharpness with a spatial list pending): the tile's virtual
 // pre-image (spatial list -> l1) is gathered with a one-pixel halo into shared memory, half a tile
-// at a time, and sharpened from there.  Rare (a warp or CutOut followed by Sharpness), so the 3x3
-// window is evaluated per pixel; what matters is that it no longer runs on the scalar executor.
-// R region: [halo tile | output half 0 | output half 1].
+// at a time, and sharpened from there with the column walk.
+// R region: [halo tile | output half 0 | output half 1].  A halo row is laid out so that the
+// tile's first pixel starts on a word: 4 - C pad bytes, the left halo pixel, the tile, the right halo.
 template <int C, bool COUNT>
 __device__ void exec_gather_sharp(const TC<C>& c) {
   const TileState& t = *c.t;
@@ -1056,14 +1183,14 @@ __device__ void exec_gather_sharp(const TC<C>& c) {
   const uint32_t base0 = c.data - (uint32_t)(by0 * pitch + in.bxb0);
   const bool use1 = !t.l1_id, use2 = !t.l2_id;  // identity LUTs are not even copied into the unit
   const float f = t.kfactor;
-  const float k1 = __int_as_float(0x3d9d89d9);  // float32(1)/float32(13)
-  const float k5 = __int_as_float(0x3ec4ec4f);  // float32(5)/float32(13)
   const int tw = in.x1 - in.x0, th = in.y1 - in.y0;
   const int hh = (th + 1) >> 1;              // rows per half
   const int vw = tw + 2;                     // halo tile width in pixels
+  const int vpitch = (4 + (tw + 1) * C + 3) & ~3;
   const uint32_t vbuf = c.r;
-  const uint32_t vbytes = (uint32_t)(((hh + 2) * vw * C + 15) & ~15);
+  const uint32_t vbytes = (uint32_t)(((hh + 2) * vpitch + 15) & ~15);
   const uint32_t obytes = (uint32_t)(hh * tw * C);
+  const int wpt = (tw * C) >> 2;             // output words per tile row
   stores_drained(c.tid);  // the whole R region is used here
   cons_sync();
   for (int half = 0; half < 2; ++half) {
@@ -1099,41 +1226,47 @@ __device__ void exec_gather_sharp(const TC<C>& c) {
           for (int ch = 0; ch < C; ++ch) v[ch] = (uint32_t)t.sp[k].color[ch];
         }
       }
+      const uint32_t va = vbuf + (uint32_t)(vy * vpitch + 4 - C + vx * C);
 #pragma unroll
-      for (int ch = 0; ch < C; ++ch)
-        asm volatile("st.shared.u8 [%0], %1;" ::"r"(vbuf + (uint32_t)(i * C + ch)), "r"(v[ch]) : "memory");
+      for (int ch = 0; ch < C; ++ch) asm volatile("st.shared.u8 [%0], %1;" ::"r"(va + ch), "r"(v[ch]) : "memory");
     }
     cons_sync();
     // phase 2: sharpen tw x (yb - ya) pixels out of the halo tile
     const uint32_t obuf = c.r + vbytes + half * obytes;
-    const int np = (yb - ya) * tw;
-    for (int i = c.tid; i < np; i += NCONS) {
-      const int ry = i / tw, rx = i - ry * tw;
-      const int y = ya + ry, x = in.x0 + rx;
-      const bool interior = y > 0 && y < H - 1 && x > 0 && x < W - 1;
-      const uint32_t ctr = vbuf + (uint32_t)(((ry + 1) * vw + rx + 1) * C);
+    auto emit_row = [&](int y, int xw, uint32_t o) {  // y: image row; xw: word column of the tile
+      const int ph = (C == 3) ? (xw % 3) : 0;         // tile rows start at channel 0 (x0 * C is a multiple of 4 * C ... of 3)
+      if (COUNT) {
 #pragma unroll
-      for (int ch = 0; ch < C; ++ch) {
-        const uint32_t orig = lds_u8(ctr + ch);
-        float deg = small_uint_to_float(orig);
-        if (interior) {
-          float acc = 0.0f;
+        for (int b = 0; b < 4; ++b) count_value(c, (ph + b) % C, byte_of(o, b));
+      } else {
+        if (use2)
+          o = map_word(o, c.l2a + (uint32_t)((ph + 0) % C) * 256u, c.l2a + (uint32_t)((ph + 1) % C) * 256u,
+                       c.l2a + (uint32_t)((ph + 2) % C) * 256u, c.l2a + (uint32_t)((ph + 3) % C) * 256u);
+        sts_u32(obuf + (uint32_t)((y - ya) * (tw * C) + (xw << 2)), o);
+      }
+    };
+    // image rows 0 and H-1 keep the original
+    for (int y = ya; y < yb; ++y)
+      if (y == 0 || y == H - 1)
+        for (int xw = c.tid; xw < wpt; xw += NCONS) emit_row(y, xw, lds_u32(vbuf + (uint32_t)((y - ya + 1) * vpitch + 4 + (xw << 2))));
+    const int in0 = max(ya, 1), in1 = min(yb, H - 1);
+    const int inner = in1 - in0;
+    if (inner > 0) {
+      const int R = in.sharp_rows;
+      const int n_strips = (inner + R - 1) / R;
+      const int n_items = wpt * n_strips;
+      for (int item = c.tid; item < n_items; item += NCONS) {
+        const int strip = item / wpt, xw = item - strip * wpt;
+        const int y_begin = in0 + strip * R, y_end = min(in1, y_begin + R);
+        uint32_t bmask = 0;
 #pragma unroll
-          for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-              const float kk = (dy == 0 && dx == 0) ? k5 : k1;
-              acc = __fadd_rn(acc, __fmul_rn(small_uint_to_float(lds_u8(ctr + (uint32_t)((dy * vw + dx) * C + ch))), kk));
-            }
-          deg = __fadd_rn(__fadd_rz(acc, 8388608.0f), -8388608.0f);  // float(trunc(acc))
+        for (int b = 0; b < 4; ++b) {
+          const int xb = in.x0 * C + (xw << 2) + b;  // byte index in the image row
+          if (xb < C || xb >= W * C - C) bmask |= 1u << b;
         }
-        uint32_t res = sharp_blend(deg, small_uint_to_float(orig), f);
-        if (COUNT) {
-          count_value(c, ch, res);
-        } else {
-          if (use2) res = lds_u8(c.l2a + ch * 256 + res);
-          asm volatile("st.shared.u8 [%0], %1;" ::"r"(obuf + (uint32_t)(i * C + ch)), "r"(res) : "memory");
-        }
+        const uint32_t col = vbuf + (uint32_t)((y_begin - 1 - (ya - 1)) * vpitch + 4 + (xw << 2));
+        sharp_walk<C>(col, vpitch, y_end - y_begin, true, true, bmask, f,
+                      [&](int r, uint32_t o) { emit_row(y_begin + r, xw, o); });
       }
     }
     cons_sync();
@@ -1142,16 +1275,12 @@ __device__ void exec_gather_sharp(const TC<C>& c) {
   cons_sync();  // the next item's staging tile overlaps these buffers
 }
 
-// ========================================================================== sharpness executor
 // K == Sharpness with no spatial op pending: the tile is a strip of whole rows; the strip plus one
-// halo row each side sits in the slot (one TMA load).  l1 is applied to the staged rows in place; a
-// thread then owns one word column (4 bytes wide) of a sub-strip and walks down it, keeping the
-// float32 products of the last two rows of its 4 + 2C-byte window in registers, so every input byte
-// is converted and multiplied once per column instead of nine times.  Results go to the output
-// staging tile and leave as one TMA store (a strip is contiguous in the image).
+// halo row each side sits in the unit(s) (one TMA load).  l1 is applied to the staged rows in place,
+// the column walk writes the output staging tile, which leaves as one TMA store (a strip is
+// contiguous in the image).
 template <int C, bool COUNT>
 __device__ void exec_sharp(const TC<C>& c) {
-  constexpr int NB = 4 + 2 * C;  // window bytes per row
   const TileState& t = *c.t;
   const SlotInfo& in = *c.info;
   const int H = c.H;
@@ -1172,8 +1301,7 @@ __device__ void exec_sharp(const TC<C>& c) {
     cons_sync();
   }
   const int wpr = row >> 2;  // words per row
-  auto emit = [&](int y, int xw, uint32_t o) {
-    const int ph = (C == 3) ? (xw % 3) : 0;  // channel of byte 0 of word xw (4 == 1 mod 3)
+  auto emit = [&](int y, int xw, int ph, uint32_t o) {  // ph: channel of byte 0 of word xw
     if (COUNT) {
 #pragma unroll
       for (int b = 0; b < 4; ++b) count_value(c, (ph + b) % C, byte_of(o, b));
@@ -1186,84 +1314,29 @@ __device__ void exec_sharp(const TC<C>& c) {
   };
   // first and last image row: every pixel is border -> blend(orig, orig) == orig
   if (y0 == 0)
-    for (int xw = c.tid; xw < wpr; xw += NCONS) emit(0, xw, lds_u32(stage + (uint32_t)((0 - sr0) * row + (xw << 2))));
+    for (int xw = c.tid; xw < wpr; xw += NCONS)
+      emit(0, xw, (C == 3) ? (xw % 3) : 0, lds_u32(stage + (uint32_t)((0 - sr0) * row + (xw << 2))));
   if (H > 1 && y0 <= H - 1 && y1 > H - 1)
-    for (int xw = c.tid; xw < wpr; xw += NCONS) emit(H - 1, xw, lds_u32(stage + (uint32_t)((H - 1 - sr0) * row + (xw << 2))));
+    for (int xw = c.tid; xw < wpr; xw += NCONS)
+      emit(H - 1, xw, (C == 3) ? (xw % 3) : 0, lds_u32(stage + (uint32_t)((H - 1 - sr0) * row + (xw << 2))));
   const int in0 = max(y0, 1), in1 = min(y1, H - 1);
   const int inner = in1 - in0;
   if (inner > 0) {
-    const float k1 = __int_as_float(0x3d9d89d9);  // float32(1)/float32(13)
-    const float k5 = __int_as_float(0x3ec4ec4f);  // float32(5)/float32(13)
-    // split the inner rows into S sub-strips so that (word columns x sub-strips) keeps every thread
-    // busy: minimise rounds * (rows per sub-strip + 2 halo rows).
-    int best_s = 1;
-    long best_cost = 1L << 60;
-    for (int S = 1; S <= 16 && S <= inner; ++S) {
-      const long rounds = ((long)wpr * S + NCONS - 1) / NCONS;
-      const long cost = rounds * ((inner + S - 1) / S + 2);
-      if (cost < best_cost) { best_cost = cost; best_s = S; }
-    }
-    const int R = (inner + best_s - 1) / best_s;
+    const int R = in.sharp_rows;
     const int n_strips = (inner + R - 1) / R;
     const int n_items = wpr * n_strips;
     for (int item = c.tid; item < n_items; item += NCONS) {
-      const int strip = item / wpr;
-      const int xw = item - strip * wpr;
-      const int y_begin = in0 + strip * R;
-      const int y_end = min(in1, y_begin + R);
+      const int strip = item / wpr, xw = item - strip * wpr;
+      const int y_begin = in0 + strip * R, y_end = min(in1, y_begin + R);
       const int xb0 = xw << 2;
-      bool border[4];  // is the byte in the first / last pixel of the row?
+      uint32_t bmask = 0;
 #pragma unroll
-      for (int b = 0; b < 4; ++b) border[b] = (xb0 + b < C) || (xb0 + b >= row - C);
-      const bool has_prev = xw > 0, has_next = xw + 1 < wpr;
-      float pa[NB], pb[NB];  // products (x k1) of rows y-1 and y
-      float ctr[4];          // float values of the centre bytes of row y
-      auto load_row = [&](int yy, float* pr, float* cvals) {
-        const uint32_t ra = stage + (uint32_t)((yy - sr0) * row + xb0);
-        const uint32_t w1 = lds_u32(ra);
-        const uint32_t w0 = has_prev ? lds_u32(ra - 4) : 0u;
-        const uint32_t w2 = has_next ? lds_u32(ra + 4) : 0u;
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const int wb = 4 - C + j;  // byte index in the 12-byte (w0, w1, w2) window
-          const uint32_t wsel = (wb < 4) ? w0 : (wb < 8) ? w1 : w2;
-          const float fv = byte_to_float(wsel, wb & 3);
-          pr[j] = __fmul_rn(fv, k1);
-          if (cvals != nullptr && j >= C && j < C + 4) cvals[j - C] = fv;
-        }
-      };
-      load_row(y_begin - 1, pa, nullptr);
-      load_row(y_begin, pb, ctr);
-      for (int y = y_begin; y < y_end; ++y) {
-        float pc[NB], nctr[4];
-        load_row(y + 1, pc, nctr);
-        uint32_t o = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const float orig = ctr[b];
-          float deg = orig;
-          if (!border[b]) {
-            // window index b + C is the byte itself, b / b + 2C its left / right neighbours
-            float acc = pa[b];
-            acc = __fadd_rn(acc, pa[b + C]);
-            acc = __fadd_rn(acc, pa[b + 2 * C]);
-            acc = __fadd_rn(acc, pb[b]);
-            acc = __fadd_rn(acc, __fmul_rn(orig, k5));
-            acc = __fadd_rn(acc, pb[b + 2 * C]);
-            acc = __fadd_rn(acc, pc[b]);
-            acc = __fadd_rn(acc, pc[b + C]);
-            acc = __fadd_rn(acc, pc[b + 2 * C]);
-            deg = __fadd_rn(__fadd_rz(acc, 8388608.0f), -8388608.0f);  // float(trunc(acc))
-          }
-          const uint32_t res = sharp_blend(deg, orig, f);
-          o = (b == 0) ? res : put_byte(o, res, b);
-        }
-        emit(y, xw, o);
-#pragma unroll
-        for (int j = 0; j < NB; ++j) { pa[j] = pb[j]; pb[j] = pc[j]; }
-#pragma unroll
-        for (int b = 0; b < 4; ++b) ctr[b] = nctr[b];
-      }
+      for (int b = 0; b < 4; ++b)
+        if (xb0 + b < C || xb0 + b >= row - C) bmask |= 1u << b;
+      const int ph = (C == 3) ? (xw % 3) : 0;  // 4 == 1 mod 3
+      const uint32_t col = stage + (uint32_t)((y_begin - 1 - sr0) * row + xb0);
+      sharp_walk<C>(col, row, y_end - y_begin, xw > 0, xw + 1 < wpr, bmask, f,
+                    [&](int r, uint32_t o) { emit(y_begin + r, xw, ph, o); });
     }
   }
   if (!COUNT) {
@@ -1273,7 +1346,7 @@ __device__ void exec_sharp(const TC<C>& c) {
       bulk_commit();
     }
   } else if (use1) {
-    fence_proxy_async();  // the slot was written through the generic proxy; the TMA refills it next
+    fence_proxy_async();  // the unit was written through the generic proxy; the TMA refills it next
   }
 }
 
@@ -1291,13 +1364,17 @@ struct TilePlanD {
   SlotInfo in;
   uint32_t tx_bytes;
   int src_sel;
+  bool box_overflow;  // a gather tile whose source box does not fit: worth retrying on a part of the tile
 };
 
 // Decides how a tile is executed.  Every lane of the producer warp computes the same plan.  This
 // runs once per tile on a single warp, so everything that does not depend on the tile (strip
 // height, flat units per tile, alignment of the batch) comes precomputed in KParams.
+// `split` > 0 plans sub-rectangle `sub` of the tile's box cut into 2^split x-aligned row bands (split = 1)
+// or 2 x 2 quarters (split = 2): used when the source box of the whole tile does not fit two units.
 template <int C>
-__device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, int img, int tile, TilePlanD& d) {
+__device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, int img, int tile, TilePlanD& d,
+                                          int split = 0, int sub = 0) {
   constexpr int UB = (C == 3) ? 48 : 16;
   const int H = p.H, W = p.W;
   const int pass_kind = t.pass_kind;
@@ -1309,9 +1386,11 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
   SlotInfo& in = d.in;
   in.cls = CLS_GENERIC; in.img = img; in.tile = tile; in.pass_kind = pass_kind;
   in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0; in.rowb = 0; in.pitch = 16; in.rows = 0;
-  in.span = 1; in._pad = 0; in.fill = 0; in.paint = 0;
+  in.span = 1; in.sharp_rows = 1; in.fillc[0] = 0; in.fillc[1] = 0; in.paint = 0;
+  in.first = 1; in.last = 1; in._pad = 0;
   d.tx_bytes = 0;
   d.src_sel = t.src_sel;
+  d.box_overflow = false;
   const bool plainK = (kmode == K_NONE || kmode == K_COLOR);
 
   // ---- the common case first: no spatial op, a flat run of units
@@ -1332,11 +1411,23 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
     const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
     box.x0 = min(W, tx * p.tw); box.x1 = min(W, box.x0 + p.tw);
     box.y0 = min(H, ty * p.th); box.y1 = min(H, box.y0 + p.th);
+    if (split == 1) {  // two row bands
+      const int hy = box.y0 + (p.th >> 1);
+      if (sub == 0) box.y1 = min(box.y1, hy); else box.y0 = min(box.y1, hy);
+    } else if (split == 2) {  // four quarters
+      const int hy = box.y0 + (p.th >> 1), hx = box.x0 + (p.tw >> 1);
+      if (sub & 2) box.y0 = min(box.y1, hy); else box.y1 = min(box.y1, hy);
+      if (sub & 1) box.x0 = min(box.x1, hx); else box.x1 = min(box.x1, hx);
+    }
   }
+  d.box_overflow = false;
   Rect reg = (n_sp > 0) ? box : strip;
   bool masks_only = n_sp > 0;
   for (int k = 0; k < n_sp; ++k) masks_only = masks_only && (t.sp[k].type == SP_MASK);
-  for (int ch = 0; ch < C; ++ch) in.fill |= (uint32_t)(t.sp[0].color[ch] & 255) << (8 * ch);
+  for (int ch = 0; ch < C; ++ch) {
+    in.fillc[0] |= (uint32_t)(t.sp[max(n_sp - 1, 0)].color[ch] & 255) << (8 * ch);
+    in.fillc[1] |= (uint32_t)(t.sp[max(n_sp - 2, 0)].color[ch] & 255) << (8 * ch);
+  }
 
   // Source bounding box of output rectangle q: push its corners back through every warp of the
   // list.  Affine maps take extremes at corners; one pixel of margin per stage covers the rounding
@@ -1367,6 +1458,7 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
     in.bxb0 = (in.bx0 * C) & ~15;  // the TMA wants a 16-byte aligned box start
     if (in.by1 - in.by0 + 1 > p.box_rows || (in.bx1 + 1) * C - in.bxb0 > p.box_bytes) {
       in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0;
+      d.box_overflow = true;
       return false;
     }
     in.rows = p.box_rows; in.rowb = p.box_bytes; in.pitch = p.box_bytes;
@@ -1394,6 +1486,7 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
     if ((long long)nrows * rowbytes <= 2 * UNIT_BYTES && (long long)(strip.y1 - strip.y0) * rowbytes <= ostage_bytes(C)) {
       in.cls = CLS_SHARP;
       in.by0 = sr0; in.rows = nrows;
+      in.sharp_rows = sharp_split(rowbytes >> 2, max(1, min(strip.y1, H - 1) - max(strip.y0, 1)));
       d.tx_bytes = (uint32_t)(nrows * rowbytes);
     }
   } else if (kmode == K_SHARP && n_sp > 0 && fast && rows16 && t.sp_fast) {
@@ -1402,6 +1495,7 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
     halo.y0 = max(0, box.y0 - 1); halo.y1 = min(H, box.y1 + 1);
     if (box.x1 > box.x0 && box.y1 > box.y0 && source_box(halo)) {
       in.cls = CLS_GATHER_SHARP;
+      in.sharp_rows = sharp_split(((box.x1 - box.x0) * C) >> 2, max(1, (box.y1 - box.y0 + 1) >> 1));
       d.tx_bytes = (uint32_t)(in.rows * in.rowb);
     }
   }
@@ -1492,56 +1586,99 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       }
       TilePlanD d;
       plan_tile<C>(p, st, img0, tile, d);
-      if (d.in.span == 2 && (pu & (NU - 1)) == NU - 1) {  // a double tile may not wrap: pad the ring
+      // takes the unit(s), hands state and plan to the consumers and issues the loads of one tile
+      auto emit_tile = [&]() {
+        if (d.in.span == 2 && (pu & (NU - 1)) == NU - 1) {  // a double tile may not wrap: pad the ring
+          const uint32_t us = pu & (NU - 1);
+          take_unit(us);
+          if (lane == 0) { sm->info[us].cls = CLS_SKIP; sm->info[us].span = 1; mbar_arrive(full0 + 8 * us); }
+          ++pu;
+        }
         const uint32_t u = pu & (NU - 1);
         take_unit(u);
-        if (lane == 0) { sm->info[u].cls = CLS_SKIP; sm->info[u].span = 1; mbar_arrive(full0 + 8 * u); }
-        ++pu;
-      }
-      const uint32_t u = pu & (NU - 1);
-      take_unit(u);
-      if (d.in.span == 2) take_unit(u + 1);
-      pu += d.in.span;
-      // hand the state to the consumers (the prefetch buffer is reused two items later): the
-      // header and the spatial list always, a LUT only if it is not the identity or the scalar
-      // executor (which indexes the tables unconditionally) will run.
-      {
-        constexpr int HDR_VECS = (int)(offsetof(TileState, l1) / 16);
-        constexpr int LUT_VECS = MAXC * 256 / 16;
-        const uint4* sv = reinterpret_cast<const uint4*>(&st);
-        uint4* dv = reinterpret_cast<uint4*>(&sm->ust[u]);
-        for (int i = lane; i < HDR_VECS; i += 32) dv[i] = sv[i];
-        const bool all = d.in.cls == CLS_GENERIC;
-        if (all || !st.l1_id)
-          for (int i = lane; i < LUT_VECS; i += 32) dv[HDR_VECS + i] = sv[HDR_VECS + i];
-        if (all || !st.l2_id)
-          for (int i = lane; i < LUT_VECS; i += 32) dv[HDR_VECS + LUT_VECS + i] = sv[HDR_VECS + LUT_VECS + i];
-      }
-      __syncwarp();
-      if (lane == 0) {
-        sm->info[u] = d.in;
-        const uint32_t fb = full0 + 8 * u;
-        const uint32_t dst = smem_addr(sm->data[u]);
-        if (d.tx_bytes == 0) {
-          mbar_arrive(fb);
-        } else {
-          mbar_arrive_expect_tx(fb, d.tx_bytes);
-          const size_t img_off = (size_t)img0 * img_bytes;
-          const uint8_t* src = (d.src_sel == 0) ? p.in + img_off
-                                               : p.scratch + (size_t)(2 * (size_t)img0 + (d.src_sel - 1)) * p.scratch_stride;
-          if (d.in.cls == CLS_FLAT) {
-            constexpr int UB = (C == 3) ? 48 : 16;
-            bulk_load(dst, src + (size_t)d.in.x0 * UB, d.tx_bytes, fb);
-          } else if (d.in.cls == CLS_SHARP) {
-            bulk_load(dst, src + (size_t)d.in.by0 * (W * C), d.tx_bytes, fb);
-          } else if (d.src_sel == 0) {
-            tensor_load_3d(dst, &tm_in, d.in.bxb0 >> 2, d.in.by0, img0, fb);
+        if (d.in.span == 2) take_unit(u + 1);
+        pu += d.in.span;
+        // the prefetch buffer is reused two items later: copy the header and the spatial list always,
+        // a LUT only if it is not the identity or the scalar executor (which indexes the tables
+        // unconditionally) will run.
+        {
+          constexpr int HDR_VECS = (int)(offsetof(TileState, l1) / 16);
+          constexpr int LUT_VECS = MAXC * 256 / 16;
+          const uint4* sv = reinterpret_cast<const uint4*>(&st);
+          uint4* dv = reinterpret_cast<uint4*>(&sm->ust[u]);
+          for (int i = lane; i < HDR_VECS; i += 32) dv[i] = sv[i];
+          const bool all = d.in.cls == CLS_GENERIC;
+          if (all || !st.l1_id)
+            for (int i = lane; i < LUT_VECS; i += 32) dv[HDR_VECS + i] = sv[HDR_VECS + i];
+          if (all || !st.l2_id)
+            for (int i = lane; i < LUT_VECS; i += 32) dv[HDR_VECS + LUT_VECS + i] = sv[HDR_VECS + LUT_VECS + i];
+        }
+        __syncwarp();
+        if (lane == 0) {
+          sm->info[u] = d.in;
+          const uint32_t fb = full0 + 8 * u;
+          const uint32_t dst = smem_addr(sm->data[u]);
+          if (d.tx_bytes == 0) {
+            mbar_arrive(fb);
           } else {
-            tensor_load_3d(dst, &tm_scr, d.in.bxb0 >> 2, d.in.by0, 2 * img0 + (d.src_sel - 1), fb);
+            mbar_arrive_expect_tx(fb, d.tx_bytes);
+            const size_t img_off = (size_t)img0 * img_bytes;
+            const uint8_t* src = (d.src_sel == 0) ? p.in + img_off
+                                                 : p.scratch + (size_t)(2 * (size_t)img0 + (d.src_sel - 1)) * p.scratch_stride;
+            if (d.in.cls == CLS_FLAT) {
+              constexpr int UB = (C == 3) ? 48 : 16;
+              bulk_load(dst, src + (size_t)d.in.x0 * UB, d.tx_bytes, fb);
+            } else if (d.in.cls == CLS_SHARP) {
+              bulk_load(dst, src + (size_t)d.in.by0 * (W * C), d.tx_bytes, fb);
+            } else if (d.src_sel == 0) {
+              tensor_load_3d(dst, &tm_in, d.in.bxb0 >> 2, d.in.by0, img0, fb);
+            } else {
+              tensor_load_3d(dst, &tm_scr, d.in.bxb0 >> 2, d.in.by0, 2 * img0 + (d.src_sel - 1), fb);
+            }
           }
         }
+        __syncwarp();
+      };
+      if (d.in.cls == CLS_FLAT && d.in.pass_kind == PASS_COUNT) {
+        // histogram of a flat image: one item covers COUNT_GROUP consecutive tiles that share one
+        // shared-memory histogram, one flush and one completion handshake
+        if (tile % COUNT_GROUP == 0) {
+          constexpr int UB = (C == 3) ? 48 : 16;
+          const int n_sub = min(COUNT_GROUP, p.n_tiles - tile);
+          for (int j = 0; j < n_sub; ++j) {
+            const int u0 = min(p.flat_units, (tile + j) * p.flat_upt), u1 = min(p.flat_units, u0 + p.flat_upt);
+            d.in.tile = tile + j; d.in.x0 = u0; d.in.x1 = u1;
+            d.in.first = (j == 0); d.in.last = (j == n_sub - 1);
+            d.tx_bytes = (uint32_t)(u1 - u0) * UB;
+            emit_tile();
+          }
+        }
+      } else if (d.box_overflow) {
+        // the source box of the whole tile does not fit: cut the tile into 2 row bands, else into 4
+        // quarters, each with its own box; the parts count as one tile for the completion handshake
+        int split = 1;
+        for (; split <= 2; ++split) {
+          bool ok = true;
+          for (int sub = 0; sub < (1 << split) && ok; ++sub) {
+            plan_tile<C>(p, st, img0, tile, d, split, sub);
+            ok = !d.box_overflow;
+          }
+          if (ok) break;
+        }
+        if (split > 2) {
+          plan_tile<C>(p, st, img0, tile, d);  // no luck: the scalar executor takes the whole tile
+          emit_tile();
+        } else {
+          const int n_sub = 1 << split;
+          for (int sub = 0; sub < n_sub; ++sub) {
+            plan_tile<C>(p, st, img0, tile, d, split, sub);
+            d.in.first = (sub == 0); d.in.last = (sub == n_sub - 1);
+            emit_tile();
+          }
+        }
+      } else {
+        emit_tile();
       }
-      __syncwarp();
       item0 = item1; img0 = img1; item1 = item2; img1 = img2; item2 = item3;
     }
     return;
@@ -1581,31 +1718,38 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
                 ? p.out + img_off
                 : p.scratch + (size_t)(2 * (size_t)img + (st.dst_sel - 1)) * p.scratch_stride;
     ImgState* g = p.states + img;
+    const bool grouped = (pass_kind == PASS_COUNT) && (cls == CLS_FLAT);
+    const int is_last = info.last;
     if (pass_kind == PASS_COUNT) {
-      for (int i = tid; i < MAXC * 256; i += NCONS) (&sm->hist[0][0])[i] = 0u;
-      if (tid < CHB_MAX_CHAIN) sm->color_cnt[tid] = 0u;
-      cons_sync();
-      run_tile<C, true>(c);
-      cons_sync();
-      for (int i = tid; i < C * 256; i += NCONS) {
-        const uint32_t v = (&sm->hist[0][0])[i];
-        if (v) atomicAdd(&g->hist[0][0] + i, v);
+      if (info.first) {
+        for (int i = tid; i < MAXC * 256; i += NCONS) (&sm->hist[0][0])[i] = 0u;
+        if (tid < CHB_MAX_CHAIN) sm->color_cnt[tid] = 0u;
+        cons_sync();
       }
-      if (tid < CHB_MAX_CHAIN && sm->color_cnt[tid]) atomicAdd(&g->color_cnt[tid], sm->color_cnt[tid]);
+      run_tile<C, true>(c);
+      if (is_last) {
+        cons_sync();
+        for (int i = tid; i < C * 256; i += NCONS) {
+          const uint32_t v = (&sm->hist[0][0])[i];
+          if (v) atomicAdd(&g->hist[0][0] + i, v);
+        }
+        if (tid < CHB_MAX_CHAIN && sm->color_cnt[tid]) atomicAdd(&g->color_cnt[tid], sm->color_cnt[tid]);
+      }
     } else {
       run_tile<C, false>(c);
     }
     mbar_arrive(empty0 + 8 * u);  // done with the unit(s): state, info and staged bytes
     if (span == 2) mbar_arrive(empty0 + 8 * (u + 1));
     cu += span;
-    if (pass_kind == PASS_WRITE_OUT) continue;
+    if (pass_kind == PASS_WRITE_OUT || !is_last) continue;
+    const unsigned expected = grouped ? (unsigned)((p.n_tiles + COUNT_GROUP - 1) / COUNT_GROUP) : (unsigned)p.n_tiles;
 
     // ---- COUNT / WRITE_SCRATCH: the last tile of the image resumes the chain walk
     stores_drained(tid);  // the finaliser scratch below aliases the output staging tiles
     cons_sync();
     if (tid == 0) {
       __threadfence();  // cumulative: publishes the histogram atomics of the whole CTA (ordered by the barrier)
-      sm->ctl[1] = (atomicAdd(&g->tiles_done, 1u) == (unsigned)p.n_tiles - 1u) ? 1 : 0;
+      sm->ctl[1] = (atomicAdd(&g->tiles_done, 1u) == expected - 1u) ? 1 : 0;
       __threadfence();
     }
     cons_sync();

@@ -93,6 +93,20 @@ def main():
         layer = A.RandomChoice([getattr(A, n)(**magnitude_kwargs(n, 10))], 1)
         ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), bufs, args.iters)
         report("op:" + n, B, 224, 224, ms)
+    # representative ordered pairs (replayed schedule: every image gets the same two ops)
+    import numpy as np
+    ra2 = A.RandAugment(2, 10, elementwise=True)._transform
+    for a, b in [("Rotate", "ShearX"), ("CutOut", "Rotate"), ("Rotate", "Sharpness"), ("Sharpness", "Rotate"),
+                 ("Rotate", "Equalize"), ("Equalize", "Rotate"), ("Color", "Rotate"), ("Brightness", "Rotate"),
+                 ("Brightness", "Color"), ("Equalize", "Sharpness"), ("Color", "Color")]:
+        sch = np.zeros((B, 2, 1, 5), np.int32)
+        sch[:, 0, 0, 0], sch[:, 1, 0, 0] = names.index(a), names.index(b)
+        sch[..., 1] = 1
+        sch[..., 3] = 100
+        sch[..., 4] = 120
+        rep = torch.from_numpy(sch).cuda()
+        ms = time_layer(lambda i, x, y: ra2(x, seed=0, call_counter=i, out=y, replay=rep), bufs, args.iters)
+        report("pair:%s->%s" % (a, b), B, 224, 224, ms)
     cbufs = make_bufs(B, 224, 224, 3, kind="constant")
     for n in ("Equalize", "AutoContrast"):
         layer = A.RandomChoice([getattr(A, n)()], 1)
