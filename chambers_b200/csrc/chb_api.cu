@@ -501,8 +501,8 @@ static int get_workspace(chb_ctx* ctx, cudaStream_t stream, int B, int max_level
     ws->states = nullptr; ws->lists = nullptr; ws->counters = nullptr;
     ws->cap_images = 0; ws->cap_levels = 0;
     CHB_CUDA(ctx, cudaMalloc(&ws->states, nb * sizeof(chb::ImgState)));
-    CHB_CUDA(ctx, cudaMalloc(&ws->lists, nb * nl * sizeof(int)));
-    CHB_CUDA(ctx, cudaMalloc(&ws->counters, 2 * (size_t)nl * sizeof(unsigned int)));
+    CHB_CUDA(ctx, cudaMalloc(&ws->lists, nb * nl * chb::NBINS * sizeof(int)));
+    CHB_CUDA(ctx, cudaMalloc(&ws->counters, (size_t)nl * (chb::NBINS + 1) * sizeof(unsigned int)));
     ws->cap_images = nb;
     ws->cap_levels = nl;
   }
@@ -580,7 +580,9 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     if (ok && ws->scratch) ok = encode_image_map(&tm_scr, ws->scratch, H, W * C, stride, (size_t)B * 2, &br, &bb);
     if (ok) { p.use_tmap = 1; p.box_rows = br; p.box_bytes = bb; }
   }
-  cudaError_t e = chb::launch_plan(p, C, stream);
+  cudaError_t e = cudaMemsetAsync(ws->counters, 0, (size_t)max_levels * (chb::NBINS + 1) * sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "counter reset");
+  e = chb::launch_plan(p, C, stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "plan kernel launch");
   ctx->launches += 1;
   const long long slots = (long long)ctx->num_sms * chb::pass_ctas_per_sm(C);
@@ -588,6 +590,7 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     p.level = level;
     long long grid = slots;
     if (level == 0 && (long long)B * tp.n_tiles < grid) grid = (long long)B * tp.n_tiles;
+    if (level > 0 && grid > slots) grid = slots;
     e = chb::launch_pass(p, tm_in, tm_scr, C, (int)grid, stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "pass kernel launch");
     ctx->launches += 1;

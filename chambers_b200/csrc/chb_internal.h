@@ -29,6 +29,10 @@ static_assert(sizeof(DevOp) == 112, "DevOp layout");
 enum { BLEND_IMAGE2 = 0, BLEND_IMAGE1 = 1, BLEND_INTERP = 2, BLEND_EXTRAP = 3 };
 
 constexpr int MAXC = 4;
+// Work items of one level are ordered by the code they run (most expensive first): a pass CTA then
+// executes long runs of the same tile executor instead of thrashing the instruction cache, and the
+// long tiles are scheduled first.
+constexpr int NBINS = 9;
 
 // ---- per-image pass state (global memory; written by the plan kernel and by pass finalisers) ----
 // The chain of one image is evaluated lazily.  Between passes the "virtual image" is
@@ -91,8 +95,8 @@ struct KParams {
   uint8_t* scratch;                   // image i, buffer s in {1, 2}: scratch + (2 i + s - 1) * stride
   unsigned long long scratch_stride;
   ImgState* states;                   // [B]
-  int* lists;                         // [max_levels][B]: images that have a pass at that level
-  unsigned int* counters;             // [0, max_levels): list lengths; [max_levels, 2 max_levels): work counters
+  int* lists;                         // [max_levels][NBINS][B]: images that have a pass at that level, binned by executor
+  unsigned int* counters;             // [max_levels][NBINS] bin lengths, then [max_levels] work counters
   int level, max_levels;
   int tiles_x, tiles_y, tw, th, n_tiles;
   int force_generic;                  // debugging: route every tile through the scalar executor

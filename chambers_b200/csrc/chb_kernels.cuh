@@ -156,6 +156,25 @@ __device__ __forceinline__ void reset_view(ImgState* s, int tid, int nt) {  // a
   }
 }
 
+// Executor bin of an image's next pass (see NBINS): most expensive code first.
+__device__ __forceinline__ int bin_of(const TileState& t) {
+  bool any_geom = false;
+  for (int k = 0; k < t.n_sp; ++k) any_geom = any_geom || (t.sp[k].type == SP_GEOM);
+  const bool count = t.pass_kind == PASS_COUNT;
+  if (t.kmode == K_SHARP) return t.n_sp > 0 ? 0 : 1;
+  if (t.kmode == K_BILINEAR) return 2;
+  if (t.n_sp >= 2 && (any_geom || count)) return 3;
+  if (t.n_sp == 1 && (any_geom || count)) return t.kmode == K_COLOR ? 4 : 5;
+  if (count) return 6;
+  return t.kmode == K_COLOR ? 7 : 8;
+}
+// Queues image `img` for its pass at `level`.
+__device__ __forceinline__ void enqueue_pass(const KParams& p, int level, const TileState& t, int img) {
+  const int bin = bin_of(t);
+  const unsigned pos = atomicAdd(p.counters + level * NBINS + bin, 1u);
+  p.lists[((size_t)level * NBINS + bin) * p.B + pos] = img;
+}
+
 // CTA-cooperative chain walk.  *s lives in shared memory; starting at s->next_op every op is folded
 // into the view until one needs the pixels.  On return s->t.pass_kind names the pass to run now; the
 // walk resumes at the same op once that pass has finished.  hmap: MAXC*256 words, etab: MAXC*256
@@ -388,8 +407,7 @@ __global__ void __launch_bounds__(PLAN_NT) plan_kernel(const KParams p, int C) {
   __shared__ uint32_t rnd[32][4], rndc[32][4];
   const int tid = threadIdx.x;
   const int img = blockIdx.x;
-  if (img == 0)
-    for (int i = tid; i < 2 * p.max_levels; i += PLAN_NT) p.counters[i] = 0u;
+  // (the counters are zeroed by a memset node in front of this kernel)
   for (int i = tid; i < STATE_VECS; i += PLAN_NT) reinterpret_cast<uint4*>(&s)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   if (tid < 32) decode_image(p, &s, rnd, rndc, img, p.H, p.W, tid);
@@ -398,6 +416,7 @@ __global__ void __launch_bounds__(PLAN_NT) plan_kernel(const KParams p, int C) {
   advance(&s, p.states + img, p, C, p.H, p.W, hmap, etab, tid, PLAN_NT, [] { __syncthreads(); });
   for (int i = tid; i < STATE_VECS; i += PLAN_NT)
     reinterpret_cast<uint4*>(p.states + img)[i] = reinterpret_cast<const uint4*>(&s)[i];
+  if (tid == 0) enqueue_pass(p, 0, s.t, img);
 }
 
 #endif  // CHB_WITH_PLAN
@@ -1524,7 +1543,14 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   const int L = p.level;
   const int H = p.H, W = p.W;
   const int img_bytes = H * W * C;
-  const unsigned n_entries = (L == 0) ? (unsigned)p.B : __ldcg(p.counters + L);
+  // entries of this level: the bins back to back
+  unsigned bin_end[NBINS];
+  unsigned n_entries = 0;
+#pragma unroll
+  for (int b = 0; b < NBINS; ++b) {
+    n_entries += __ldcg(p.counters + L * NBINS + b);
+    bin_end[b] = n_entries;
+  }
   // an item is (entry << tile_shift) | tile; tile indices >= n_tiles (padding to a power of two) are skipped
   const unsigned n_items = n_entries << p.tile_shift;
   const uint32_t full0 = smem_addr(&sm->full[0]), empty0 = smem_addr(&sm->empty[0]);
@@ -1540,7 +1566,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   if (tid >= NCONS) {
     // ------------------------------------------------------------------ producer warp
     const int lane = tid - NCONS;
-    unsigned* work = p.counters + p.max_levels + L;
+    unsigned* work = p.counters + p.max_levels * NBINS + L;
     auto claim = [&]() -> unsigned {
       unsigned v = 0;
       if (lane == 0) v = atomicAdd(work, 1u);
@@ -1548,8 +1574,13 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     };
     auto image_of = [&](unsigned item) -> int {
       if (item >= n_items) return -1;
-      const int entry = (int)(item >> p.tile_shift);
-      return (L == 0) ? entry : __ldcg(p.lists + (size_t)L * p.B + entry);
+      const unsigned entry = item >> p.tile_shift;
+      int bin = 0;
+      unsigned first = 0;
+#pragma unroll
+      for (int b = 0; b < NBINS - 1; ++b)
+        if (entry >= bin_end[b]) { bin = b + 1; first = bin_end[b]; }
+      return __ldcg(p.lists + ((size_t)L * NBINS + bin) * p.B + (entry - first));
     };
     auto fetch_state = [&](int img, int buf) {
       if (lane == 0 && img >= 0) {
@@ -1770,10 +1801,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     advance(fs, g, p, C, H, W, hmap, etab, tid, NCONS, [] { cons_sync(); });
     for (int i = tid; i < STATE_VECS; i += NCONS)
       reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(fs)[i];
-    if (tid == 0 && L + 1 < p.max_levels) {
-      const unsigned pos = atomicAdd(p.counters + L + 1, 1u);
-      p.lists[(size_t)(L + 1) * p.B + pos] = img;
-    }
+    if (tid == 0 && L + 1 < p.max_levels) enqueue_pass(p, L + 1, fs->t, img);
     cons_sync();  // the R region is free again
   }
   if (tid < 32) bulk_wait_all0();  // every store of this CTA has landed before the grid retires

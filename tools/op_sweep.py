@@ -81,6 +81,11 @@ def main():
     from oracle.policy import magnitude_kwargs  # parameters only (no pixels): same table as the layers use
     names = ["AutoContrast", "Equalize", "Invert", "Brightness", "Contrast", "Color", "Sharpness", "ShearX", "ShearY",
              "TranslateX", "TranslateY", "Posterize", "Solarize", "SolarizeAdd", "CutOut", "Rotate"]
+    if args.only == "RandAugment":
+        layer = A.RandAugment(2, 10, elementwise=True)._transform
+        ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), bufs, args.iters, warm=1)
+        report("RandAugment(2,10)", B, 224, 224, ms)
+        return
     if args.only:
         layer = A.RandomChoice([getattr(A, args.only)(**magnitude_kwargs(args.only, 10))], 1)
         ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), bufs, args.iters, warm=1)
