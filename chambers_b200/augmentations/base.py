@@ -173,7 +173,7 @@ def build_policy(transforms, n_draws, elementwise):
 
 
 def run_policy(inputs, transforms, n_draws, elementwise, seed, call_counter, batch_total=None,
-               image_index_base=0, replay=None, record=False, out=None):
+               image_index_base=0, replay=None, record=False, out=None, built=None):
     """Apply RandomChoice(transforms, n_draws, elementwise) to ``inputs`` on the GPU.
 
     Returns (output, schedule-or-None).  ``inputs``: torch CUDA uint8 NHWC (stream-ordered device
@@ -182,7 +182,7 @@ def run_policy(inputs, transforms, n_draws, elementwise, seed, call_counter, bat
     B, H, W, C = (int(d) for d in inputs.shape)
     if batch_total is None:
         batch_total = B
-    pol, _keep, K = build_policy(transforms, n_draws, elementwise)
+    pol, _keep, K = built if built is not None else build_policy(transforms, n_draws, elementwise)
     sched_shape = (B, int(n_draws), K, _lib.CHB_SCHED_FIELDS)
     lib = _lib.load()
 

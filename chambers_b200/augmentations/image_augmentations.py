@@ -8,7 +8,7 @@ struct of the C ABI and every pixel is produced by ``libchambers_aug.so``.
 """
 
 from .. import _lib
-from .base import Layer, register, serialize, deserialize, run_policy, check_uint8
+from .base import build_policy, Layer, register, serialize, deserialize, run_policy, check_uint8
 
 _INTERP = _lib.INTERPOLATIONS
 _FILL = _lib.FILL_MODES
@@ -352,10 +352,17 @@ class RandomChoice(Layer):
     def call(self, inputs, seed=None, call_counter=None, replay=None, record=False, batch_total=None,
              image_index_base=0, out=None, **kwargs):
         seed, call_counter = self._stream(seed, call_counter)
-        table = [_flatten_transform(t) for t in self.transforms]
-        res, sched = run_policy(inputs, table, self.n_transforms, self.elementwise, seed, call_counter,
+        # the C structs of the policy are built once per (transforms, n, elementwise): per call this
+        # costs tens of microseconds of Python, more than the kernels of a small batch
+        key = (tuple(id(t) for t in self.transforms), self.n_transforms, bool(self.elementwise))
+        cached = getattr(self, "_built_policy", None)
+        if cached is None or cached[0] != key:
+            table = [_flatten_transform(t) for t in self.transforms]
+            cached = (key, table, build_policy(table, self.n_transforms, self.elementwise))
+            self._built_policy = cached
+        res, sched = run_policy(inputs, cached[1], self.n_transforms, self.elementwise, seed, call_counter,
                                 batch_total=batch_total, image_index_base=image_index_base,
-                                replay=replay, record=record, out=out)
+                                replay=replay, record=record, out=out, built=cached[2])
         self.last_schedule = sched
         return res
 

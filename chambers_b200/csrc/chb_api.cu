@@ -537,7 +537,11 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   if ((unsigned long long)B * 2ull * (unsigned long long)tp.n_tiles >= 0xFFFF0000ull)
     return fail(ctx, CHB_ERR_UNSUPPORTED, "batch * tiles exceeds the 32-bit work counter");
   const int chain = pol->n_draws * K;
-  const int max_levels = chain + 1;  // every op adds at most one pass before the final write
+  // Passes per image.  An op triggers an extra pass only if it is a histogram op (COUNT) or finds the
+  // kernel slot K occupied / frozen by an earlier op (WRITE_SCRATCH).  After a pass the view is plain
+  // again (or has a valid histogram), so the op right after a pass-triggering FIRST op cannot trigger
+  // one itself: a chain of n >= 2 ops has at most n - 1 extra passes, a single op at most one.
+  const int max_levels = chain > 2 ? chain : 2;
   // tiles read neighbours of their own region: an in-place call goes through a temporary.
   const bool overlap = (d_in < d_out + (size_t)B * img_bytes) && (d_out < d_in + (size_t)B * img_bytes);
   const size_t stride = (img_bytes + 255) / 256 * 256;

@@ -1522,6 +1522,16 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
   in.span = (d.tx_bytes > (uint32_t)UNIT_BYTES) ? 2 : 1;
 }
 
+// Re-planning of one part of a split tile.  (Making this and the cold executors __noinline__ was
+// tried to shrink the kernel: the calls put the tile context on the stack and the flat path lost a
+// third of its speed, so everything stays inlined.)
+template <int C>
+__device__ __forceinline__ TilePlanD plan_tile_part(const KParams& p, const TileState& t, int img, int tile, int split, int sub) {
+  TilePlanD d;
+  plan_tile<C>(p, t, img, tile, d, split, sub);
+  return d;
+}
+
 // ================================================================================ pass kernel
 template <int C, bool COUNT>
 __device__ __forceinline__ void run_tile(const TC<C>& c) {
@@ -1589,7 +1599,13 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       }
     };
     // items are claimed three ahead, image indices resolved two ahead, states fetched one ahead
-    unsigned item0 = claim(), item1 = claim(), item2 = claim();
+    unsigned item0, item1, item2;
+    {
+      unsigned v = 0;
+      if (lane == 0) v = atomicAdd(work, 3u);  // the first three claims in one round trip
+      item0 = __shfl_sync(0xFFFFFFFFu, v, 0);
+      item1 = item0 + 1; item2 = item0 + 2;
+    }
     int img0 = image_of(item0), img1 = image_of(item1);
     fetch_state(img0, 0);
     uint32_t pu = 0;          // next unit (monotonic)
@@ -1670,44 +1686,36 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
         }
         __syncwarp();
       };
-      if (d.in.cls == CLS_FLAT && d.in.pass_kind == PASS_COUNT) {
-        // histogram of a flat image: one item covers COUNT_GROUP consecutive tiles that share one
-        // shared-memory histogram, one flush and one completion handshake
-        if (tile % COUNT_GROUP == 0) {
-          constexpr int UB = (C == 3) ? 48 : 16;
-          const int n_sub = min(COUNT_GROUP, p.n_tiles - tile);
-          for (int j = 0; j < n_sub; ++j) {
-            const int u0 = min(p.flat_units, (tile + j) * p.flat_upt), u1 = min(p.flat_units, u0 + p.flat_upt);
-            d.in.tile = tile + j; d.in.x0 = u0; d.in.x1 = u1;
-            d.in.first = (j == 0); d.in.last = (j == n_sub - 1);
-            d.tx_bytes = (uint32_t)(u1 - u0) * UB;
-            emit_tile();
-          }
-        }
+      // One claimed item becomes n_sub tiles in the ring (all counted as one for the completion
+      // handshake): COUNT_GROUP consecutive flat tiles that share one histogram flush, or the 2 / 4
+      // parts of a gather tile whose source box does not fit two units.
+      int n_sub = 1, split = 0;
+      const bool group = (d.in.cls == CLS_FLAT && d.in.pass_kind == PASS_COUNT);
+      if (group) {
+        n_sub = (tile % COUNT_GROUP == 0) ? min(COUNT_GROUP, p.n_tiles - tile) : 0;
       } else if (d.box_overflow) {
-        // the source box of the whole tile does not fit: cut the tile into 2 row bands, else into 4
-        // quarters, each with its own box; the parts count as one tile for the completion handshake
-        int split = 1;
-        for (; split <= 2; ++split) {
+        for (split = 1; split <= 2; ++split) {
           bool ok = true;
           for (int sub = 0; sub < (1 << split) && ok; ++sub) {
-            plan_tile<C>(p, st, img0, tile, d, split, sub);
+            d = plan_tile_part<C>(p, st, img0, tile, split, sub);
             ok = !d.box_overflow;
           }
           if (ok) break;
         }
-        if (split > 2) {
-          plan_tile<C>(p, st, img0, tile, d);  // no luck: the scalar executor takes the whole tile
-          emit_tile();
-        } else {
-          const int n_sub = 1 << split;
-          for (int sub = 0; sub < n_sub; ++sub) {
-            plan_tile<C>(p, st, img0, tile, d, split, sub);
-            d.in.first = (sub == 0); d.in.last = (sub == n_sub - 1);
-            emit_tile();
-          }
+        if (split > 2) split = 0;  // no luck: the scalar executor takes the whole tile
+        n_sub = 1 << split;
+        if (split == 0) d = plan_tile_part<C>(p, st, img0, tile, 0, 0);
+      }
+      for (int sub = 0; sub < n_sub; ++sub) {
+        if (group) {
+          constexpr int UB = (C == 3) ? 48 : 16;
+          const int u0 = min(p.flat_units, (tile + sub) * p.flat_upt), u1 = min(p.flat_units, u0 + p.flat_upt);
+          d.in.tile = tile + sub; d.in.x0 = u0; d.in.x1 = u1;
+          d.tx_bytes = (uint32_t)(u1 - u0) * UB;
+        } else if (split > 0) {
+          d = plan_tile_part<C>(p, st, img0, tile, split, sub);
         }
-      } else {
+        d.in.first = (sub == 0); d.in.last = (sub == n_sub - 1);
         emit_tile();
       }
       item0 = item1; img0 = img1; item1 = item2; img1 = img2; item2 = item3;

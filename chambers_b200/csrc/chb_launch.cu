@@ -24,8 +24,11 @@ TilePlan plan_tiles(int H, int W) {
   return t;
 }
 
+cudaError_t configure_plan();
+
 cudaError_t configure_kernels() {
   cudaError_t e;
+  if ((e = configure_plan()) != cudaSuccess) return e;
   if ((e = configure_c1()) != cudaSuccess) return e;
   if ((e = configure_c2()) != cudaSuccess) return e;
   if ((e = configure_c3()) != cudaSuccess) return e;
