@@ -7,13 +7,14 @@ batches (BASELINE.json configs[1]) per B200, weak-scaled over --gpus N with no d
         --master-port P bench.py --gpus N --steps K --warmup W
 
 One JSON line on rank 0.  A "step" is one pass of the policy over one batch:
-  value     whole-job images/s with the inputs already resident in HBM (one fused kernel per step,
-            CUDA-event timed, max over ranks); input/output buffers rotate through a pool larger
+  value     whole-job images/s with the inputs already resident in HBM (one plan kernel + one pass
+            kernel per level per step, CUDA-event timed, max over ranks); input/output buffers rotate through a pool larger
             than L2 so no step re-reads a cached batch
   e2e       the same metric through the public layer API with HOST (pinned) buffers: H2D copy,
             kernels and D2H copy inside the timed region (chb_policy_apply_host)
-  roofline  HBM: algorithmic bytes (2*H*W*C per image) / average launch duration,
-            against MEASURED_PEAKS.json's measured copy bandwidth
+  roofline  HBM: algorithmic bytes (2*H*W*C per image) / average duration of one step's
+            kernels, against MEASURED_PEAKS.json's measured copy bandwidth; traffic = DRAM bytes of one
+            step from the ncu capture recorded in profiles/r01_traffic.json
   cpu_baseline  the oracle port (numpy restatement of the reference; TensorFlow is not installable
             here) timed on this box's host cores over a bounded sample -- a reported baseline only
 --impl reference times that same CPU port as the reference arm (rank 0 only).
@@ -162,6 +163,17 @@ class ClockSampler:
             self._thread.join(timeout=1.0)
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def measured_traffic(args):
+    """DRAM bytes (read + write) of one step, from an `ncu` capture of this command (tools/gpu_traffic.sh);
+    None if no capture of this workload is committed."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        key = "%s_b%d" % (args.policy, args.batch)
+        return rec[key]["dram_bytes_per_step"]
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -324,7 +336,8 @@ def run_native(args, rank, local_rank, world):
         "clocks": clocks,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "chb::pass_kernel<3>",
+                     "traffic": measured_traffic(args), "peak_source": peak_src,
+                     "kernel": "chb::plan_kernel + chb::pass_kernel<3> x levels (one step)",
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "frac_of_spec_8TBs": achieved / 8000.0},
         "e2e": e2e,
