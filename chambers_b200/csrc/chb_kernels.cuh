@@ -31,6 +31,8 @@
 //   exec_sharp    Sharpness: row strip + halo staged in shared memory, sliding 3x3 window per word column
 //   exec_generic  anything, one pixel per thread straight from global memory
 #pragma once
+#include <string.h>
+
 #include "chb_device.cuh"
 
 namespace chb {
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(PLAN_NT) plan_kernel(const KParams p, int C) {
   __shared__ uint32_t rnd[32][4], rndc[32][4];
   const int tid = threadIdx.x;
   const int img = blockIdx.x;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // level 0 may set itself up while we plan
   // (the counters are zeroed by a memset node in front of this kernel)
   for (int i = tid; i < STATE_VECS; i += PLAN_NT) reinterpret_cast<uint4*>(&s)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
@@ -1551,8 +1554,21 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   PassSmem<C>* sm = reinterpret_cast<PassSmem<C>*>(smem_raw);
   const int tid = threadIdx.x;
   const int L = p.level;
+  // Programmatic dependent launch: let the next kernel of the call (the next level) be scheduled as
+  // our CTAs retire, and do not read what the previous kernel wrote before it has completed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int H = p.H, W = p.W;
   const int img_bytes = H * W * C;
+  const uint32_t full0 = smem_addr(&sm->full[0]), empty0 = smem_addr(&sm->empty[0]);
+  const uint32_t stbar0 = smem_addr(&sm->stbar[0]);
+  if (tid == 0) {
+    for (int u = 0; u < NU; ++u) { mbar_init(full0 + 8 * u, 1); mbar_init(empty0 + 8 * u, NCONS); }
+    mbar_init(stbar0, 1); mbar_init(stbar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __syncthreads();
   // entries of this level: the bins back to back
   unsigned bin_end[NBINS];
   unsigned n_entries = 0;
@@ -1563,15 +1579,6 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   }
   // an item is (entry << tile_shift) | tile; tile indices >= n_tiles (padding to a power of two) are skipped
   const unsigned n_items = n_entries << p.tile_shift;
-  const uint32_t full0 = smem_addr(&sm->full[0]), empty0 = smem_addr(&sm->empty[0]);
-  const uint32_t stbar0 = smem_addr(&sm->stbar[0]);
-  if (tid == 0) {
-    for (int u = 0; u < NU; ++u) { mbar_init(full0 + 8 * u, 1); mbar_init(empty0 + 8 * u, NCONS); }
-    mbar_init(stbar0, 1); mbar_init(stbar0 + 8, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    fence_proxy_async();
-  }
-  __syncthreads();
 
   if (tid >= NCONS) {
     // ------------------------------------------------------------------ producer warp
@@ -1817,8 +1824,18 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
 
 template <int C>
 cudaError_t launch_pass_c(const KParams& p, const TMap& tm_in, const TMap& tm_scr, int grid, cudaStream_t stream) {
-  pass_kernel<C><<<grid, NT, sizeof(PassSmem<C>), stream>>>(p, tm_in, tm_scr);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = sizeof(PassSmem<C>);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // may start before the previous kernel has drained
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, pass_kernel<C>, p, tm_in, tm_scr);
 }
 
 template <int C>
