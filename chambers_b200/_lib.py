@@ -9,7 +9,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libchambers_aug.so")
+# CHB_LIB selects another build of the same library (tools/variants.py: timeline / experiment builds).
+LIB_PATH = os.environ.get("CHB_LIB") or os.path.join(_PKG, "libchambers_aug.so")
 
 CHB_MAX_SUBOPS = 4
 CHB_MAX_CHAIN = 8
@@ -90,6 +91,7 @@ SIGNATURES = {
     "chb_policy_apply_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChbPolicy), _i64, _i64,
                                    _u64, _u32, _vp, _vp]),
     "chb_set_debug": (_i, [_vp, _i]),
+    "chb_debug_timeline": (_i, [_vp, _vp, _i]),
     "chb_tile_plan": (_i, [_i, _i] + [ctypes.POINTER(_i)] * 4),
 }
 

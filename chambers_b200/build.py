@@ -44,17 +44,25 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+def build_variant(name, defines):
+    """Debug / experiment build next to the production library: libchambers_aug_<name>.so compiled
+    with extra -D flags (e.g. CHB_TIMELINE).  Select it at run time with CHB_LIB=<path>."""
+    out = os.path.join(PKG_DIR, "libchambers_aug_%s.so" % name)
+    return build_library(force=True, out_path=out, extra=["-D" + d for d in defines], obj_tag="_" + name)
+
+
+def build_library(force=False, verbose=False, out_path=None, extra=(), obj_tag=""):
     """Compile the CUDA extension if it is missing or stale; returns the .so path."""
     if not force and not needs_build():
         return LIB_PATH
+    out_path = out_path or LIB_PATH
     nvcc = find_nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
     inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
     procs = []
     for src in SOURCES:  # one nvcc per translation unit, all in parallel
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + inc + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", obj_tag + ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + list(extra) + inc + ["-c", "-o", obj, os.path.join(CSRC, src)]
         procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log, failed, objs = "", False, []
     for cmd, obj, pr in procs:
@@ -63,18 +71,22 @@ def build_library(force=False, verbose=False):
         failed = failed or pr.returncode != 0
         objs.append(obj)
     if not failed:
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out_path] + objs
         res = subprocess.run(cmd, capture_output=True, text=True)
         log += " ".join(cmd) + "\n" + res.stdout + res.stderr
         failed = res.returncode != 0
-    with open(os.path.join(PKG_DIR, "build.log"), "w") as f:
+    with open(os.path.join(PKG_DIR, "build%s.log" % obj_tag), "w") as f:
         f.write(log)
     if failed:
         raise RuntimeError("nvcc failed:\n" + log[-8000:])
     if verbose:
         print(log)
-    return LIB_PATH
+    return out_path
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:  # python -m chambers_b200.build --variant timeline CHB_TIMELINE [MORE_DEFINES...]
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose=True))

@@ -47,6 +47,7 @@ struct chb_ctx {
   std::string err;
   int64_t launches = 0;
   int force_generic = 0;  // CHB_FORCE_GENERIC=1: every tile through the scalar executor (debugging)
+  unsigned long long* timeline = nullptr;  // debug builds only (chb_debug_timeline)
   std::vector<Workspace*> workspaces;
   std::vector<PolicyEntry*> cache;
   // e2e pipeline
@@ -388,6 +389,7 @@ extern "C" void chb_destroy(chb_ctx* ctx) {
     cudaFree(ctx->st_in[i]); cudaFree(ctx->st_out[i]);
     cudaFree(ctx->st_replay[i]); cudaFree(ctx->st_record[i]);
   }
+  cudaFree(ctx->timeline);
   delete ctx;
 }
 
@@ -395,6 +397,29 @@ extern "C" int chb_set_debug(chb_ctx* ctx, int force_generic) {
   if (!ctx) return CHB_ERR_INVALID;
   ctx->force_generic = force_generic ? 1 : 0;
   return CHB_OK;
+}
+
+static const size_t kTimelineWords = (size_t)CHB_MAX_CHAIN * 1024 * 2 * 16;
+
+extern "C" int chb_debug_timeline(chb_ctx* ctx, uint64_t* host_out, int max_words) {
+  if (!ctx) return CHB_ERR_INVALID;
+#ifdef CHB_TIMELINE
+  CHB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->timeline) {
+    CHB_CUDA(ctx, cudaMalloc(&ctx->timeline, kTimelineWords * 8));
+    CHB_CUDA(ctx, cudaMemset(ctx->timeline, 0, kTimelineWords * 8));
+  }
+  if (!host_out) return 0;
+  CHB_CUDA(ctx, cudaDeviceSynchronize());
+  size_t n = max_words < 0 ? 0 : (size_t)max_words;
+  if (n > kTimelineWords) n = kTimelineWords;
+  CHB_CUDA(ctx, cudaMemcpy(host_out, ctx->timeline, n * 8, cudaMemcpyDeviceToHost));
+  CHB_CUDA(ctx, cudaMemset(ctx->timeline, 0, kTimelineWords * 8));
+  return (int)n;
+#else
+  (void)host_out; (void)max_words;
+  return fail(ctx, CHB_ERR_UNSUPPORTED, "chb_debug_timeline: the library was built without -DCHB_TIMELINE");
+#endif
 }
 
 extern "C" int chb_tile_plan(int H, int W, int* tiles_x, int* tiles_y, int* tw, int* th) {
@@ -562,10 +587,8 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   p.max_levels = max_levels;
   p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y; p.tw = tp.tw; p.th = tp.th; p.n_tiles = tp.n_tiles;
   p.force_generic = ctx->force_generic;
+  p.timeline = ctx->timeline;
   {
-    int shift = 0;
-    while ((1 << shift) < tp.n_tiles) ++shift;
-    p.tile_shift = shift;
     p.strip_rows = (H + tp.n_tiles - 1) / tp.n_tiles;
     const int ub = (C == 3) ? 48 : 16;
     p.flat_units = (int)(img_bytes / ub);

@@ -102,10 +102,10 @@ struct KParams {
   int force_generic;                  // debugging: route every tile through the scalar executor
   int use_tmap, box_rows, box_bytes;  // gather tiles: one tensor-map box of box_rows x box_bytes per tile
   // per-launch constants of the tile planner
-  int tile_shift;                     // items are (entry << tile_shift) | tile
   int strip_rows;                     // rows of a strip tile: ceil(H / n_tiles)
   int flat_units, flat_upt;           // flat runs: units per image (48 bytes for C = 3, else 16) and per tile
   int flags;                          // 1: in is 16-byte aligned, 2: out is, 4: images are whole 16-byte units, 8: rows are
+  unsigned long long* timeline;       // debug builds (-DCHB_TIMELINE): [levels][1024 CTAs][2][16] words, else NULL
 };
 
 // Opaque copy of a CUtensorMap (cuda.h), passed to the pass kernel as a __grid_constant__ parameter.

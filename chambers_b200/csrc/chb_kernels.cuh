@@ -43,7 +43,10 @@ constexpr int NT = NCONS + 32;                   // + one producer warp
 constexpr int PLAN_NT = 128;                     // threads per plan CTA
 constexpr int NU = 4;                            // pipeline units per CTA; a tile occupies one or two
 constexpr int UNIT_BYTES = 16 * 1024;            // staged source bytes of one unit
-constexpr int COUNT_GROUP = 4;                   // flat COUNT tiles per histogram flush (one item = 4 consecutive tiles)
+// TileStates are prefetched one item ahead into a ring indexed by the item number and read in place
+// by the consumers.  At most NU items are in flight (each holds a unit), so when item j's state is
+// fetched (one iteration early) the oldest item that can still be in use is j - NU: NU + 2 buffers.
+constexpr int NST = NU + 2;
 constexpr int LHIST_CH_BYTES = 64 * 32 * 4;      // lane-private u8x4 histogram of one channel
 constexpr int STATE_VECS = (int)(offsetof(ImgState, hist) / 16);   // everything but the histogram
 constexpr int TILE_VECS = (int)(sizeof(TileState) / 16);
@@ -60,6 +63,40 @@ static_assert(offsetof(ImgState, next_op) == sizeof(TileState), "finaliser part 
 struct Rect {
   int x0, x1, y0, y1;
 };
+
+// Debug timeline (-DCHB_TIMELINE, tools/timeline.py): every pass CTA leaves two 16-word records,
+// [level][cta][producer | consumer][16], in KParams::timeline.  Stamps are %globaltimer (ns),
+// accumulators are clock64 cycles.  Compiled out of the production library.
+#ifdef CHB_TIMELINE
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL_DECL()                    \
+  unsigned long long tl_acc[16];     \
+  for (int i_ = 0; i_ < 16; ++i_) tl_acc[i_] = 0; \
+  long long tl_t0 = 0;               \
+  (void)tl_t0
+#define TL_T0() tl_t0 = clock64()
+#define TL_ACC(i) tl_acc[i] += (unsigned long long)(clock64() - tl_t0)
+#define TL_ADD(i, v) tl_acc[i] += (unsigned long long)(v)
+#define TL_STAMP(i) tl_acc[i] = tl_now()
+#define TL_STAMP_ONCE(i) if (tl_acc[i] == 0) tl_acc[i] = tl_now()
+#define TL_FLUSH(role, leader)                                                                             \
+  if (p.timeline && (leader)) {                                                                            \
+    unsigned long long* o_ = p.timeline + (((size_t)p.level * 1024 + blockIdx.x) * 2 + (role)) * 16;       \
+    for (int i_ = 0; i_ < 16; ++i_) o_[i_] = tl_acc[i_];                                                    \
+  }
+#else
+#define TL_DECL()
+#define TL_T0()
+#define TL_ACC(i)
+#define TL_ADD(i, v)
+#define TL_STAMP(i)
+#define TL_STAMP_ONCE(i)
+#define TL_FLUSH(role, leader)
+#endif
 
 // Walks the spatial list from the last op to the first.  Returns -1 when the output pixel resolves
 // to source pixel (x, y) (updated in place), else the index of the spatial entry whose colour it shows.
@@ -446,18 +483,17 @@ struct alignas(16) SlotInfo {  // written by the producer, read by the consumers
   int32_t span;                      // units this tile occupies (1 or 2)
   int32_t sharp_rows;                // SHARP classes: rows per sub-strip of the column walk
   int32_t first, last;               // COUNT: first / last tile of a group that shares one histogram flush
-  int32_t _pad;
+  int32_t st_idx;                    // which prefetched TileState (PassSmem::stg) belongs to this tile
 };
 
 template <int C>
 struct alignas(128) PassSmem {
-  unsigned long long full[NU], empty[NU], stbar[2];
+  unsigned long long full[NU], empty[NU], stbar[NST];
   int32_t ctl[4];
   uint32_t color_cnt[CHB_MAX_CHAIN];
   uint32_t hist[MAXC][256];  // tile-local counts of a COUNT pass
   SlotInfo info[NU];
-  TileState ust[NU];         // the TileState of the tile whose first unit this is
-  TileState stg[2];          // producer-private prefetch buffers
+  TileState stg[NST];        // ring of prefetched TileStates, indexed by item number (see NST)
   alignas(128) uint8_t data[NU][UNIT_BYTES];
   alignas(128) uint8_t r[r_bytes(C)];
 };
@@ -1409,7 +1445,7 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
   in.cls = CLS_GENERIC; in.img = img; in.tile = tile; in.pass_kind = pass_kind;
   in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0; in.rowb = 0; in.pitch = 16; in.rows = 0;
   in.span = 1; in.sharp_rows = 1; in.fillc[0] = 0; in.fillc[1] = 0; in.paint = 0;
-  in.first = 1; in.last = 1; in._pad = 0;
+  in.first = 1; in.last = 1; in.st_idx = 0;
   d.tx_bytes = 0;
   d.src_sel = t.src_sel;
   d.box_overflow = false;
@@ -1554,6 +1590,8 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   PassSmem<C>* sm = reinterpret_cast<PassSmem<C>*>(smem_raw);
   const int tid = threadIdx.x;
   const int L = p.level;
+  TL_DECL();
+  TL_STAMP(0);
   // Programmatic dependent launch: let the next kernel of the call (the next level) be scheduled as
   // our CTAs retire, and do not read what the previous kernel wrote before it has completed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -1563,12 +1601,13 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   const uint32_t stbar0 = smem_addr(&sm->stbar[0]);
   if (tid == 0) {
     for (int u = 0; u < NU; ++u) { mbar_init(full0 + 8 * u, 1); mbar_init(empty0 + 8 * u, NCONS); }
-    mbar_init(stbar0, 1); mbar_init(stbar0 + 8, 1);
+    for (int b = 0; b < NST; ++b) mbar_init(stbar0 + 8 * b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
+  TL_STAMP(1);
   // entries of this level: the bins back to back
   unsigned bin_end[NBINS];
   unsigned n_entries = 0;
@@ -1577,21 +1616,28 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     n_entries += __ldcg(p.counters + L * NBINS + b);
     bin_end[b] = n_entries;
   }
-  // an item is (entry << tile_shift) | tile; tile indices >= n_tiles (padding to a power of two) are skipped
-  const unsigned n_items = n_entries << p.tile_shift;
+  // A claim is a *chunk*: G consecutive tiles of one entry (one atomic, one image lookup and one
+  // TileState fetch per chunk instead of per tile).  G grows with the work per CTA so that small
+  // batches keep enough chunks per CTA for the dynamic schedule to balance the tail.
+  const unsigned n_tiles_u = (unsigned)p.n_tiles;
+  unsigned G = 1;
+  {
+    const unsigned per_cta = (n_entries * n_tiles_u) / gridDim.x;
+    if (per_cta >= 48u) G = 4; else if (per_cta >= 12u) G = 2;
+  }
+  const unsigned cpi = (n_tiles_u + G - 1u) / G;  // chunks per image
+  const unsigned n_chunks = n_entries * cpi;
 
   if (tid >= NCONS) {
     // ------------------------------------------------------------------ producer warp
     const int lane = tid - NCONS;
     unsigned* work = p.counters + p.max_levels * NBINS + L;
-    auto claim = [&]() -> unsigned {
-      unsigned v = 0;
-      if (lane == 0) v = atomicAdd(work, 1u);
-      return __shfl_sync(0xFFFFFFFFu, v, 0);
-    };
-    auto image_of = [&](unsigned item) -> int {
-      if (item >= n_items) return -1;
-      const unsigned entry = item >> p.tile_shift;
+    // image and first tile of a chunk (-1 past the end)
+    auto chunk_image = [&](unsigned chunk, int& t0) -> int {
+      t0 = 0;
+      if (chunk >= n_chunks) return -1;
+      const unsigned entry = chunk / cpi;
+      t0 = (int)((chunk - entry * cpi) * G);
       int bin = 0;
       unsigned first = 0;
 #pragma unroll
@@ -1605,21 +1651,28 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
         bulk_load(smem_addr(&sm->stg[buf]), p.states + img, (uint32_t)sizeof(TileState), stbar0 + 8 * buf);
       }
     };
-    // items are claimed three ahead, image indices resolved two ahead, states fetched one ahead
-    unsigned item0, item1, item2;
+    // chunks are claimed three ahead (the atomic of chunk k + 3 is in flight while chunk k is issued),
+    // image indices resolved two ahead, states fetched one ahead
+    unsigned chunk1, chunk2;
+    int img0, img1, t00, t01;
     {
       unsigned v = 0;
       if (lane == 0) v = atomicAdd(work, 3u);  // the first three claims in one round trip
-      item0 = __shfl_sync(0xFFFFFFFFu, v, 0);
-      item1 = item0 + 1; item2 = item0 + 2;
+      v = __shfl_sync(0xFFFFFFFFu, v, 0);
+      chunk1 = v + 1; chunk2 = v + 2;
+      img0 = chunk_image(v, t00);
+      img1 = chunk_image(chunk1, t01);
     }
-    int img0 = image_of(item0), img1 = image_of(item1);
     fetch_state(img0, 0);
+    uint32_t sb = 0;          // state buffer of the current chunk
+    uint32_t st_par = 0;      // parity to wait for on stbar[b]
     uint32_t pu = 0;          // next unit (monotonic)
     uint32_t empty_par = 0xF; // parity to wait for on empty[u]: a fresh barrier passes parity 1
-    for (uint32_t k = 0;; ++k) {
+    for (;;) {
       auto take_unit = [&](uint32_t u) {  // wait until the consumers have released unit u
+        TL_T0();
         mbar_wait(empty0 + 8 * u, (empty_par >> u) & 1u);
+        TL_ACC(8);
         empty_par ^= 1u << u;
       };
       if (img0 < 0) {
@@ -1628,105 +1681,92 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
         if (lane == 0) { sm->info[u].cls = CLS_END; mbar_arrive(full0 + 8 * u); }
         break;
       }
-      fetch_state(img1, (k + 1) & 1);
-      const int img2 = image_of(item2);
-      const unsigned item3 = claim();
-      mbar_wait(stbar0 + 8 * (k & 1), (k >> 1) & 1u);
-      const TileState& st = sm->stg[k & 1];
-      const int tile = (int)(item0 & ((1u << p.tile_shift) - 1u));
-      if (tile >= p.n_tiles) {  // padding item
-        item0 = item1; img0 = img1; item1 = item2; img1 = img2; item2 = item3;
-        continue;
-      }
-      TilePlanD d;
-      plan_tile<C>(p, st, img0, tile, d);
-      // takes the unit(s), hands state and plan to the consumers and issues the loads of one tile
-      auto emit_tile = [&]() {
-        if (d.in.span == 2 && (pu & (NU - 1)) == NU - 1) {  // a double tile may not wrap: pad the ring
-          const uint32_t us = pu & (NU - 1);
-          take_unit(us);
-          if (lane == 0) { sm->info[us].cls = CLS_SKIP; sm->info[us].span = 1; mbar_arrive(full0 + 8 * us); }
-          ++pu;
-        }
-        const uint32_t u = pu & (NU - 1);
-        take_unit(u);
-        if (d.in.span == 2) take_unit(u + 1);
-        pu += d.in.span;
-        // the prefetch buffer is reused two items later: copy the header and the spatial list always,
-        // a LUT only if it is not the identity or the scalar executor (which indexes the tables
-        // unconditionally) will run.
-        {
-          constexpr int HDR_VECS = (int)(offsetof(TileState, l1) / 16);
-          constexpr int LUT_VECS = MAXC * 256 / 16;
-          const uint4* sv = reinterpret_cast<const uint4*>(&st);
-          uint4* dv = reinterpret_cast<uint4*>(&sm->ust[u]);
-          for (int i = lane; i < HDR_VECS; i += 32) dv[i] = sv[i];
-          const bool all = d.in.cls == CLS_GENERIC;
-          if (all || !st.l1_id)
-            for (int i = lane; i < LUT_VECS; i += 32) dv[HDR_VECS + i] = sv[HDR_VECS + i];
-          if (all || !st.l2_id)
-            for (int i = lane; i < LUT_VECS; i += 32) dv[HDR_VECS + LUT_VECS + i] = sv[HDR_VECS + LUT_VECS + i];
-        }
-        __syncwarp();
-        if (lane == 0) {
-          sm->info[u] = d.in;
-          const uint32_t fb = full0 + 8 * u;
-          const uint32_t dst = smem_addr(sm->data[u]);
-          if (d.tx_bytes == 0) {
-            mbar_arrive(fb);
-          } else {
-            mbar_arrive_expect_tx(fb, d.tx_bytes);
-            const size_t img_off = (size_t)img0 * img_bytes;
-            const uint8_t* src = (d.src_sel == 0) ? p.in + img_off
-                                                 : p.scratch + (size_t)(2 * (size_t)img0 + (d.src_sel - 1)) * p.scratch_stride;
-            if (d.in.cls == CLS_FLAT) {
-              constexpr int UB = (C == 3) ? 48 : 16;
-              bulk_load(dst, src + (size_t)d.in.x0 * UB, d.tx_bytes, fb);
-            } else if (d.in.cls == CLS_SHARP) {
-              bulk_load(dst, src + (size_t)d.in.by0 * (W * C), d.tx_bytes, fb);
-            } else if (d.src_sel == 0) {
-              tensor_load_3d(dst, &tm_in, d.in.bxb0 >> 2, d.in.by0, img0, fb);
+      const uint32_t sb_next = (sb + 1 == NST) ? 0u : sb + 1;
+      fetch_state(img1, (int)sb_next);
+      int t02;
+      const int img2 = chunk_image(chunk2, t02);
+      unsigned raw3 = 0;
+      if (lane == 0) raw3 = atomicAdd(work, 1u);  // consumed at the end of this chunk
+      TL_T0();
+      mbar_wait(stbar0 + 8 * sb, (st_par >> sb) & 1u);
+      TL_ACC(9);
+      st_par ^= 1u << sb;
+      const TileState& st = sm->stg[sb];
+      const int t_end = min(p.n_tiles, t00 + (int)G);
+      for (int tile = t00; tile < t_end; ++tile) {
+        TL_T0();
+        TilePlanD d;
+        plan_tile<C>(p, st, img0, tile, d);
+        // takes the unit(s), hands the plan to the consumers and issues the loads of one tile
+        auto emit_tile = [&]() {
+          if (d.in.span == 2 && (pu & (NU - 1)) == NU - 1) {  // a double tile may not wrap: pad the ring
+            const uint32_t us = pu & (NU - 1);
+            take_unit(us);
+            if (lane == 0) { sm->info[us].cls = CLS_SKIP; sm->info[us].span = 1; mbar_arrive(full0 + 8 * us); }
+            ++pu;
+          }
+          const uint32_t u = pu & (NU - 1);
+          take_unit(u);
+          if (d.in.span == 2) take_unit(u + 1);
+          pu += d.in.span;
+          d.in.st_idx = (int)sb;  // the consumers read the prefetched state in place
+          if (lane == 0) {
+            sm->info[u] = d.in;
+            const uint32_t fb = full0 + 8 * u;
+            const uint32_t dst = smem_addr(sm->data[u]);
+            if (d.tx_bytes == 0) {
+              mbar_arrive(fb);
             } else {
-              tensor_load_3d(dst, &tm_scr, d.in.bxb0 >> 2, d.in.by0, 2 * img0 + (d.src_sel - 1), fb);
+              mbar_arrive_expect_tx(fb, d.tx_bytes);
+              const size_t img_off = (size_t)img0 * img_bytes;
+              const uint8_t* src = (d.src_sel == 0) ? p.in + img_off
+                                                   : p.scratch + (size_t)(2 * (size_t)img0 + (d.src_sel - 1)) * p.scratch_stride;
+              if (d.in.cls == CLS_FLAT) {
+                constexpr int UB = (C == 3) ? 48 : 16;
+                bulk_load(dst, src + (size_t)d.in.x0 * UB, d.tx_bytes, fb);
+              } else if (d.in.cls == CLS_SHARP) {
+                bulk_load(dst, src + (size_t)d.in.by0 * (W * C), d.tx_bytes, fb);
+              } else if (d.src_sel == 0) {
+                tensor_load_3d(dst, &tm_in, d.in.bxb0 >> 2, d.in.by0, img0, fb);
+              } else {
+                tensor_load_3d(dst, &tm_scr, d.in.bxb0 >> 2, d.in.by0, 2 * img0 + (d.src_sel - 1), fb);
+              }
             }
           }
-        }
-        __syncwarp();
-      };
-      // One claimed item becomes n_sub tiles in the ring (all counted as one for the completion
-      // handshake): COUNT_GROUP consecutive flat tiles that share one histogram flush, or the 2 / 4
-      // parts of a gather tile whose source box does not fit two units.
-      int n_sub = 1, split = 0;
-      const bool group = (d.in.cls == CLS_FLAT && d.in.pass_kind == PASS_COUNT);
-      if (group) {
-        n_sub = (tile % COUNT_GROUP == 0) ? min(COUNT_GROUP, p.n_tiles - tile) : 0;
-      } else if (d.box_overflow) {
-        for (split = 1; split <= 2; ++split) {
-          bool ok = true;
-          for (int sub = 0; sub < (1 << split) && ok; ++sub) {
-            d = plan_tile_part<C>(p, st, img0, tile, split, sub);
-            ok = !d.box_overflow;
+          __syncwarp();
+        };
+        // A gather tile whose source box does not fit two units is issued as 2 / 4 parts.  The
+        // first part of the chunk's first tile and the last part of its last tile carry the
+        // first / last flags: the chunk shares one histogram flush and counts once towards the
+        // completion handshake of a COUNT / WRITE_SCRATCH pass.
+        int n_sub = 1, split = 0;
+        if (d.box_overflow) {
+          for (split = 1; split <= 2; ++split) {
+            bool ok = true;
+            for (int sub = 0; sub < (1 << split) && ok; ++sub) {
+              d = plan_tile_part<C>(p, st, img0, tile, split, sub);
+              ok = !d.box_overflow;
+            }
+            if (ok) break;
           }
-          if (ok) break;
+          if (split > 2) split = 0;  // no luck: the scalar executor takes the whole tile
+          n_sub = 1 << split;
+          if (split == 0) d = plan_tile_part<C>(p, st, img0, tile, 0, 0);
         }
-        if (split > 2) split = 0;  // no luck: the scalar executor takes the whole tile
-        n_sub = 1 << split;
-        if (split == 0) d = plan_tile_part<C>(p, st, img0, tile, 0, 0);
-      }
-      for (int sub = 0; sub < n_sub; ++sub) {
-        if (group) {
-          constexpr int UB = (C == 3) ? 48 : 16;
-          const int u0 = min(p.flat_units, (tile + sub) * p.flat_upt), u1 = min(p.flat_units, u0 + p.flat_upt);
-          d.in.tile = tile + sub; d.in.x0 = u0; d.in.x1 = u1;
-          d.tx_bytes = (uint32_t)(u1 - u0) * UB;
-        } else if (split > 0) {
-          d = plan_tile_part<C>(p, st, img0, tile, split, sub);
+        TL_ACC(11);
+        for (int sub = 0; sub < n_sub; ++sub) {
+          if (split > 0) d = plan_tile_part<C>(p, st, img0, tile, split, sub);
+          d.in.first = (tile == t00 && sub == 0); d.in.last = (tile == t_end - 1 && sub == n_sub - 1);
+          emit_tile();
         }
-        d.in.first = (sub == 0); d.in.last = (sub == n_sub - 1);
-        emit_tile();
       }
-      item0 = item1; img0 = img1; item1 = item2; img1 = img2; item2 = item3;
+      TL_T0();
+      const unsigned chunk3 = __shfl_sync(0xFFFFFFFFu, raw3, 0);
+      TL_ACC(10);
+      img0 = img1; t00 = t01; img1 = img2; t01 = t02; chunk2 = chunk3; sb = sb_next;
     }
+    TL_STAMP(4);
+    TL_FLUSH(0, lane == 0);
     return;
   }
 
@@ -1740,11 +1780,14 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   uint32_t full_par = 0;  // parity to wait for on full[u]
   for (;;) {
     const uint32_t u = cu & (NU - 1);
+    TL_T0();
     mbar_wait(full0 + 8 * u, (full_par >> u) & 1u);
+    TL_ACC(6);
     full_par ^= 1u << u;
     const SlotInfo& info = sm->info[u];
     const int cls = info.cls;
     if (cls == CLS_END) break;
+    TL_STAMP_ONCE(2);
     if (cls == CLS_SKIP) {
       mbar_arrive(empty0 + 8 * u);
       ++cu;
@@ -1753,7 +1796,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     const int span = info.span;
     const int img = info.img, pass_kind = info.pass_kind;
     const size_t img_off = (size_t)img * img_bytes;
-    const TileState& st = sm->ust[u];
+    const TileState& st = sm->stg[info.st_idx];
     c.t = &st; c.info = &info; c.tile = info.tile;
     c.data = smem_addr(sm->data[u]);
     c.ostage = c.r + (nstore & 1u) * ostage_bytes(C);
@@ -1764,8 +1807,8 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
                 ? p.out + img_off
                 : p.scratch + (size_t)(2 * (size_t)img + (st.dst_sel - 1)) * p.scratch_stride;
     ImgState* g = p.states + img;
-    const bool grouped = (pass_kind == PASS_COUNT) && (cls == CLS_FLAT);
     const int is_last = info.last;
+    TL_T0();
     if (pass_kind == PASS_COUNT) {
       if (info.first) {
         for (int i = tid; i < MAXC * 256; i += NCONS) (&sm->hist[0][0])[i] = 0u;
@@ -1784,13 +1827,17 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     } else {
       run_tile<C, false>(c);
     }
+    TL_ACC(7 + cls);  // cls 1..5 -> slots 8..12
+    TL_ADD(5, 1);
+    TL_STAMP(3);
     mbar_arrive(empty0 + 8 * u);  // done with the unit(s): state, info and staged bytes
     if (span == 2) mbar_arrive(empty0 + 8 * (u + 1));
     cu += span;
     if (pass_kind == PASS_WRITE_OUT || !is_last) continue;
-    const unsigned expected = grouped ? (unsigned)((p.n_tiles + COUNT_GROUP - 1) / COUNT_GROUP) : (unsigned)p.n_tiles;
+    const unsigned expected = cpi;  // every chunk of the image reports once, on its last tile
 
     // ---- COUNT / WRITE_SCRATCH: the last tile of the image resumes the chain walk
+    TL_T0();
     stores_drained(tid);  // the finaliser scratch below aliases the output staging tiles
     cons_sync();
     if (tid == 0) {
@@ -1799,7 +1846,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       __threadfence();
     }
     cons_sync();
-    if (!sm->ctl[1]) continue;
+    if (!sm->ctl[1]) { TL_ACC(13); continue; }
     ImgState* fs = reinterpret_cast<ImgState*>(sm->r);
     uint32_t* hmap = reinterpret_cast<uint32_t*>(sm->r + sizeof(ImgState));
     uint8_t* etab = sm->r + sizeof(ImgState) + MAXC * 256 * 4;
@@ -1818,8 +1865,12 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(fs)[i];
     if (tid == 0 && L + 1 < p.max_levels) enqueue_pass(p, L + 1, fs->t, img);
     cons_sync();  // the R region is free again
+    TL_ACC(13);
+    TL_ADD(14, 1);
   }
   if (tid < 32) bulk_wait_all0();  // every store of this CTA has landed before the grid retires
+  TL_STAMP(4);
+  TL_FLUSH(1, tid == 0);
 }
 
 template <int C>
