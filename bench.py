@@ -337,7 +337,7 @@ def run_native(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(args), "peak_source": peak_src,
-                     "kernel": "chb::plan_kernel + chb::pass_kernel<3> x levels (one step)",
+                     "kernel": "chb::plan_kernel + chb::pass_kernel<3> (one step)",
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "frac_of_spec_8TBs": achieved / 8000.0},
         "e2e": e2e,

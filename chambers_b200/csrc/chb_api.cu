@@ -31,7 +31,6 @@ struct Workspace {
   int* lists = nullptr;
   unsigned int* counters = nullptr;
   size_t cap_images = 0;
-  int cap_levels = 0;
   uint8_t* scratch = nullptr;
   size_t scratch_bytes = 0;
   uint8_t* inplace = nullptr;
@@ -399,11 +398,10 @@ extern "C" int chb_set_debug(chb_ctx* ctx, int force_generic) {
   return CHB_OK;
 }
 
-static const size_t kTimelineWords = (size_t)CHB_MAX_CHAIN * 1024 * 2 * 16;
-
 extern "C" int chb_debug_timeline(chb_ctx* ctx, uint64_t* host_out, int max_words) {
   if (!ctx) return CHB_ERR_INVALID;
 #ifdef CHB_TIMELINE
+  const size_t kTimelineWords = (size_t)1024 * 2 * 16;
   CHB_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!ctx->timeline) {
     CHB_CUDA(ctx, cudaMalloc(&ctx->timeline, kTimelineWords * 8));
@@ -507,7 +505,7 @@ static int grow(chb_ctx* ctx, void** ptr, size_t* have, size_t want) {
   return CHB_OK;
 }
 
-static int get_workspace(chb_ctx* ctx, cudaStream_t stream, int B, int max_levels, size_t scratch_bytes,
+static int get_workspace(chb_ctx* ctx, cudaStream_t stream, int B, size_t scratch_bytes,
                          size_t inplace_bytes, Workspace** out) {
   Workspace* ws = nullptr;
   for (Workspace* w : ctx->workspaces)
@@ -517,19 +515,19 @@ static int get_workspace(chb_ctx* ctx, cudaStream_t stream, int B, int max_level
     ws->stream = stream;
     ctx->workspaces.push_back(ws);
   }
-  if ((size_t)B > ws->cap_images || max_levels > ws->cap_levels) {
-    const size_t nb = (size_t)B > ws->cap_images ? (size_t)B : ws->cap_images;
-    const int nl = max_levels > ws->cap_levels ? max_levels : ws->cap_levels;
+  if ((size_t)B > ws->cap_images) {
+    const size_t nb = (size_t)B;
     if (ws->states) CHB_CUDA(ctx, cudaFree(ws->states));
     if (ws->lists) CHB_CUDA(ctx, cudaFree(ws->lists));
     if (ws->counters) CHB_CUDA(ctx, cudaFree(ws->counters));
     ws->states = nullptr; ws->lists = nullptr; ws->counters = nullptr;
-    ws->cap_images = 0; ws->cap_levels = 0;
+    ws->cap_images = 0;
     CHB_CUDA(ctx, cudaMalloc(&ws->states, nb * sizeof(chb::ImgState)));
-    CHB_CUDA(ctx, cudaMalloc(&ws->lists, nb * nl * chb::NBINS * sizeof(int)));
-    CHB_CUDA(ctx, cudaMalloc(&ws->counters, (size_t)nl * (chb::NBINS + 1) * sizeof(unsigned int)));
+    CHB_CUDA(ctx, cudaMalloc(&ws->lists, nb * chb::NBINS * sizeof(int)));
+    // counters and the continuation list share one allocation (one memset per call): 32 counter
+    // words, then one entry per possible pass after an image's first plus slack for void tickets
+    CHB_CUDA(ctx, cudaMalloc(&ws->counters, (32 + nb * CHB_MAX_CHAIN + 2048) * sizeof(unsigned int)));
     ws->cap_images = nb;
-    ws->cap_levels = nl;
   }
   int r = grow(ctx, (void**)&ws->scratch, &ws->scratch_bytes, scratch_bytes);
   if (r != CHB_OK) return r;
@@ -562,16 +560,15 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   if ((unsigned long long)B * 2ull * (unsigned long long)tp.n_tiles >= 0xFFFF0000ull)
     return fail(ctx, CHB_ERR_UNSUPPORTED, "batch * tiles exceeds the 32-bit work counter");
   const int chain = pol->n_draws * K;
-  // Passes per image.  An op triggers an extra pass only if it is a histogram op (COUNT) or finds the
-  // kernel slot K occupied / frozen by an earlier op (WRITE_SCRATCH).  After a pass the view is plain
-  // again (or has a valid histogram), so the op right after a pass-triggering FIRST op cannot trigger
-  // one itself: a chain of n >= 2 ops has at most n - 1 extra passes, a single op at most one.
-  const int max_levels = chain > 2 ? chain : 2;
+  // An op triggers an extra pass over the pixels only if it is a histogram op (COUNT) or finds the
+  // kernel slot K occupied / frozen by an earlier op (WRITE_SCRATCH).  Every pass after an image's
+  // first is run by the CTA that completed the previous one (chb_kernels.cuh), so a call is one plan
+  // launch and one pass launch whatever the chain length.
   // tiles read neighbours of their own region: an in-place call goes through a temporary.
   const bool overlap = (d_in < d_out + (size_t)B * img_bytes) && (d_out < d_in + (size_t)B * img_bytes);
   const size_t stride = (img_bytes + 255) / 256 * 256;
   Workspace* ws = nullptr;
-  r = get_workspace(ctx, stream, B, max_levels, chain >= 2 ? (size_t)B * 2 * stride : 0,
+  r = get_workspace(ctx, stream, B, chain >= 2 ? (size_t)B * 2 * stride : 0,
                     overlap ? (size_t)B * img_bytes : 0, &ws);
   if (r != CHB_OK) return r;
 
@@ -584,7 +581,6 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   p.replay = d_replay; p.record = d_record;
   p.scratch = ws->scratch; p.scratch_stride = stride;
   p.states = ws->states; p.lists = ws->lists; p.counters = ws->counters;
-  p.max_levels = max_levels;
   p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y; p.tw = tp.tw; p.th = tp.th; p.n_tiles = tp.n_tiles;
   p.force_generic = ctx->force_generic;
   p.timeline = ctx->timeline;
@@ -607,21 +603,17 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     if (ok && ws->scratch) ok = encode_image_map(&tm_scr, ws->scratch, H, W * C, stride, (size_t)B * 2, &br, &bb);
     if (ok) { p.use_tmap = 1; p.box_rows = br; p.box_bytes = bb; }
   }
-  cudaError_t e = cudaMemsetAsync(ws->counters, 0, (size_t)max_levels * (chb::NBINS + 1) * sizeof(unsigned int), stream);
+  p.cont = reinterpret_cast<int*>(ws->counters + 32);
+  cudaError_t e = cudaMemsetAsync(ws->counters, 0, (32 + (size_t)B * CHB_MAX_CHAIN + 2048) * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "counter reset");
   e = chb::launch_plan(p, C, stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "plan kernel launch");
   ctx->launches += 1;
-  const long long slots = (long long)ctx->num_sms * chb::pass_ctas_per_sm(C);
-  for (int level = 0; level < max_levels; ++level) {
-    p.level = level;
-    long long grid = slots;
-    if (level == 0 && (long long)B * tp.n_tiles < grid) grid = (long long)B * tp.n_tiles;
-    if (level > 0 && grid > slots) grid = slots;
-    e = chb::launch_pass(p, tm_in, tm_scr, C, (int)grid, stream);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "pass kernel launch");
-    ctx->launches += 1;
-  }
+  long long grid = (long long)ctx->num_sms * chb::pass_ctas_per_sm(C);
+  if ((long long)B * tp.n_tiles < grid) grid = (long long)B * tp.n_tiles;
+  e = chb::launch_pass(p, tm_in, tm_scr, C, (int)grid, stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "pass kernel launch");
+  ctx->launches += 1;
   if (overlap) CHB_CUDA(ctx, cudaMemcpyAsync(d_out, ws->inplace, (size_t)B * img_bytes, cudaMemcpyDeviceToDevice, stream));
   return CHB_OK;
 }

@@ -88,9 +88,15 @@ __device__ __forceinline__ void bulk_wait_all0() {  // this thread's stores are 
 __device__ __forceinline__ void fence_proxy_async() {  // generic-proxy smem writes -> visible to the async proxy
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// Same for every state space: global bytes written through the generic proxy (or by bulk stores)
+// before a TMA load of them, and the other way round.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // Barrier of the NCONS consumer threads of a pass CTA (the producer warp never joins it).
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// Image bytes read through the generic proxy go to L2 (ld.global.cg): a scratch image may have been
+// written by another SM earlier in the same kernel, and L1 is not coherent.
+__device__ __forceinline__ int ldg_pixel(const uint8_t* p) { return (int)__ldcg(p); }
 // Streaming global accesses: image bytes are touched once per pass, keep them out of L1.
 __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 

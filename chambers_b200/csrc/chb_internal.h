@@ -32,7 +32,7 @@ constexpr int MAXC = 4;
 // Work items of one level are ordered by the code they run (most expensive first): a pass CTA then
 // executes long runs of the same tile executor instead of thrashing the instruction cache, and the
 // long tiles are scheduled first.
-constexpr int NBINS = 9;
+constexpr int NBINS = 18;  // two groups (passes that are not / are the image's last) of 9 executor bins
 
 // ---- per-image pass state (global memory; written by the plan kernel and by pass finalisers) ----
 // The chain of one image is evaluated lazily.  Between passes the "virtual image" is
@@ -95,9 +95,10 @@ struct KParams {
   uint8_t* scratch;                   // image i, buffer s in {1, 2}: scratch + (2 i + s - 1) * stride
   unsigned long long scratch_stride;
   ImgState* states;                   // [B]
-  int* lists;                         // [max_levels][NBINS][B]: images that have a pass at that level, binned by executor
-  unsigned int* counters;             // [max_levels][NBINS] bin lengths, then [max_levels] work counters
-  int level, max_levels;
+  int* lists;                         // [NBINS][B]: the images, binned by the executor of their first pass
+  unsigned int* counters;             // [NBINS] bin lengths, then: work counter, ticket counter, continuation
+                                      // entries allocated, images that may still publish a continuation
+  int* cont;                          // continuation list: image + 1 per published pass, 0 = not yet (follows counters)
   int tiles_x, tiles_y, tw, th, n_tiles;
   int force_generic;                  // debugging: route every tile through the scalar executor
   int use_tmap, box_rows, box_bytes;  // gather tiles: one tensor-map box of box_rows x box_bytes per tile

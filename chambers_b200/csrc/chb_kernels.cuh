@@ -85,7 +85,7 @@ __device__ __forceinline__ unsigned long long tl_now() {
 #define TL_STAMP_ONCE(i) if (tl_acc[i] == 0) tl_acc[i] = tl_now()
 #define TL_FLUSH(role, leader)                                                                             \
   if (p.timeline && (leader)) {                                                                            \
-    unsigned long long* o_ = p.timeline + (((size_t)p.level * 1024 + blockIdx.x) * 2 + (role)) * 16;       \
+    unsigned long long* o_ = p.timeline + (((size_t)blockIdx.x) * 2 + (role)) * 16;       \
     for (int i_ = 0; i_ < 16; ++i_) o_[i_] = tl_acc[i_];                                                    \
   }
 #else
@@ -195,23 +195,28 @@ __device__ __forceinline__ void reset_view(ImgState* s, int tid, int nt) {  // a
   }
 }
 
-// Executor bin of an image's next pass (see NBINS): most expensive code first.
+// Executor bin of an image's next pass (see NBINS).  Passes that are not the image's last one
+// (COUNT / WRITE_SCRATCH) come first -- the CTA that finishes such a pass continues with the image's
+// next pass itself, so starting them early keeps that second stage out of the tail -- and within
+// each group the most expensive code runs first.
 __device__ __forceinline__ int bin_of(const TileState& t) {
   bool any_geom = false;
   for (int k = 0; k < t.n_sp; ++k) any_geom = any_geom || (t.sp[k].type == SP_GEOM);
   const bool count = t.pass_kind == PASS_COUNT;
-  if (t.kmode == K_SHARP) return t.n_sp > 0 ? 0 : 1;
-  if (t.kmode == K_BILINEAR) return 2;
-  if (t.n_sp >= 2 && (any_geom || count)) return 3;
-  if (t.n_sp == 1 && (any_geom || count)) return t.kmode == K_COLOR ? 4 : 5;
-  if (count) return 6;
-  return t.kmode == K_COLOR ? 7 : 8;
+  const int group = (t.pass_kind == PASS_WRITE_OUT) ? NBINS / 2 : 0;
+  if (t.kmode == K_SHARP) return group + (t.n_sp > 0 ? 0 : 1);
+  if (t.kmode == K_BILINEAR) return group + 2;
+  if (t.n_sp >= 2 && (any_geom || count)) return group + 3;
+  if (t.n_sp == 1 && (any_geom || count)) return group + (t.kmode == K_COLOR ? 4 : 5);
+  if (count) return group + 6;
+  return group + (t.kmode == K_COLOR ? 7 : 8);
 }
-// Queues image `img` for its pass at `level`.
-__device__ __forceinline__ void enqueue_pass(const KParams& p, int level, const TileState& t, int img) {
+constexpr int HEAVY_BINS = 4;  // bins 0..3 of a group: tiles cost microseconds each, claimed one at a time
+// Queues image `img` for its first pass.
+__device__ __forceinline__ void enqueue_pass(const KParams& p, const TileState& t, int img) {
   const int bin = bin_of(t);
-  const unsigned pos = atomicAdd(p.counters + level * NBINS + bin, 1u);
-  p.lists[((size_t)level * NBINS + bin) * p.B + pos] = img;
+  const unsigned pos = atomicAdd(p.counters + bin, 1u);
+  p.lists[(size_t)bin * p.B + pos] = img;
 }
 
 // CTA-cooperative chain walk.  *s lives in shared memory; starting at s->next_op every op is folded
@@ -456,7 +461,10 @@ __global__ void __launch_bounds__(PLAN_NT) plan_kernel(const KParams p, int C) {
   advance(&s, p.states + img, p, C, p.H, p.W, hmap, etab, tid, PLAN_NT, [] { __syncthreads(); });
   for (int i = tid; i < STATE_VECS; i += PLAN_NT)
     reinterpret_cast<uint4*>(p.states + img)[i] = reinterpret_cast<const uint4*>(&s)[i];
-  if (tid == 0) enqueue_pass(p, 0, s.t, img);
+  if (tid == 0) {
+    if (s.t.pass_kind != PASS_WRITE_OUT) atomicAdd(p.counters + NBINS + 3, 1u);  // this image will publish a continuation
+    enqueue_pass(p, s.t, img);
+  }
 }
 
 #endif  // CHB_WITH_PLAN
@@ -484,6 +492,8 @@ struct alignas(16) SlotInfo {  // written by the producer, read by the consumers
   int32_t sharp_rows;                // SHARP classes: rows per sub-strip of the column walk
   int32_t first, last;               // COUNT: first / last tile of a group that shares one histogram flush
   int32_t st_idx;                    // which prefetched TileState (PassSmem::stg) belongs to this tile
+  uint32_t expected;                 // COUNT / WRITE_SCRATCH: chunks of this image that report to tiles_done
+  int32_t _pad[3];
 };
 
 template <int C>
@@ -558,7 +568,7 @@ __device__ void exec_generic(const TC<C>& c) {
       } else {
         const uint8_t* px = src + ((size_t)sy * W + sx) * C;
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) v[ch] = __ldg(px + ch);
+        for (int ch = 0; ch < C; ++ch) v[ch] = ldg_pixel(px + ch);
         if (kmode == K_NONE) {
           if (!COUNT) {
 #pragma unroll
@@ -589,7 +599,7 @@ __device__ void exec_generic(const TC<C>& c) {
         int sx = xx, sy = yy;
         const int k = resolve(t.sp, t.n_sp, H, W, sx, sy);
         if (k >= 0) return t.sp[k].color[ch];
-        return t.l1[ch][__ldg(src + ((size_t)sy * W + sx) * C + ch)];
+        return t.l1[ch][ldg_pixel(src + ((size_t)sy * W + sx) * C + ch)];
       };
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) {
@@ -633,7 +643,7 @@ __device__ void exec_generic(const TC<C>& c) {
       for (int ch = 0; ch < C; ++ch) {
         auto tap = [&](bool in, int iy, int ix) -> float {
           if (!in) return (float)fill;
-          return (float)t.l1[ch][__ldg(src + ((size_t)iy * W + ix) * C + ch)];
+          return (float)t.l1[ch][ldg_pixel(src + ((size_t)iy * W + ix) * C + ch)];
         };
         const float v00 = tap(iny0 && inx0, iy0, ix0), v01 = tap(iny0 && inx1, iy0, ix1);
         const float v10 = tap(iny1 && inx0, iy1, ix0), v11 = tap(iny1 && inx1, iy1, ix1);
@@ -830,7 +840,7 @@ __device__ void exec_flat(const TC<C>& c) {
         }
       }
 #pragma unroll
-      for (int ch = 0; ch < C; ++ch) v[ch] = c.src[(size_t)pix * C + ch];
+      for (int ch = 0; ch < C; ++ch) v[ch] = ldg_pixel(c.src + (size_t)pix * C + ch);
       if (kmode == K_NONE) {
         if (!COUNT && use1) {
 #pragma unroll
@@ -1058,7 +1068,7 @@ __device__ void gather_list(const TC<C>& c) {
         } else {  // never taken if the box is right; keeps a box error from becoming a wrong pixel
           const uint8_t* px = c.src + ((size_t)sy * W + sx) * C;
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) v[ch] = __ldg(px + ch);
+          for (int ch = 0; ch < C; ++ch) v[ch] = ldg_pixel(px + ch);
         }
         if (kmode == K_NONE) {
           if (!COUNT && use1) {
@@ -1273,7 +1283,7 @@ __device__ void exec_gather_sharp(const TC<C>& c) {
           } else {
             const uint8_t* px = c.src + ((size_t)sy * W + sx) * C;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) v[ch] = __ldg(px + ch);
+            for (int ch = 0; ch < C; ++ch) v[ch] = ldg_pixel(px + ch);
           }
           if (use1) {
 #pragma unroll
@@ -1445,7 +1455,7 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
   in.cls = CLS_GENERIC; in.img = img; in.tile = tile; in.pass_kind = pass_kind;
   in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0; in.rowb = 0; in.pitch = 16; in.rows = 0;
   in.span = 1; in.sharp_rows = 1; in.fillc[0] = 0; in.fillc[1] = 0; in.paint = 0;
-  in.first = 1; in.last = 1; in.st_idx = 0;
+  in.first = 1; in.last = 1; in.st_idx = 0; in.expected = 1u; in._pad[0] = in._pad[1] = in._pad[2] = 0;
   d.tx_bytes = 0;
   d.src_sel = t.src_sel;
   d.box_overflow = false;
@@ -1589,11 +1599,10 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   extern __shared__ __align__(128) uint8_t smem_raw[];
   PassSmem<C>* sm = reinterpret_cast<PassSmem<C>*>(smem_raw);
   const int tid = threadIdx.x;
-  const int L = p.level;
   TL_DECL();
   TL_STAMP(0);
-  // Programmatic dependent launch: let the next kernel of the call (the next level) be scheduled as
-  // our CTAs retire, and do not read what the previous kernel wrote before it has completed.
+  // Programmatic dependent launch: set up while the plan kernel still runs, do not read what it
+  // wrote before it has completed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int H = p.H, W = p.W;
   const int img_bytes = H * W * C;
@@ -1608,162 +1617,263 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   TL_STAMP(1);
-  // entries of this level: the bins back to back
+  // first passes of all images: the bins back to back
   unsigned bin_end[NBINS];
   unsigned n_entries = 0;
 #pragma unroll
   for (int b = 0; b < NBINS; ++b) {
-    n_entries += __ldcg(p.counters + L * NBINS + b);
+    n_entries += __ldcg(p.counters + b);
     bin_end[b] = n_entries;
   }
-  // A claim is a *chunk*: G consecutive tiles of one entry (one atomic, one image lookup and one
-  // TileState fetch per chunk instead of per tile).  G grows with the work per CTA so that small
-  // batches keep enough chunks per CTA for the dynamic schedule to balance the tail.
+  // A claim is a *chunk* of one entry: one tile for the heavy bins, G consecutive tiles for the
+  // light ones (one atomic, one image lookup and one TileState fetch per chunk).  G grows with the
+  // work per CTA so that small batches keep enough chunks per CTA for the dynamic schedule to
+  // balance the tail.  The bins form four segments: non-final heavy | light, final heavy | light.
   const unsigned n_tiles_u = (unsigned)p.n_tiles;
   unsigned G = 1;
   {
     const unsigned per_cta = (n_entries * n_tiles_u) / gridDim.x;
     if (per_cta >= 48u) G = 4; else if (per_cta >= 12u) G = 2;
   }
-  const unsigned cpi = (n_tiles_u + G - 1u) / G;  // chunks per image
-  const unsigned n_chunks = n_entries * cpi;
+  const unsigned cpi = (n_tiles_u + G - 1u) / G;  // chunks per image of a light bin
+  unsigned seg_entry0[4], seg_begin[5];
+  {
+    const int first_bin[4] = {0, HEAVY_BINS, NBINS / 2, NBINS / 2 + HEAVY_BINS};
+    const int last_bin[4] = {HEAVY_BINS - 1, NBINS / 2 - 1, NBINS / 2 + HEAVY_BINS - 1, NBINS - 1};
+    seg_begin[0] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      seg_entry0[k] = first_bin[k] ? bin_end[first_bin[k] - 1] : 0u;
+      seg_begin[k + 1] = seg_begin[k] + (bin_end[last_bin[k]] - seg_entry0[k]) * ((k & 1) ? cpi : n_tiles_u);
+    }
+  }
+  const unsigned n_chunks = seg_begin[4];
 
   if (tid >= NCONS) {
     // ------------------------------------------------------------------ producer warp
     const int lane = tid - NCONS;
-    unsigned* work = p.counters + p.max_levels * NBINS + L;
-    // image and first tile of a chunk (-1 past the end)
-    auto chunk_image = [&](unsigned chunk, int& t0) -> int {
-      t0 = 0;
-      if (chunk >= n_chunks) return -1;
-      const unsigned entry = chunk / cpi;
-      t0 = (int)((chunk - entry * cpi) * G);
+    unsigned* work = p.counters + NBINS;
+    struct Chunk { int img, t0, t1; unsigned expected; int local; };
+    // image and tiles of a global chunk (img = -1 past the end)
+    auto global_chunk = [&](unsigned chunk) -> Chunk {
+      Chunk c = {-1, 0, 0, 1u, 0};
+      if (chunk >= n_chunks) return c;
+      unsigned sbeg = 0, sent = seg_entry0[0];
+      bool heavy = true;
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (chunk >= seg_begin[k]) { sbeg = seg_begin[k]; sent = seg_entry0[k]; heavy = !(k & 1); }
+      const unsigned cp = heavy ? n_tiles_u : cpi;
+      const unsigned loc = chunk - sbeg;
+      const unsigned e_in = loc / cp;
+      const unsigned ci = loc - e_in * cp;
+      const unsigned entry = sent + e_in;
+      c.t0 = (int)(heavy ? ci : ci * G);
+      c.t1 = min(p.n_tiles, c.t0 + (int)(heavy ? 1u : G));
+      c.expected = cp;
       int bin = 0;
       unsigned first = 0;
 #pragma unroll
       for (int b = 0; b < NBINS - 1; ++b)
         if (entry >= bin_end[b]) { bin = b + 1; first = bin_end[b]; }
-      return __ldcg(p.lists + ((size_t)L * NBINS + bin) * p.B + (entry - first));
+      c.img = __ldcg(p.lists + (size_t)bin * p.B + (entry - first));
+      return c;
     };
     auto fetch_state = [&](int img, int buf) {
-      if (lane == 0 && img >= 0) {
+      if (lane == 0) {
         mbar_arrive_expect_tx(stbar0 + 8 * buf, (uint32_t)sizeof(TileState));
         bulk_load(smem_addr(&sm->stg[buf]), p.states + img, (uint32_t)sizeof(TileState), stbar0 + 8 * buf);
       }
     };
-    // chunks are claimed three ahead (the atomic of chunk k + 3 is in flight while chunk k is issued),
-    // image indices resolved two ahead, states fetched one ahead
-    unsigned chunk1, chunk2;
-    int img0, img1, t00, t01;
+    const Chunk none = {-1, 0, 0, 1u, 0};
+    // Continuations: when a CTA completes a COUNT / WRITE_SCRATCH pass of an image it publishes the
+    // image in p.cont (entry = image + 1; 0 = not yet published).  Every producer holds one *ticket*
+    // into that list (ticket -> entry ticket / cpi_c, tiles (ticket % cpi_c) * Gc ...) and polls it
+    // once per chunk; a published ticket goes into the pipeline ahead of the global queue, so the
+    // next pass of an image is spread over all CTAs as soon as it exists.  p.counters[NBINS + 3]
+    // counts the images that may still publish: when it is zero an unpublished ticket is void.
+    const unsigned Gc = (G >= 4u) ? 2u : 1u;
+    const unsigned cpi_c = (n_tiles_u + Gc - 1u) / Gc;
+    unsigned* cwork = p.counters + NBINS + 1;
+    volatile unsigned* pending = p.counters + NBINS + 3;
+    volatile int* cont = p.cont;
+    // Pipeline: c0 is issued now (its state fetch is in flight), c1's state is fetched while c0 is
+    // issued, c2 is resolved (image lookup) meanwhile, and the claim of the chunk after that is in
+    // flight.  Every chunk and ticket is claimed dynamically, also the first ones: a CTA that has
+    // not started yet (the SMs may be shared with another stream's kernel) must not own any work
+    // that running CTAs wait for.
+    Chunk c0, c1, c2;
+    unsigned chunk_next;  // claimed, not yet resolved
+    unsigned ticket;
     {
-      unsigned v = 0;
-      if (lane == 0) v = atomicAdd(work, 3u);  // the first three claims in one round trip
+      unsigned v = 0, tv = 0;
+      if (lane == 0) { v = atomicAdd(work, 3u); tv = atomicAdd(cwork, 1u); }
       v = __shfl_sync(0xFFFFFFFFu, v, 0);
-      chunk1 = v + 1; chunk2 = v + 2;
-      img0 = chunk_image(v, t00);
-      img1 = chunk_image(chunk1, t01);
+      ticket = __shfl_sync(0xFFFFFFFFu, tv, 0);
+      c0 = global_chunk(v);
+      c1 = global_chunk(v + 1u);
+      chunk_next = v + 2u;
     }
-    fetch_state(img0, 0);
-    uint32_t sb = 0;          // state buffer of the current chunk
+    bool g_done = false;      // the global queue is exhausted
+    bool ticket_wait = false; // a new ticket has been requested (traw)
+    unsigned traw = 0;
+    int polled = 0;           // what the last poll of the ticket's entry returned (lane 0; 0 = not published)
+    uint32_t ring = 0;        // next state buffer to allocate
+    uint32_t sb0 = 0, sb1 = 0;
     uint32_t st_par = 0;      // parity to wait for on stbar[b]
     uint32_t pu = 0;          // next unit (monotonic)
     uint32_t empty_par = 0xF; // parity to wait for on empty[u]: a fresh barrier passes parity 1
-    for (;;) {
-      auto take_unit = [&](uint32_t u) {  // wait until the consumers have released unit u
-        TL_T0();
-        mbar_wait(empty0 + 8 * u, (empty_par >> u) & 1u);
-        TL_ACC(8);
-        empty_par ^= 1u << u;
-      };
-      if (img0 < 0) {
-        const uint32_t u = pu & (NU - 1);
-        take_unit(u);
-        if (lane == 0) { sm->info[u].cls = CLS_END; mbar_arrive(full0 + 8 * u); }
-        break;
-      }
-      const uint32_t sb_next = (sb + 1 == NST) ? 0u : sb + 1;
-      fetch_state(img1, (int)sb_next);
-      int t02;
-      const int img2 = chunk_image(chunk2, t02);
-      unsigned raw3 = 0;
-      if (lane == 0) raw3 = atomicAdd(work, 1u);  // consumed at the end of this chunk
+    auto take_unit = [&](uint32_t u) {  // wait until the consumers have released unit u
       TL_T0();
-      mbar_wait(stbar0 + 8 * sb, (st_par >> sb) & 1u);
-      TL_ACC(9);
-      st_par ^= 1u << sb;
-      const TileState& st = sm->stg[sb];
-      const int t_end = min(p.n_tiles, t00 + (int)G);
-      for (int tile = t00; tile < t_end; ++tile) {
-        TL_T0();
-        TilePlanD d;
-        plan_tile<C>(p, st, img0, tile, d);
-        // takes the unit(s), hands the plan to the consumers and issues the loads of one tile
-        auto emit_tile = [&]() {
-          if (d.in.span == 2 && (pu & (NU - 1)) == NU - 1) {  // a double tile may not wrap: pad the ring
-            const uint32_t us = pu & (NU - 1);
-            take_unit(us);
-            if (lane == 0) { sm->info[us].cls = CLS_SKIP; sm->info[us].span = 1; mbar_arrive(full0 + 8 * us); }
-            ++pu;
+      mbar_wait(empty0 + 8 * u, (empty_par >> u) & 1u);
+      TL_ACC(8);
+      empty_par ^= 1u << u;
+    };
+    auto alloc_state = [&]() -> uint32_t { const uint32_t b = ring; ring = (ring + 1 == NST) ? 0u : ring + 1; return b; };
+    auto cont_chunk = [&](int entry_value) -> Chunk {
+      Chunk c;
+      const unsigned ci = ticket % cpi_c;
+      c.img = entry_value - 1; c.t0 = (int)(ci * Gc); c.t1 = min(p.n_tiles, c.t0 + (int)Gc); c.expected = cpi_c; c.local = 1;
+      return c;
+    };
+    if (c0.img >= 0) { sb0 = alloc_state(); fetch_state(c0.img, (int)sb0); }
+    for (;;) {
+      if (c1.img >= 0) {
+        sb1 = alloc_state();
+        if (c1.local) { __threadfence(); fence_proxy_async_all(); }  // published by another CTA's finaliser (generic proxy)
+        fetch_state(c1.img, (int)sb1);
+      }
+      // two ahead: a published continuation first, else the next global chunk
+      bool claimed = false;
+      unsigned raw = 0;
+      {
+        const int pv = __shfl_sync(0xFFFFFFFFu, polled, 0);
+        if (pv > 0) {
+          c2 = cont_chunk(pv);
+          if (lane == 0) traw = atomicAdd(cwork, 1u);
+          ticket_wait = true;
+          polled = 0;
+        } else if (!g_done) {
+          c2 = global_chunk(chunk_next);
+          if (c2.img < 0) {
+            g_done = true;
+          } else {
+            claimed = true;
+            if (lane == 0) raw = atomicAdd(work, 1u);  // consumed at the end of this iteration
           }
-          const uint32_t u = pu & (NU - 1);
-          take_unit(u);
-          if (d.in.span == 2) take_unit(u + 1);
-          pu += d.in.span;
-          d.in.st_idx = (int)sb;  // the consumers read the prefetched state in place
-          if (lane == 0) {
-            sm->info[u] = d.in;
-            const uint32_t fb = full0 + 8 * u;
-            const uint32_t dst = smem_addr(sm->data[u]);
-            if (d.tx_bytes == 0) {
-              mbar_arrive(fb);
-            } else {
-              mbar_arrive_expect_tx(fb, d.tx_bytes);
-              const size_t img_off = (size_t)img0 * img_bytes;
-              const uint8_t* src = (d.src_sel == 0) ? p.in + img_off
-                                                   : p.scratch + (size_t)(2 * (size_t)img0 + (d.src_sel - 1)) * p.scratch_stride;
-              if (d.in.cls == CLS_FLAT) {
-                constexpr int UB = (C == 3) ? 48 : 16;
-                bulk_load(dst, src + (size_t)d.in.x0 * UB, d.tx_bytes, fb);
-              } else if (d.in.cls == CLS_SHARP) {
-                bulk_load(dst, src + (size_t)d.in.by0 * (W * C), d.tx_bytes, fb);
-              } else if (d.src_sel == 0) {
-                tensor_load_3d(dst, &tm_in, d.in.bxb0 >> 2, d.in.by0, img0, fb);
+        } else {
+          c2 = none;
+        }
+        // poll the ticket for the next iteration (not while a new ticket is on its way)
+        if (!ticket_wait && lane == 0) polled = cont[ticket / cpi_c];
+      }
+      if (c0.img >= 0) {
+        TL_T0();
+        mbar_wait(stbar0 + 8 * sb0, (st_par >> sb0) & 1u);
+        TL_ACC(9);
+        st_par ^= 1u << sb0;
+        const TileState& st = sm->stg[sb0];
+        const int img0 = c0.img;
+        for (int tile = c0.t0; tile < c0.t1; ++tile) {
+          TL_T0();
+          TilePlanD d;
+          plan_tile<C>(p, st, img0, tile, d);
+          // takes the unit(s), hands the plan to the consumers and issues the loads of one tile
+          auto emit_tile = [&]() {
+            if (d.in.span == 2 && (pu & (NU - 1)) == NU - 1) {  // a double tile may not wrap: pad the ring
+              const uint32_t us = pu & (NU - 1);
+              take_unit(us);
+              if (lane == 0) { sm->info[us].cls = CLS_SKIP; sm->info[us].span = 1; mbar_arrive(full0 + 8 * us); }
+              ++pu;
+            }
+            const uint32_t u = pu & (NU - 1);
+            take_unit(u);
+            if (d.in.span == 2) take_unit(u + 1);
+            pu += d.in.span;
+            d.in.st_idx = (int)sb0;  // the consumers read the prefetched state in place
+            d.in.expected = c0.expected;
+            if (lane == 0) {
+              sm->info[u] = d.in;
+              const uint32_t fb = full0 + 8 * u;
+              const uint32_t dst = smem_addr(sm->data[u]);
+              if (d.tx_bytes == 0) {
+                mbar_arrive(fb);
               } else {
-                tensor_load_3d(dst, &tm_scr, d.in.bxb0 >> 2, d.in.by0, 2 * img0 + (d.src_sel - 1), fb);
+                mbar_arrive_expect_tx(fb, d.tx_bytes);
+                const size_t img_off = (size_t)img0 * img_bytes;
+                const uint8_t* src = (d.src_sel == 0) ? p.in + img_off
+                                                     : p.scratch + (size_t)(2 * (size_t)img0 + (d.src_sel - 1)) * p.scratch_stride;
+                if (d.in.cls == CLS_FLAT) {
+                  constexpr int UB = (C == 3) ? 48 : 16;
+                  bulk_load(dst, src + (size_t)d.in.x0 * UB, d.tx_bytes, fb);
+                } else if (d.in.cls == CLS_SHARP) {
+                  bulk_load(dst, src + (size_t)d.in.by0 * (W * C), d.tx_bytes, fb);
+                } else if (d.src_sel == 0) {
+                  tensor_load_3d(dst, &tm_in, d.in.bxb0 >> 2, d.in.by0, img0, fb);
+                } else {
+                  tensor_load_3d(dst, &tm_scr, d.in.bxb0 >> 2, d.in.by0, 2 * img0 + (d.src_sel - 1), fb);
+                }
               }
             }
-          }
-          __syncwarp();
-        };
-        // A gather tile whose source box does not fit two units is issued as 2 / 4 parts.  The
-        // first part of the chunk's first tile and the last part of its last tile carry the
-        // first / last flags: the chunk shares one histogram flush and counts once towards the
-        // completion handshake of a COUNT / WRITE_SCRATCH pass.
-        int n_sub = 1, split = 0;
-        if (d.box_overflow) {
-          for (split = 1; split <= 2; ++split) {
-            bool ok = true;
-            for (int sub = 0; sub < (1 << split) && ok; ++sub) {
-              d = plan_tile_part<C>(p, st, img0, tile, split, sub);
-              ok = !d.box_overflow;
+            __syncwarp();
+          };
+          // A gather tile whose source box does not fit two units is issued as 2 / 4 parts.  The
+          // first part of the chunk's first tile and the last part of its last tile carry the
+          // first / last flags: the chunk shares one histogram flush and counts once towards the
+          // completion handshake of a COUNT / WRITE_SCRATCH pass.
+          int n_sub = 1, split = 0;
+          if (d.box_overflow) {
+            for (split = 1; split <= 2; ++split) {
+              bool ok = true;
+              for (int sub = 0; sub < (1 << split) && ok; ++sub) {
+                d = plan_tile_part<C>(p, st, img0, tile, split, sub);
+                ok = !d.box_overflow;
+              }
+              if (ok) break;
             }
-            if (ok) break;
+            if (split > 2) split = 0;  // no luck: the scalar executor takes the whole tile
+            n_sub = 1 << split;
+            if (split == 0) d = plan_tile_part<C>(p, st, img0, tile, 0, 0);
           }
-          if (split > 2) split = 0;  // no luck: the scalar executor takes the whole tile
-          n_sub = 1 << split;
-          if (split == 0) d = plan_tile_part<C>(p, st, img0, tile, 0, 0);
+          TL_ACC(11);
+          for (int sub = 0; sub < n_sub; ++sub) {
+            if (split > 0) d = plan_tile_part<C>(p, st, img0, tile, split, sub);
+            d.in.first = (tile == c0.t0 && sub == 0); d.in.last = (tile == c0.t1 - 1 && sub == n_sub - 1);
+            emit_tile();
+          }
         }
-        TL_ACC(11);
-        for (int sub = 0; sub < n_sub; ++sub) {
-          if (split > 0) d = plan_tile_part<C>(p, st, img0, tile, split, sub);
-          d.in.first = (tile == t00 && sub == 0); d.in.last = (tile == t_end - 1 && sub == n_sub - 1);
-          emit_tile();
+      } else if (c1.img < 0 && c2.img < 0 && !ticket_wait) {
+        // Nothing left to issue: the global queue is exhausted.  Wait for the ticket: it is either
+        // published, or void once no image can publish any more.
+        TL_T0();
+        int pv = 0;
+        if (lane == 0) {
+          for (;;) {
+            pv = cont[ticket / cpi_c];
+            if (pv > 0) break;
+            if (*pending == 0u) {
+              __threadfence();
+              pv = cont[ticket / cpi_c];
+              break;
+            }
+            __nanosleep(100);
+          }
+          polled = pv;
+        }
+        pv = __shfl_sync(0xFFFFFFFFu, pv, 0);
+        TL_ACC(12);
+        if (pv <= 0) {
+          const uint32_t u = pu & (NU - 1);
+          take_unit(u);
+          if (lane == 0) { sm->info[u].cls = CLS_END; mbar_arrive(full0 + 8 * u); }
+          break;
         }
       }
       TL_T0();
-      const unsigned chunk3 = __shfl_sync(0xFFFFFFFFu, raw3, 0);
+      if (claimed) chunk_next = __shfl_sync(0xFFFFFFFFu, raw, 0);
+      if (ticket_wait) { ticket = __shfl_sync(0xFFFFFFFFu, traw, 0); ticket_wait = false; }
       TL_ACC(10);
-      img0 = img1; t00 = t01; img1 = img2; t01 = t02; chunk2 = chunk3; sb = sb_next;
+      c0 = c1; sb0 = sb1; c1 = c2;
     }
     TL_STAMP(4);
     TL_FLUSH(0, lane == 0);
@@ -1794,6 +1904,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       continue;
     }
     const int span = info.span;
+    const unsigned expected = info.expected;  // chunks of the image that report once each, on their last tile
     const int img = info.img, pass_kind = info.pass_kind;
     const size_t img_off = (size_t)img * img_bytes;
     const TileState& st = sm->stg[info.st_idx];
@@ -1834,11 +1945,14 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     if (span == 2) mbar_arrive(empty0 + 8 * (u + 1));
     cu += span;
     if (pass_kind == PASS_WRITE_OUT || !is_last) continue;
-    const unsigned expected = cpi;  // every chunk of the image reports once, on its last tile
 
-    // ---- COUNT / WRITE_SCRATCH: the last tile of the image resumes the chain walk
+    // ---- COUNT / WRITE_SCRATCH: the CTA that completes the image's last chunk resumes the chain walk
     TL_T0();
-    stores_drained(tid);  // the finaliser scratch below aliases the output staging tiles
+    if (tid < 32) {
+      // the finaliser scratch below aliases the output staging tiles; a scratch image must also
+      // have landed in global memory before the pass is reported complete
+      if (pass_kind == PASS_WRITE_SCRATCH) { bulk_wait_all0(); fence_proxy_async_all(); } else { bulk_wait_read0(); }
+    }
     cons_sync();
     if (tid == 0) {
       __threadfence();  // cumulative: publishes the histogram atomics of the whole CTA (ordered by the barrier)
@@ -1863,8 +1977,22 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     advance(fs, g, p, C, H, W, hmap, etab, tid, NCONS, [] { cons_sync(); });
     for (int i = tid; i < STATE_VECS; i += NCONS)
       reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(fs)[i];
-    if (tid == 0 && L + 1 < p.max_levels) enqueue_pass(p, L + 1, fs->t, img);
-    cons_sync();  // the R region is free again
+    const int fs_next_pass = fs->t.pass_kind;
+    // Publish the image's next pass: whichever CTAs hold the tickets of its chunks fetch the state
+    // just written (and, after a WRITE_SCRATCH pass, the scratch image) with TMA loads.
+    __threadfence();
+    fence_proxy_async_all();
+    cons_sync();  // the R region is free again, the state is in global memory
+    if (tid == 0) {
+      const bool more = fs_next_pass != PASS_WRITE_OUT;  // the image will publish again
+      const unsigned pos = atomicAdd(p.counters + NBINS + 2, 1u);
+      __threadfence();
+      *reinterpret_cast<volatile int*>(p.cont + pos) = img + 1;
+      if (!more) {
+        __threadfence();
+        atomicSub(p.counters + NBINS + 3, 1u);
+      }
+    }
     TL_ACC(13);
     TL_ADD(14, 1);
   }

@@ -53,7 +53,7 @@ def main():
     lib = _lib.load()
     ctx = _lib.context(0)
     _lib.check(ctx, lib.chb_debug_timeline(ctx, None, 0))
-    words = 8 * 1024 * 2 * 16
+    words = 1024 * 2 * 16
     host = np.zeros(words, dtype=np.uint64)
     # one recorded call on buffers that have not been touched for n - 1 calls (L2-cold like the bench)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -63,11 +63,11 @@ def main():
     torch.cuda.synchronize()
     got = lib.chb_debug_timeline(ctx, host.ctypes.data_as(ctypes.c_void_p), words)
     assert got == words, got
-    rec = host.reshape(8, 1024, 2, 16).astype(np.int64)
+    rec = host.reshape(1, 1024, 2, 16).astype(np.int64)
     t_base = None
     report = {"batch": B, "size": S, "policy": args.policy, "call_ms": e0.elapsed_time(e1), "levels": []}
     print("call %.1f us (debug build)" % (1e3 * e0.elapsed_time(e1)))
-    for L in range(8):
+    for L in range(1):
         cons = rec[L, :, 1, :]
         prod = rec[L, :, 0, :]
         live = cons[:, 0] > 0
@@ -88,7 +88,7 @@ def main():
         for k, name in CLS.items():
             lv["consumer_cycles"][name] = tot(cons[:, k])
         lv["producer_cycles"] = {"wait_empty": tot(prod[:, 8]), "wait_state": tot(prod[:, 9]), "wait_claim": tot(prod[:, 10]),
-                                 "plan": tot(prod[:, 11])}
+                                 "plan": tot(prod[:, 11]), "quiesce": tot(prod[:, 12])}
         nct = max(1, int(live.sum()))
         print("level %d: %d CTAs (%d with tiles), %d tiles" % (L, lv["ctas"], lv["ctas_with_tiles"], lv["tiles"]))
         for k in ("enter_us", "dep_wait_done_us", "first_tile_us", "last_tile_done_us", "exit_us"):
