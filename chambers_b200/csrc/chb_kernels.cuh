@@ -493,7 +493,12 @@ struct alignas(16) SlotInfo {  // written by the producer, read by the consumers
   int32_t first, last;               // COUNT: first / last tile of a group that shares one histogram flush
   int32_t st_idx;                    // which prefetched TileState (PassSmem::stg) belongs to this tile
   uint32_t expected;                 // COUNT / WRITE_SCRATCH: chunks of this image that report to tiles_done
-  int32_t _pad[3];
+  int32_t rpi;                       // warp-autonomous gather: tile rows per warp step (32 / quads per row)
+  int32_t n_steps;                   //   steps of the tile: ceil(th / rpi)
+  uint32_t inv_n16, inv_qpr;         //   ceil(1024 / d) for d = 16-byte vectors / quads per tile row: lane / d == (lane * inv) >> 10
+  int32_t _pad;
+  const uint8_t* src;                // source image of this pass (the batch or a scratch image)
+  uint8_t* dst;                      // destination image (unused by COUNT passes)
 };
 
 template <int C>
@@ -506,6 +511,7 @@ struct alignas(128) PassSmem {
   TileState stg[NST];        // ring of prefetched TileStates, indexed by item number (see NST)
   alignas(128) uint8_t data[NU][UNIT_BYTES];
   alignas(128) uint8_t r[r_bytes(C)];
+  alignas(16) uint8_t wst[NCONS / 32][128 * C];  // per-warp staging of the warp-autonomous gather: rows x tw x C <= 128 C bytes
 };
 
 template <int C>
@@ -1033,6 +1039,164 @@ __device__ void gather_fast(const TC<C>& c) {
   }
 }
 
+// ------------------------------------------------------------------ warp-autonomous executors
+// WRITE passes of gather tiles need no CTA-wide barrier: every consumer warp takes its own rows of
+// the tile, stores them itself and moves on to the next tile on its own.  (The same was tried for
+// flat runs -- each warp storing its 1.5 KB slice with its own TMA store, in place or through private
+// staging -- and lost 10-25 % against one 9 KB store per tile behind a CTA barrier: profiles/r01_v10.)
+
+// Gather tile with one or two spatial entries, WRITE pass (the per-pixel arithmetic is gather_fast's).
+// A warp takes whole rows of the tile: 4 pixels per lane, 32 / (tw / 4) rows per step, steps 8 apart.
+// The step's rows go through `wst` (this warp's private staging, rows x tw x C bytes) so that they
+// leave as 16-byte vectors; only __syncwarp() orders the two.  PLAIN: the staged bytes are the
+// result (no LUT, no Color), so the 4 x C byte loads of a quad issue back to back.
+template <int C, bool TWO, bool PLAIN>
+__device__ __forceinline__ void gather_warp(const TC<C>& c, int warp, uint32_t wst) {
+  const TileState& t = *c.t;
+  const SlotInfo& in = *c.info;
+  const int H = c.H, W = c.W;
+  const int tw = in.x1 - in.x0, th = in.y1 - in.y0;
+  const int n_sp = t.n_sp;
+  const Spatial& ea = t.sp[n_sp - 1];
+  const Spatial& eb = t.sp[TWO ? n_sp - 2 : 0];
+  const bool a_geom = !TWO || ea.type == SP_GEOM;
+  const bool b_geom = TWO && eb.type == SP_GEOM;
+  const float t0 = ea.t[0], t1 = ea.t[1], t2 = ea.t[2], t3 = ea.t[3], t4 = ea.t[4], t5 = ea.t[5];
+  const float u0 = eb.t[0], u1 = eb.t[1], u2 = eb.t[2], u3 = eb.t[3], u4 = eb.t[4], u5 = eb.t[5];
+  const int ay0 = ea.y0, ay1 = ea.y1, ax0 = ea.x0, ax1 = ea.x1;
+  const int by0m = eb.y0, by1m = eb.y1, bx0m = eb.x0, bx1m = eb.x1;
+  const int kmode = t.kmode;
+  const bool use1 = !t.l1_id, use2 = !t.l2_id;
+  const float f = t.kfactor;
+  const uint32_t fill_a = in.fillc[0], fill_b = in.fillc[1];
+  const uint32_t fa_addr = smem_addr(&in.fillc[0]), fb_addr = smem_addr(&in.fillc[1]);  // a miss is just another address
+  const int pitch = in.pitch;
+  const uint32_t base0 = c.data - (uint32_t)(in.by0 * pitch + in.bxb0);
+  const int qpr = tw >> 2;              // quads per row: 4, 8, 12 or 16 for C == 3 (rows are whole 16-byte vectors)
+  const int rpi = in.rpi;               // rows per step: 32 / qpr
+  // lane -> (row of the step, quad of the row) and -> (row, vector) of the store, without divisions:
+  // lane / d == (lane * ceil(1024 / d)) >> 10 for lane < 32, d <= 32 (the producer computed the factors)
+  const int sub = (int)(((uint32_t)c.lane * in.inv_qpr) >> 10), rq = c.lane - sub * qpr;
+  const bool active = sub < rpi;
+  const int rowb = tw * C;              // bytes of a tile row: a whole number of 16-byte vectors
+  const int n16 = rowb >> 4;
+  const int nvec = rpi * n16;           // <= 32
+  const int vrow = (int)(((uint32_t)c.lane * in.inv_n16) >> 10), vq = c.lane - vrow * n16;
+  uint8_t* dbase = c.dst + ((size_t)in.y0 * W + in.x0) * C + (vq << 4);
+  const uint32_t st_w = wst + (uint32_t)(sub * rowb + (rq << 2) * C);
+  const uint32_t st_r = wst + (uint32_t)(vrow * rowb + (vq << 4));
+  const int xq = in.x0 + (rq << 2);
+  float ax[4], bx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float fx = small_uint_to_float((uint32_t)(xq + i));
+    ax[i] = __fmul_rn(t0, fx);
+    bx[i] = __fmul_rn(t3, fx);
+  }
+  const int n_steps = in.n_steps;
+  for (int g = warp; g < n_steps; g += NCONS / 32) {
+    const int ry = g * rpi + sub;
+    if (active && ry < th) {
+      const int y = in.y0 + ry;
+      const float fy = small_uint_to_float((uint32_t)y);
+      const float t1y = __fmul_rn(t1, fy), t4y = __fmul_rn(t4, fy);
+      uint32_t adr[4];
+      uint32_t hit = 0;  // bit i: pixel i shows entry a's colour, bit 4 + i: entry b's
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int ix = xq + i, iy = y;
+        bool hit_a, hit_b = false;
+        if (a_geom) {
+          int jx, jy;
+          const bool inx = src_index(__fadd_rn(__fadd_rn(ax[i], t1y), t2), W, jx);
+          const bool iny = src_index(__fadd_rn(__fadd_rn(bx[i], t4y), t5), H, jy);
+          hit_a = !(inx && iny);
+          ix = jx; iy = jy;
+        } else {
+          hit_a = (iy >= ay0) && (iy < ay1) && (ix >= ax0) && (ix < ax1);
+        }
+        if (TWO && !hit_a) {
+          if (b_geom) {
+            const float gx = small_uint_to_float((uint32_t)ix), gy = small_uint_to_float((uint32_t)iy);
+            int jx, jy;
+            const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(u0, gx), __fmul_rn(u1, gy)), u2), W, jx);
+            const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(u3, gx), __fmul_rn(u4, gy)), u5), H, jy);
+            hit_b = !(inx && iny);
+            ix = jx; iy = jy;
+          } else {
+            hit_b = (iy >= by0m) && (iy < by1m) && (ix >= bx0m) && (ix < bx1m);
+          }
+        }
+        adr[i] = !(hit_a || hit_b) ? base0 + (uint32_t)(iy * pitch + ix * C) : (hit_a ? fa_addr : fb_addr);
+        if (!PLAIN) hit |= (hit_a ? 1u : 0u) << i | (hit_b ? 16u : 0u) << i;
+      }
+      uint32_t v[4][C];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(adr[i] + ch);
+      if (!PLAIN) {
+        if (kmode == K_NONE) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(c.l1a + ch * 256 + v[i][ch]);
+        } else if (C == 3) {
+          if (use1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(c.l1a + ch * 256 + v[i][ch]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            color_pixel_f(small_uint_to_float(v[i][0]), small_uint_to_float(v[i][1 % C]), small_uint_to_float(v[i][2 % C]), f,
+                          v[i][0], v[i][1 % C], v[i][2 % C]);
+          if (use2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(c.l2a + ch * 256 + v[i][ch]);
+          }
+        }
+        // the spatial colours already are final colours
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool ha = (hit >> i) & 1u, hb = (hit >> (4 + i)) & 1u;
+          const uint32_t fillv = ha ? fill_a : fill_b;
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) v[i][ch] = (ha || hb) ? byte_of(fillv, ch) : v[i][ch];
+        }
+      }
+      uint32_t o[C];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+          const int bi = i * C + ch;
+          o[bi >> 2] = ((bi & 3) == 0) ? (v[i][ch] & 255u) : put_byte(o[bi >> 2], v[i][ch], bi & 3);
+        }
+#pragma unroll
+      for (int w = 0; w < C; ++w) sts_u32(st_w + 4 * w, o[w]);
+    }
+    __syncwarp();
+    const int r2 = g * rpi + vrow;
+    if (c.lane < nvec && r2 < th) *reinterpret_cast<uint4*>(dbase + (size_t)r2 * (W * C)) = lds_v4(st_r);
+    __syncwarp();
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void exec_gather_warp(const TC<C>& c, int warp, uint32_t wst) {
+  const TileState& t = *c.t;
+  const bool plain = (t.kmode == K_NONE) && t.l1_id;
+  if (t.n_sp == 2) {
+    if (plain) gather_warp<C, true, true>(c, warp, wst); else gather_warp<C, true, false>(c, warp, wst);
+  } else {
+    if (plain) gather_warp<C, false, true>(c, warp, wst); else gather_warp<C, false, false>(c, warp, wst);
+  }
+}
+
 // General form: any list of constant-fill warps and masks.
 template <int C, bool COUNT>
 __device__ void gather_list(const TC<C>& c) {
@@ -1137,8 +1301,9 @@ template <int C, bool COUNT>
 __device__ void exec_gather(const TC<C>& c) {
   const TileState& t = *c.t;
   const SlotInfo& in = *c.info;
-  if (t.n_sp == 1 && t.sp[0].type == SP_GEOM) gather_fast<C, COUNT, false>(c);
-  else if (t.n_sp == 2) gather_fast<C, COUNT, true>(c);
+  // (WRITE passes of the one- and two-entry forms run warp-autonomously: exec_gather_warp)
+  if (COUNT && t.n_sp == 1 && t.sp[0].type == SP_GEOM) gather_fast<C, true, false>(c);
+  else if (COUNT && t.n_sp == 2) gather_fast<C, true, true>(c);
   else gather_list<C, COUNT>(c);
   if (!COUNT) {
     store_barrier(c);  // also flips the staging tile: the next item writes the other one
@@ -1455,7 +1620,8 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
   in.cls = CLS_GENERIC; in.img = img; in.tile = tile; in.pass_kind = pass_kind;
   in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0; in.rowb = 0; in.pitch = 16; in.rows = 0;
   in.span = 1; in.sharp_rows = 1; in.fillc[0] = 0; in.fillc[1] = 0; in.paint = 0;
-  in.first = 1; in.last = 1; in.st_idx = 0; in.expected = 1u; in._pad[0] = in._pad[1] = in._pad[2] = 0;
+  in.first = 1; in.last = 1; in.st_idx = 0; in.expected = 1u; in.rpi = 1; in.n_steps = 0; in.inv_n16 = 1024u; in.inv_qpr = 1024u; in._pad = 0;
+  in.src = nullptr; in.dst = nullptr;
   d.tx_bytes = 0;
   d.src_sel = t.src_sel;
   d.box_overflow = false;
@@ -1537,7 +1703,14 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
     if (fast && (p.flags & 4) && src16 && dst16) {  // CutOut only: a flat run with the rectangles painted over it
       const int u0 = min(p.flat_units, tile * p.flat_upt), u1 = min(p.flat_units, u0 + p.flat_upt);
       in.cls = CLS_FLAT;
-      in.paint = n_sp;
+      // paint only if a rectangle reaches the rows of this run (most tiles of a CutOut image are plain)
+      if (u1 > u0) {
+        constexpr int PPU = UB / C;
+        const int yf = (u0 * PPU) / W, yl = (u1 * PPU - 1) / W;
+        bool hit = false;
+        for (int k = 0; k < n_sp; ++k) hit = hit || (yl >= t.sp[k].y0 && yf < t.sp[k].y1 && t.sp[k].x1 > t.sp[k].x0);
+        in.paint = hit ? n_sp : 0;
+      }
       reg.x0 = u0; reg.x1 = u1; reg.y0 = 0; reg.y1 = 0;
       d.tx_bytes = (uint32_t)(u1 - u0) * UB;
     } else {
@@ -1609,7 +1782,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   const uint32_t full0 = smem_addr(&sm->full[0]), empty0 = smem_addr(&sm->empty[0]);
   const uint32_t stbar0 = smem_addr(&sm->stbar[0]);
   if (tid == 0) {
-    for (int u = 0; u < NU; ++u) { mbar_init(full0 + 8 * u, 1); mbar_init(empty0 + 8 * u, NCONS); }
+    for (int u = 0; u < NU; ++u) { mbar_init(full0 + 8 * u, 1); mbar_init(empty0 + 8 * u, NCONS / 32); }
     for (int b = 0; b < NST; ++b) mbar_init(stbar0 + 8 * b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
@@ -1617,41 +1790,48 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   TL_STAMP(1);
-  // first passes of all images: the bins back to back
-  unsigned bin_end[NBINS];
-  unsigned n_entries = 0;
-#pragma unroll
-  for (int b = 0; b < NBINS; ++b) {
-    n_entries += __ldcg(p.counters + b);
-    bin_end[b] = n_entries;
-  }
-  // A claim is a *chunk* of one entry: one tile for the heavy bins, G consecutive tiles for the
-  // light ones (one atomic, one image lookup and one TileState fetch per chunk).  G grows with the
-  // work per CTA so that small batches keep enough chunks per CTA for the dynamic schedule to
-  // balance the tail.  The bins form four segments: non-final heavy | light, final heavy | light.
-  const unsigned n_tiles_u = (unsigned)p.n_tiles;
-  unsigned G = 1;
-  {
-    const unsigned per_cta = (n_entries * n_tiles_u) / gridDim.x;
-    if (per_cta >= 48u) G = 4; else if (per_cta >= 12u) G = 2;
-  }
-  const unsigned cpi = (n_tiles_u + G - 1u) / G;  // chunks per image of a light bin
-  unsigned seg_entry0[4], seg_begin[5];
-  {
-    const int first_bin[4] = {0, HEAVY_BINS, NBINS / 2, NBINS / 2 + HEAVY_BINS};
-    const int last_bin[4] = {HEAVY_BINS - 1, NBINS / 2 - 1, NBINS / 2 + HEAVY_BINS - 1, NBINS - 1};
-    seg_begin[0] = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      seg_entry0[k] = first_bin[k] ? bin_end[first_bin[k] - 1] : 0u;
-      seg_begin[k + 1] = seg_begin[k] + (bin_end[last_bin[k]] - seg_entry0[k]) * ((k & 1) ? cpi : n_tiles_u);
-    }
-  }
-  const unsigned n_chunks = seg_begin[4];
-
   if (tid >= NCONS) {
     // ------------------------------------------------------------------ producer warp
     const int lane = tid - NCONS;
+    // first passes of all images: the bins back to back
+    // (one lane per bin reads its length -- every thread of every CTA reading the same few words made
+    // that cache line a hot spot worth up to 15 us of start-up -- and a warp scan turns them into ends)
+    unsigned bin_end[NBINS];
+    unsigned n_entries = 0;
+    {
+      unsigned incl = (lane < NBINS) ? __ldcg(p.counters + lane) : 0u;
+  #pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += o;
+      }
+  #pragma unroll
+      for (int b = 0; b < NBINS; ++b) bin_end[b] = __shfl_sync(0xFFFFFFFFu, incl, b);
+      n_entries = bin_end[NBINS - 1];
+    }
+    // A claim is a *chunk* of one entry: one tile for the heavy bins, G consecutive tiles for the
+    // light ones (one atomic, one image lookup and one TileState fetch per chunk).  G grows with the
+    // work per CTA so that small batches keep enough chunks per CTA for the dynamic schedule to
+    // balance the tail.  The bins form four segments: non-final heavy | light, final heavy | light.
+    const unsigned n_tiles_u = (unsigned)p.n_tiles;
+    unsigned G = 1;
+    const unsigned per_cta = (n_entries * n_tiles_u) / gridDim.x;  // tiles per CTA
+    if (per_cta >= 48u) G = 4; else if (per_cta >= 12u) G = 2;
+    const unsigned cpi = (n_tiles_u + G - 1u) / G;  // chunks per image of a light bin
+    unsigned seg_entry0[4], seg_begin[5];
+    {
+      const int first_bin[4] = {0, HEAVY_BINS, NBINS / 2, NBINS / 2 + HEAVY_BINS};
+      const int last_bin[4] = {HEAVY_BINS - 1, NBINS / 2 - 1, NBINS / 2 + HEAVY_BINS - 1, NBINS - 1};
+      seg_begin[0] = 0;
+  #pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        seg_entry0[k] = first_bin[k] ? bin_end[first_bin[k] - 1] : 0u;
+        seg_begin[k + 1] = seg_begin[k] + (bin_end[last_bin[k]] - seg_entry0[k]) * ((k & 1) ? cpi : n_tiles_u);
+      }
+    }
+    const unsigned n_chunks = seg_begin[4];
+    TL_STAMP(13);
+
     unsigned* work = p.counters + NBINS;
     struct Chunk { int img, t0, t1; unsigned expected; int local; };
     // image and tiles of a global chunk (img = -1 past the end)
@@ -1692,7 +1872,9 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     // once per chunk; a published ticket goes into the pipeline ahead of the global queue, so the
     // next pass of an image is spread over all CTAs as soon as it exists.  p.counters[NBINS + 3]
     // counts the images that may still publish: when it is zero an unpublished ticket is void.
-    const unsigned Gc = (G >= 4u) ? 2u : 1u;
+    // (large batches: a ticket is a whole image, so a CTA runs 16+ tiles of one executor before its code changes again)
+    unsigned Gc = 1u;
+    while (Gc * 2u <= n_tiles_u && Gc * 16u <= per_cta) Gc *= 2u;  // at most an eighth of a CTA's share
     const unsigned cpi_c = (n_tiles_u + Gc - 1u) / Gc;
     unsigned* cwork = p.counters + NBINS + 1;
     volatile unsigned* pending = p.counters + NBINS + 3;
@@ -1706,13 +1888,17 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     unsigned chunk_next;  // claimed, not yet resolved
     unsigned ticket;
     {
-      unsigned v = 0, tv = 0;
-      if (lane == 0) { v = atomicAdd(work, 3u); tv = atomicAdd(cwork, 1u); }
-      v = __shfl_sync(0xFFFFFFFFu, v, 0);
+      // three separate claims (in flight together): all CTAs start at once, so the first chunks --
+      // the most expensive tiles of the batch -- are dealt round-robin instead of three to a CTA
+      unsigned v0 = 0, v1 = 0, v2 = 0, tv = 0;
+      if (lane == 0) { v0 = atomicAdd(work, 1u); v1 = atomicAdd(work, 1u); v2 = atomicAdd(work, 1u); tv = atomicAdd(cwork, 1u); }
+      v0 = __shfl_sync(0xFFFFFFFFu, v0, 0);
+      v1 = __shfl_sync(0xFFFFFFFFu, v1, 0);
+      chunk_next = __shfl_sync(0xFFFFFFFFu, v2, 0);
       ticket = __shfl_sync(0xFFFFFFFFu, tv, 0);
-      c0 = global_chunk(v);
-      c1 = global_chunk(v + 1u);
-      chunk_next = v + 2u;
+      TL_STAMP(5);
+      c0 = global_chunk(v0);
+      c1 = global_chunk(v1);
     }
     bool g_done = false;      // the global queue is exhausted
     bool ticket_wait = false; // a new ticket has been requested (traw)
@@ -1771,6 +1957,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
         TL_T0();
         mbar_wait(stbar0 + 8 * sb0, (st_par >> sb0) & 1u);
         TL_ACC(9);
+        TL_STAMP_ONCE(6);
         st_par ^= 1u << sb0;
         const TileState& st = sm->stg[sb0];
         const int img0 = c0.img;
@@ -1793,6 +1980,23 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
             d.in.st_idx = (int)sb0;  // the consumers read the prefetched state in place
             d.in.expected = c0.expected;
             if (lane == 0) {
+              const size_t img_off = (size_t)img0 * img_bytes;
+              const uint8_t* src = (d.src_sel == 0) ? p.in + img_off
+                                                   : p.scratch + (size_t)(2 * (size_t)img0 + (d.src_sel - 1)) * p.scratch_stride;
+              d.in.src = src;
+              d.in.dst = (d.in.pass_kind == PASS_WRITE_OUT)
+                             ? p.out + img_off
+                             : p.scratch + (size_t)(2 * (size_t)img0 + (st.dst_sel - 1)) * p.scratch_stride;
+              if (d.in.cls == CLS_GATHER) {  // split of the tile over lanes and warp steps (exec_gather_warp)
+                const int tw = d.in.x1 - d.in.x0, th = d.in.y1 - d.in.y0;
+                const int qpr = max(1, tw >> 2);
+                const int rpi = max(1, 32 / qpr);
+                const int n16 = max(1, (tw * C) >> 4);
+                d.in.rpi = rpi;
+                d.in.n_steps = (th + rpi - 1) / rpi;
+                d.in.inv_n16 = (uint32_t)((1024 + n16 - 1) / n16);
+                d.in.inv_qpr = (uint32_t)((1024 + qpr - 1) / qpr);
+              }
               sm->info[u] = d.in;
               const uint32_t fb = full0 + 8 * u;
               const uint32_t dst = smem_addr(sm->data[u]);
@@ -1800,9 +2004,6 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
                 mbar_arrive(fb);
               } else {
                 mbar_arrive_expect_tx(fb, d.tx_bytes);
-                const size_t img_off = (size_t)img0 * img_bytes;
-                const uint8_t* src = (d.src_sel == 0) ? p.in + img_off
-                                                     : p.scratch + (size_t)(2 * (size_t)img0 + (d.src_sel - 1)) * p.scratch_stride;
                 if (d.in.cls == CLS_FLAT) {
                   constexpr int UB = (C == 3) ? 48 : 16;
                   bulk_load(dst, src + (size_t)d.in.x0 * UB, d.tx_bytes, fb);
@@ -1816,6 +2017,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
               }
             }
             __syncwarp();
+            TL_STAMP_ONCE(7);
           };
           // A gather tile whose source box does not fit two units is issued as 2 / 4 parts.  The
           // first part of the chunk's first tile and the last part of its last tile carry the
@@ -1886,6 +2088,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
   c.nstore = &nstore;
   c.p = &p; c.sm = sm; c.r = smem_addr(sm->r);
   c.H = H; c.W = W; c.HW = H * W; c.img_bytes = img_bytes; c.tid = tid; c.lane = tid & 31;
+  const int warp = tid >> 5, lane = tid & 31;
   uint32_t cu = 0;        // next unit (monotonic)
   uint32_t full_par = 0;  // parity to wait for on full[u]
   for (;;) {
@@ -1899,24 +2102,21 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     if (cls == CLS_END) break;
     TL_STAMP_ONCE(2);
     if (cls == CLS_SKIP) {
-      mbar_arrive(empty0 + 8 * u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * u);
       ++cu;
       continue;
     }
     const int span = info.span;
     const unsigned expected = info.expected;  // chunks of the image that report once each, on their last tile
     const int img = info.img, pass_kind = info.pass_kind;
-    const size_t img_off = (size_t)img * img_bytes;
     const TileState& st = sm->stg[info.st_idx];
     c.t = &st; c.info = &info; c.tile = info.tile;
     c.data = smem_addr(sm->data[u]);
     c.ostage = c.r + (nstore & 1u) * ostage_bytes(C);
     c.l1a = smem_addr(&st.l1[0][0]); c.l2a = smem_addr(&st.l2[0][0]);
-    c.src = (st.src_sel == 0) ? p.in + img_off
-                              : p.scratch + (size_t)(2 * (size_t)img + (st.src_sel - 1)) * p.scratch_stride;
-    c.dst = (pass_kind == PASS_WRITE_OUT)
-                ? p.out + img_off
-                : p.scratch + (size_t)(2 * (size_t)img + (st.dst_sel - 1)) * p.scratch_stride;
+    c.src = info.src;
+    c.dst = info.dst;
     ImgState* g = p.states + img;
     const int is_last = info.last;
     TL_T0();
@@ -1935,23 +2135,31 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
         }
         if (tid < CHB_MAX_CHAIN && sm->color_cnt[tid]) atomicAdd(&g->color_cnt[tid], sm->color_cnt[tid]);
       }
+    } else if (cls == CLS_GATHER && (st.n_sp == 2 || (st.n_sp == 1 && st.sp[0].type == SP_GEOM))) {
+      exec_gather_warp<C>(c, warp, smem_addr(sm->wst[warp]));
     } else {
       run_tile<C, false>(c);
     }
     TL_ACC(7 + cls);  // cls 1..5 -> slots 8..12
     TL_ADD(5, 1);
     TL_STAMP(3);
-    mbar_arrive(empty0 + 8 * u);  // done with the unit(s): state, info and staged bytes
-    if (span == 2) mbar_arrive(empty0 + 8 * (u + 1));
+    // this warp is done with the unit(s): state, info and staged bytes
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(empty0 + 8 * u);
+      if (span == 2) mbar_arrive(empty0 + 8 * (u + 1));
+    }
     cu += span;
     if (pass_kind == PASS_WRITE_OUT || !is_last) continue;
 
     // ---- COUNT / WRITE_SCRATCH: the CTA that completes the image's last chunk resumes the chain walk
     TL_T0();
-    if (tid < 32) {
-      // the finaliser scratch below aliases the output staging tiles; a scratch image must also
-      // have landed in global memory before the pass is reported complete
-      if (pass_kind == PASS_WRITE_SCRATCH) { bulk_wait_all0(); fence_proxy_async_all(); } else { bulk_wait_read0(); }
+    // the finaliser scratch below aliases the output staging tiles; a scratch image must also
+    // have landed in global memory before the pass is reported complete
+    if (pass_kind == PASS_WRITE_SCRATCH) {
+      if (lane == 0) { bulk_wait_all0(); fence_proxy_async_all(); }
+    } else if (tid < 32) {
+      bulk_wait_read0();
     }
     cons_sync();
     if (tid == 0) {

@@ -33,8 +33,8 @@ try:
 except Exception as e: print("no sweep", e)
 PY
 if [ -f chambers_b200/libchambers_aug_timeline.so ]; then
-  for spec in ${TIMELINES:-"256 randaugment" "4096 Equalize" "4096 randaugment"}; do
-    set -- $spec
+  for spec in ${TIMELINES:-256,randaugment 4096,Equalize 4096,randaugment}; do
+    set -- ${spec//,/ }
     echo "=== timeline B=$1 $2"
     CHB_LIB=$PWD/chambers_b200/libchambers_aug_timeline.so timeout 300 python tools/timeline.py --batch $1 --policy $2 --out gpurun_out/timeline_$1_$2.json 2>&1 | tail -40
   done

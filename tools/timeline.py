@@ -83,6 +83,10 @@ def main():
         if worked.any():
             lv["first_tile_us"] = rel(cons[worked, 2])
             lv["last_tile_done_us"] = rel(cons[worked, 3])
+        for k, nm in ((13, "prod_counters_read_us"), (5, "prod_first_claim_us"), (6, "prod_first_state_us"), (7, "prod_first_issue_us")):
+            ok = prod[:, k] > 0
+            if ok.any():
+                lv[nm] = rel(prod[ok, k])
         tot = lambda a: float(a.sum())  # noqa: E731
         lv["consumer_cycles"] = {"wait_full": tot(cons[:, 6]), "finalise": tot(cons[:, 13]), "finalised_images": int(cons[:, 14].sum())}
         for k, name in CLS.items():
@@ -91,7 +95,8 @@ def main():
                                  "plan": tot(prod[:, 11]), "quiesce": tot(prod[:, 12])}
         nct = max(1, int(live.sum()))
         print("level %d: %d CTAs (%d with tiles), %d tiles" % (L, lv["ctas"], lv["ctas_with_tiles"], lv["tiles"]))
-        for k in ("enter_us", "dep_wait_done_us", "first_tile_us", "last_tile_done_us", "exit_us"):
+        for k in ("enter_us", "dep_wait_done_us", "prod_counters_read_us", "prod_first_claim_us", "prod_first_state_us", "prod_first_issue_us",
+                  "first_tile_us", "last_tile_done_us", "exit_us"):
             if k in lv:
                 print("   %-18s first %8.1f  last %8.1f" % (k, lv[k][0], lv[k][1]))
         print("   consumer cycles per CTA: " + "  ".join("%s %.0f" % (k, v / nct) for k, v in lv["consumer_cycles"].items() if k != "finalised_images"))
