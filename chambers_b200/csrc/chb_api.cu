@@ -37,7 +37,9 @@ struct Workspace {
   size_t inplace_bytes = 0;
 };
 
-static const int kPipe = 3;         // e2e pipeline depth (streams / staging buffers)
+static const int kPipeMax = 8;      // e2e pipeline: at most this many streams / staging buffers
+static int g_pipe = 4;              // streams in use (CHB_E2E_STREAMS)
+static int g_chunk_kb = 2560;       // target chunk size of the host path in KiB (CHB_E2E_CHUNK_KB)
 
 struct chb_ctx {
   int device = 0;
@@ -50,11 +52,11 @@ struct chb_ctx {
   std::vector<Workspace*> workspaces;
   std::vector<PolicyEntry*> cache;
   // e2e pipeline
-  cudaStream_t streams[kPipe] = {nullptr, nullptr, nullptr};
-  uint8_t* st_in[kPipe] = {nullptr, nullptr, nullptr};
-  uint8_t* st_out[kPipe] = {nullptr, nullptr, nullptr};
-  int32_t* st_replay[kPipe] = {nullptr, nullptr, nullptr};
-  int32_t* st_record[kPipe] = {nullptr, nullptr, nullptr};
+  cudaStream_t streams[kPipeMax] = {};
+  uint8_t* st_in[kPipeMax] = {};
+  uint8_t* st_out[kPipeMax] = {};
+  int32_t* st_replay[kPipeMax] = {};
+  int32_t* st_record[kPipeMax] = {};
   size_t st_img_bytes = 0, st_sched_bytes = 0;
 };
 
@@ -368,6 +370,8 @@ extern "C" int chb_init(int device, chb_ctx** out) {
         qres == cudaDriverEntryPointSuccess)
       g_encode_tiled = (EncodeTiledFn)fn;
   }
+  if (const char* e = getenv("CHB_E2E_STREAMS")) { int v = atoi(e); if (v >= 1 && v <= kPipeMax) g_pipe = v; }
+  if (const char* e = getenv("CHB_E2E_CHUNK_KB")) { int v = atoi(e); if (v >= 64) g_chunk_kb = v; }
   const char* fg = getenv("CHB_FORCE_GENERIC");
   ctx->force_generic = (fg && fg[0] && fg[0] != '0') ? 1 : 0;
   *out = ctx;
@@ -383,7 +387,7 @@ extern "C" void chb_destroy(chb_ctx* ctx) {
     cudaFree(ws->states); cudaFree(ws->lists); cudaFree(ws->counters); cudaFree(ws->scratch); cudaFree(ws->inplace);
     delete ws;
   }
-  for (int i = 0; i < kPipe; ++i) {
+  for (int i = 0; i < kPipeMax; ++i) {
     if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
     cudaFree(ctx->st_in[i]); cudaFree(ctx->st_out[i]);
     cudaFree(ctx->st_replay[i]); cudaFree(ctx->st_record[i]);
@@ -588,10 +592,22 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     p.strip_rows = (H + tp.n_tiles - 1) / tp.n_tiles;
     const int ub = (C == 3) ? 48 : 16;
     p.flat_units = (int)(img_bytes / ub);
+    p.n_flat_tiles = tp.n_tiles;
     p.flat_upt = (p.flat_units + tp.n_tiles - 1) / tp.n_tiles;
     p.flags = ((((uintptr_t)d_in & 15) == 0) ? 1 : 0) | ((((uintptr_t)p.out & 15) == 0) ? 2 : 0) |
               (((img_bytes & 15) == 0) ? 4 : 0) | (((((size_t)W * C) & 15) == 0) ? 8 : 0);
     if (!(p.flags & 4)) p.flags &= ~3;  // images that are not whole 16-byte units are not aligned beyond the first
+    // When every pass without a spatial op runs as a flat run (aligned batch, fast executors), flat
+    // runs get their own, smaller tile count: tiles of up to 256 units keep all 256 consumer threads
+    // busy (a 224 x 224 x 3 image is 13 runs of 242 units instead of 16 of 196).
+    if ((p.flags & 7) == 7 && !p.force_generic && p.flat_units > 0) {
+      int nf = (p.flat_units + 255) / 256;
+      if (nf < 1) nf = 1;
+      if (nf < tp.n_tiles) {
+        p.n_flat_tiles = nf;
+        p.flat_upt = (p.flat_units + nf - 1) / nf;
+      }
+    }
   }
   // gather tiles fetch their source bounding box as one 3-D tensor-map box (rows must be whole 16-byte units)
   chb::TMap tm_in, tm_scr;
@@ -665,29 +681,29 @@ extern "C" int chb_apply_op(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, i
 
 // ------------------------------------------------------------------------------ e2e pipeline
 static int ensure_staging(chb_ctx* ctx, size_t img_bytes, size_t sched_bytes) {
-  for (int i = 0; i < kPipe; ++i)
+  for (int i = 0; i < g_pipe; ++i)
     if (!ctx->streams[i]) CHB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
   if (img_bytes > ctx->st_img_bytes) {
-    for (int i = 0; i < kPipe; ++i) {
+    for (int i = 0; i < g_pipe; ++i) {
       if (ctx->st_in[i]) CHB_CUDA(ctx, cudaFree(ctx->st_in[i]));
       if (ctx->st_out[i]) CHB_CUDA(ctx, cudaFree(ctx->st_out[i]));
       ctx->st_in[i] = ctx->st_out[i] = nullptr;
     }
     ctx->st_img_bytes = 0;
-    for (int i = 0; i < kPipe; ++i) {
+    for (int i = 0; i < g_pipe; ++i) {
       CHB_CUDA(ctx, cudaMalloc(&ctx->st_in[i], img_bytes));
       CHB_CUDA(ctx, cudaMalloc(&ctx->st_out[i], img_bytes));
     }
     ctx->st_img_bytes = img_bytes;
   }
   if (sched_bytes > ctx->st_sched_bytes) {
-    for (int i = 0; i < kPipe; ++i) {
+    for (int i = 0; i < g_pipe; ++i) {
       if (ctx->st_replay[i]) CHB_CUDA(ctx, cudaFree(ctx->st_replay[i]));
       if (ctx->st_record[i]) CHB_CUDA(ctx, cudaFree(ctx->st_record[i]));
       ctx->st_replay[i] = ctx->st_record[i] = nullptr;
     }
     ctx->st_sched_bytes = 0;
-    for (int i = 0; i < kPipe; ++i) {
+    for (int i = 0; i < g_pipe; ++i) {
       CHB_CUDA(ctx, cudaMalloc(&ctx->st_replay[i], sched_bytes));
       CHB_CUDA(ctx, cudaMalloc(&ctx->st_record[i], sched_bytes));
     }
@@ -714,8 +730,13 @@ extern "C" int chb_policy_apply_host(chb_ctx* ctx, const uint8_t* h_in, uint8_t*
                          seed, call_counter, nullptr, nullptr, 0);
   }
   if (!h_in || !h_out) return fail(ctx, CHB_ERR_INVALID, "NULL image pointer");
-  // chunk so that copy-in, kernel and copy-out of neighbouring chunks overlap.
-  int n_chunks = 8;
+  // chunk so that copy-in, kernel and copy-out of neighbouring chunks overlap: small enough that the
+  // first copy-in and the last copy-out (which overlap nothing) are short, large enough that a chunk's
+  // copies dwarf its launch overheads.
+  long long n_chunks_ll = (long long)(((size_t)B * img + (size_t)g_chunk_kb * 1024 - 1) / ((size_t)g_chunk_kb * 1024));
+  if (n_chunks_ll < 1) n_chunks_ll = 1;
+  if (n_chunks_ll > 64) n_chunks_ll = 64;
+  int n_chunks = (int)n_chunks_ll;
   if (B < n_chunks) n_chunks = B;
   const int per = (B + n_chunks - 1) / n_chunks;
   const size_t sched_per_img = (size_t)policy->n_draws * K * CHB_SCHED_FIELDS * sizeof(int32_t);
@@ -723,7 +744,7 @@ extern "C" int chb_policy_apply_host(chb_ctx* ctx, const uint8_t* h_in, uint8_t*
   if (r != CHB_OK) return r;
   for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
     const int nb = (B - b0 < per) ? (B - b0) : per;
-    const int sl = c % kPipe;
+    const int sl = c % g_pipe;
     cudaStream_t st = ctx->streams[sl];
     // staging slot reuse is ordered by the slot's own stream.
     CHB_CUDA(ctx, cudaMemcpyAsync(ctx->st_in[sl], h_in + (size_t)b0 * img, (size_t)nb * img, cudaMemcpyHostToDevice, st));
@@ -740,6 +761,6 @@ extern "C" int chb_policy_apply_host(chb_ctx* ctx, const uint8_t* h_in, uint8_t*
       CHB_CUDA(ctx, cudaMemcpyAsync((uint8_t*)h_record + (size_t)b0 * sched_per_img, ctx->st_record[sl],
                                     (size_t)nb * sched_per_img, cudaMemcpyDeviceToHost, st));
   }
-  for (int i = 0; i < kPipe; ++i) CHB_CUDA(ctx, cudaStreamSynchronize(ctx->streams[i]));
+  for (int i = 0; i < g_pipe; ++i) CHB_CUDA(ctx, cudaStreamSynchronize(ctx->streams[i]));
   return CHB_OK;
 }

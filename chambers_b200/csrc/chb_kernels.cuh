@@ -212,6 +212,8 @@ __device__ __forceinline__ int bin_of(const TileState& t) {
   return group + (t.kmode == K_COLOR ? 7 : 8);
 }
 constexpr int HEAVY_BINS = 4;  // bins 0..3 of a group: tiles cost microseconds each, claimed one at a time
+constexpr int FLAT_BIN0 = 6;   // bins 6..8 of a group: flat runs
+constexpr int CONT_FLAT = 1 << 30;
 // Queues image `img` for its first pass.
 __device__ __forceinline__ void enqueue_pass(const KParams& p, const TileState& t, int img) {
   const int bin = bin_of(t);
@@ -832,7 +834,7 @@ __device__ void exec_flat(const TC<C>& c) {
     }
   }
   // ragged tail of the image (whole pixels, fewer than one unit): last tile, one pixel per thread
-  if (c.tile == c.p->n_tiles - 1) {
+  if (c.tile == c.p->n_flat_tiles - 1) {
     const int p0 = (c.img_bytes / UB) * UB / C;
     for (int pix = p0 + c.tid; pix < c.HW; pix += NCONS) {
       int v[C];
@@ -1424,6 +1426,13 @@ __device__ void exec_gather_sharp(const TC<C>& c) {
   const uint32_t vbytes = (uint32_t)(((hh + 2) * vpitch + 15) & ~15);
   const uint32_t obytes = (uint32_t)(hh * tw * C);
   const int wpt = (tw * C) >> 2;             // output words per tile row
+  const uint32_t inv_vw = in.inv_qpr;        // ceil(2^32 / vw), from the producer
+  const bool one = (n_sp == 1) && !box_empty;
+  const Spatial& e0 = t.sp[0];
+  const bool e_geom = e0.type == SP_GEOM;
+  const float g0 = e0.t[0], g1 = e0.t[1], g2 = e0.t[2], g3 = e0.t[3], g4 = e0.t[4], g5 = e0.t[5];
+  const int my0 = e0.y0, my1 = e0.y1, mx0 = e0.x0, mx1 = e0.x1;
+  const uint32_t fill_addr = smem_addr(&in.fillc[0]);  // the (final) colour bytes of the entry
   stores_drained(c.tid);  // the whole R region is used here
   cons_sync();
   for (int half = 0; half < 2; ++half) {
@@ -1432,31 +1441,53 @@ __device__ void exec_gather_sharp(const TC<C>& c) {
     // phase 1: virtual pre-image on [x0-1, x1] x [ya-1, yb]
     const int nv = (yb - ya + 2) * vw;
     for (int i = c.tid; i < nv; i += NCONS) {
-      const int vy = i / vw, vx = i - vy * vw;
+      const int vy = (int)__umulhi((uint32_t)i, inv_vw), vx = i - vy * vw;  // i / vw, exact for i < 2^16
       const int y = ya - 1 + vy, x = in.x0 - 1 + vx;
       uint32_t v[C];
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) v[ch] = 0;
       if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) {
-        int sx = x, sy = y;
-        const int k = resolve(t.sp, n_sp, H, W, sx, sy);
-        if (k < 0) {
-          if (!box_empty && (uint32_t)(sx - bx0) <= box_w && (uint32_t)(sy - by0) <= box_h) {
-            const uint32_t a = base0 + (uint32_t)(sy * pitch + sx * C);
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(a + ch);
+        if (one) {
+          // one constant-fill entry (all a two-op chain can put in front of Sharpness): the exact
+          // index step of the gather tiles; the staged box covers every source pixel
+          int sx = x, sy = y;
+          bool hit;
+          if (e_geom) {
+            const float fx = small_uint_to_float((uint32_t)x), fy = small_uint_to_float((uint32_t)y);
+            const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(g0, fx), __fmul_rn(g1, fy)), g2), W, sx);
+            const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(g3, fx), __fmul_rn(g4, fy)), g5), H, sy);
+            hit = !(inx && iny);
           } else {
-            const uint8_t* px = c.src + ((size_t)sy * W + sx) * C;
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) v[ch] = ldg_pixel(px + ch);
+            hit = (y >= my0) && (y < my1) && (x >= mx0) && (x < mx1);
           }
-          if (use1) {
+          const uint32_t a = hit ? fill_addr : base0 + (uint32_t)(sy * pitch + sx * C);
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(a + ch);
+          if (use1 && !hit) {
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(c.l1a + ch * 256 + v[ch]);
           }
         } else {
+          int sx = x, sy = y;
+          const int k = resolve(t.sp, n_sp, H, W, sx, sy);
+          if (k < 0) {
+            if (!box_empty && (uint32_t)(sx - bx0) <= box_w && (uint32_t)(sy - by0) <= box_h) {
+              const uint32_t a = base0 + (uint32_t)(sy * pitch + sx * C);
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) v[ch] = (uint32_t)t.sp[k].color[ch];
+              for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(a + ch);
+            } else {
+              const uint8_t* px = c.src + ((size_t)sy * W + sx) * C;
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) v[ch] = ldg_pixel(px + ch);
+            }
+            if (use1) {
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(c.l1a + ch * 256 + v[ch]);
+            }
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) v[ch] = (uint32_t)t.sp[k].color[ch];
+          }
         }
       }
       const uint32_t va = vbuf + (uint32_t)(vy * vpitch + 4 - C + vx * C);
@@ -1812,24 +1843,29 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     // A claim is a *chunk* of one entry: one tile for the heavy bins, G consecutive tiles for the
     // light ones (one atomic, one image lookup and one TileState fetch per chunk).  G grows with the
     // work per CTA so that small batches keep enough chunks per CTA for the dynamic schedule to
-    // balance the tail.  The bins form four segments: non-final heavy | light, final heavy | light.
-    const unsigned n_tiles_u = (unsigned)p.n_tiles;
+    // balance the tail.  Each group of bins (passes that are not / are the image's last) forms three
+    // segments: heavy | light 2-D tiles | flat runs (which have their own tile count, p.n_flat_tiles).
+    const unsigned n_tiles_u = (unsigned)p.n_tiles, n_flat_u = (unsigned)p.n_flat_tiles;
     unsigned G = 1;
     const unsigned per_cta = (n_entries * n_tiles_u) / gridDim.x;  // tiles per CTA
     if (per_cta >= 48u) G = 4; else if (per_cta >= 12u) G = 2;
-    const unsigned cpi = (n_tiles_u + G - 1u) / G;  // chunks per image of a light bin
-    unsigned seg_entry0[4], seg_begin[5];
+    const unsigned cpi = (n_tiles_u + G - 1u) / G;       // chunks per image of a light bin
+    const unsigned cpi_flat = (n_flat_u + G - 1u) / G;   // ... of a flat bin
+    constexpr int NSEG = 6;
+    unsigned seg_entry0[NSEG], seg_begin[NSEG + 1];
     {
-      const int first_bin[4] = {0, HEAVY_BINS, NBINS / 2, NBINS / 2 + HEAVY_BINS};
-      const int last_bin[4] = {HEAVY_BINS - 1, NBINS / 2 - 1, NBINS / 2 + HEAVY_BINS - 1, NBINS - 1};
+      const int H2 = NBINS / 2;
+      const int first_bin[NSEG] = {0, HEAVY_BINS, FLAT_BIN0, H2, H2 + HEAVY_BINS, H2 + FLAT_BIN0};
+      const int last_bin[NSEG] = {HEAVY_BINS - 1, FLAT_BIN0 - 1, H2 - 1, H2 + HEAVY_BINS - 1, H2 + FLAT_BIN0 - 1, NBINS - 1};
       seg_begin[0] = 0;
   #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < NSEG; ++k) {
+        const unsigned cp = (k % 3 == 0) ? n_tiles_u : (k % 3 == 1) ? cpi : cpi_flat;
         seg_entry0[k] = first_bin[k] ? bin_end[first_bin[k] - 1] : 0u;
-        seg_begin[k + 1] = seg_begin[k] + (bin_end[last_bin[k]] - seg_entry0[k]) * ((k & 1) ? cpi : n_tiles_u);
+        seg_begin[k + 1] = seg_begin[k] + (bin_end[last_bin[k]] - seg_entry0[k]) * cp;
       }
     }
-    const unsigned n_chunks = seg_begin[4];
+    const unsigned n_chunks = seg_begin[NSEG];
     TL_STAMP(13);
 
     unsigned* work = p.counters + NBINS;
@@ -1839,17 +1875,18 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       Chunk c = {-1, 0, 0, 1u, 0};
       if (chunk >= n_chunks) return c;
       unsigned sbeg = 0, sent = seg_entry0[0];
-      bool heavy = true;
+      int kind = 0;  // 0 heavy, 1 light, 2 flat
 #pragma unroll
-      for (int k = 1; k < 4; ++k)
-        if (chunk >= seg_begin[k]) { sbeg = seg_begin[k]; sent = seg_entry0[k]; heavy = !(k & 1); }
-      const unsigned cp = heavy ? n_tiles_u : cpi;
+      for (int k = 1; k < NSEG; ++k)
+        if (chunk >= seg_begin[k]) { sbeg = seg_begin[k]; sent = seg_entry0[k]; kind = k % 3; }
+      const unsigned cp = (kind == 0) ? n_tiles_u : (kind == 1) ? cpi : cpi_flat;
+      const unsigned tiles = (kind == 2) ? n_flat_u : n_tiles_u;
       const unsigned loc = chunk - sbeg;
       const unsigned e_in = loc / cp;
       const unsigned ci = loc - e_in * cp;
       const unsigned entry = sent + e_in;
-      c.t0 = (int)(heavy ? ci : ci * G);
-      c.t1 = min(p.n_tiles, c.t0 + (int)(heavy ? 1u : G));
+      c.t0 = (int)(kind == 0 ? ci : ci * G);
+      c.t1 = (int)min(tiles, (unsigned)c.t0 + (kind == 0 ? 1u : G));
       c.expected = cp;
       int bin = 0;
       unsigned first = 0;
@@ -1916,10 +1953,16 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       empty_par ^= 1u << u;
     };
     auto alloc_state = [&]() -> uint32_t { const uint32_t b = ring; ring = (ring + 1 == NST) ? 0u : ring + 1; return b; };
+    // (bit 30 of an entry: the pass is a flat run, which has n_flat_tiles tiles -- the tickets of the
+    // chunks beyond them are void)
     auto cont_chunk = [&](int entry_value) -> Chunk {
       Chunk c;
       const unsigned ci = ticket % cpi_c;
-      c.img = entry_value - 1; c.t0 = (int)(ci * Gc); c.t1 = min(p.n_tiles, c.t0 + (int)Gc); c.expected = cpi_c; c.local = 1;
+      const bool flat = (entry_value & CONT_FLAT) != 0;
+      const unsigned tiles = flat ? n_flat_u : n_tiles_u;
+      c.img = (entry_value & ~CONT_FLAT) - 1; c.t0 = (int)(ci * Gc); c.t1 = (int)min(tiles, ci * Gc + Gc);
+      c.expected = (tiles + Gc - 1u) / Gc; c.local = 1;
+      if (c.t0 >= c.t1) c.img = -1;
       return c;
     };
     if (c0.img >= 0) { sb0 = alloc_state(); fetch_state(c0.img, (int)sb0); }
@@ -1987,6 +2030,10 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
               d.in.dst = (d.in.pass_kind == PASS_WRITE_OUT)
                              ? p.out + img_off
                              : p.scratch + (size_t)(2 * (size_t)img0 + (st.dst_sel - 1)) * p.scratch_stride;
+              if (d.in.cls == CLS_GATHER_SHARP) {  // halo tile width -> exact division by multiplication
+                const unsigned vw = (unsigned)(d.in.x1 - d.in.x0 + 2);
+                d.in.inv_qpr = (uint32_t)((0x100000000ull + vw - 1ull) / vw);
+              }
               if (d.in.cls == CLS_GATHER) {  // split of the tile over lanes and warp steps (exec_gather_warp)
                 const int tw = d.in.x1 - d.in.x0, th = d.in.y1 - d.in.y0;
                 const int qpr = max(1, tw >> 2);
@@ -2186,6 +2233,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     for (int i = tid; i < STATE_VECS; i += NCONS)
       reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(fs)[i];
     const int fs_next_pass = fs->t.pass_kind;
+    const int fs_next_flat = (p.n_flat_tiles != p.n_tiles && (bin_of(fs->t) % (NBINS / 2)) >= FLAT_BIN0) ? CONT_FLAT : 0;
     // Publish the image's next pass: whichever CTAs hold the tickets of its chunks fetch the state
     // just written (and, after a WRITE_SCRATCH pass, the scratch image) with TMA loads.
     __threadfence();
@@ -2195,7 +2243,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       const bool more = fs_next_pass != PASS_WRITE_OUT;  // the image will publish again
       const unsigned pos = atomicAdd(p.counters + NBINS + 2, 1u);
       __threadfence();
-      *reinterpret_cast<volatile int*>(p.cont + pos) = img + 1;
+      *reinterpret_cast<volatile int*>(p.cont + pos) = (img + 1) | fs_next_flat;
       if (!more) {
         __threadfence();
         atomicSub(p.counters + NBINS + 3, 1u);
