@@ -195,25 +195,36 @@ __device__ __forceinline__ void reset_view(ImgState* s, int tid, int nt) {  // a
   }
 }
 
-// Executor bin of an image's next pass (see NBINS).  Passes that are not the image's last one
-// (COUNT / WRITE_SCRATCH) come first -- the CTA that finishes such a pass continues with the image's
-// next pass itself, so starting them early keeps that second stage out of the tail -- and within
-// each group the most expensive code runs first.
+// Executor bin of an image's next pass (see NBINS).  Bins are laid out in the order the work should
+// start: the heavy executors first (their tiles cost microseconds each, so they must not be left for
+// the tail) -- passes that are not the image's last one before final ones, because the image's next
+// pass can only be published once they are done -- then the light 2-D tiles and the flat runs, again
+// non-final before final.  Within each segment the most expensive code comes first.
+//   0..3   heavy, non-final     4..7   heavy, final
+//   8..9   light, non-final    10..12  flat, non-final    13..14  light, final    15..17  flat, final
+constexpr int HEAVY_BINS = 4;
+// segment k: first / last bin and kind (0 heavy: one tile per claim, 1 light, 2 flat)
+__host__ __device__ constexpr int seg_first(int k) { return k == 0 ? 0 : k == 1 ? 4 : k == 2 ? 8 : k == 3 ? 10 : k == 4 ? 13 : 15; }
+__host__ __device__ constexpr int seg_last(int k) { return k == 0 ? 3 : k == 1 ? 7 : k == 2 ? 9 : k == 3 ? 12 : k == 4 ? 14 : 17; }
+__host__ __device__ constexpr int seg_kind(int k) { return k < 2 ? 0 : (k == 2 || k == 4) ? 1 : 2; }
+constexpr int CONT_FLAT = 1 << 30;
+__device__ __forceinline__ bool is_flat_bin(int bin) { return (bin >= 10 && bin <= 12) || bin >= 15; }
 __device__ __forceinline__ int bin_of(const TileState& t) {
   bool any_geom = false;
   for (int k = 0; k < t.n_sp; ++k) any_geom = any_geom || (t.sp[k].type == SP_GEOM);
   const bool count = t.pass_kind == PASS_COUNT;
-  const int group = (t.pass_kind == PASS_WRITE_OUT) ? NBINS / 2 : 0;
-  if (t.kmode == K_SHARP) return group + (t.n_sp > 0 ? 0 : 1);
-  if (t.kmode == K_BILINEAR) return group + 2;
-  if (t.n_sp >= 2 && (any_geom || count)) return group + 3;
-  if (t.n_sp == 1 && (any_geom || count)) return group + (t.kmode == K_COLOR ? 4 : 5);
-  if (count) return group + 6;
-  return group + (t.kmode == K_COLOR ? 7 : 8);
+  const bool fin = t.pass_kind == PASS_WRITE_OUT;
+  int cost;  // executor cost class, most expensive first
+  if (t.kmode == K_SHARP) cost = t.n_sp > 0 ? 0 : 1;
+  else if (t.kmode == K_BILINEAR) cost = 2;
+  else if (t.n_sp >= 2 && (any_geom || count)) cost = 3;
+  else if (t.n_sp == 1 && (any_geom || count)) cost = t.kmode == K_COLOR ? 4 : 5;
+  else if (count) cost = 6;
+  else cost = t.kmode == K_COLOR ? 7 : 8;
+  if (cost < HEAVY_BINS) return (fin ? 4 : 0) + cost;
+  if (cost < 6) return (fin ? 13 : 8) + (cost - 4);
+  return (fin ? 15 : 10) + (cost - 6);
 }
-constexpr int HEAVY_BINS = 4;  // bins 0..3 of a group: tiles cost microseconds each, claimed one at a time
-constexpr int FLAT_BIN0 = 6;   // bins 6..8 of a group: flat runs
-constexpr int CONT_FLAT = 1 << 30;
 // Queues image `img` for its first pass.
 __device__ __forceinline__ void enqueue_pass(const KParams& p, const TileState& t, int img) {
   const int bin = bin_of(t);
@@ -1775,9 +1786,7 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
   in.span = (d.tx_bytes > (uint32_t)UNIT_BYTES) ? 2 : 1;
 }
 
-// Re-planning of one part of a split tile.  (Making this and the cold executors __noinline__ was
-// tried to shrink the kernel: the calls put the tile context on the stack and the flat path lost a
-// third of its speed, so everything stays inlined.)
+// Re-planning of one part of a split tile.
 template <int C>
 __device__ __forceinline__ TilePlanD plan_tile_part(const KParams& p, const TileState& t, int img, int tile, int split, int sub) {
   TilePlanD d;
@@ -1786,6 +1795,10 @@ __device__ __forceinline__ TilePlanD plan_tile_part(const KParams& p, const Tile
 }
 
 // ================================================================================ pass kernel
+// (Making the rarely used executors -- scalar, list gather, COUNT forms of the Sharpness executors --
+// real calls was measured twice to shrink the hot instruction footprint: the calls cost the flat
+// path 10-20 % (identity 69 -> 54 %, LUT ops 51 -> 44 % of the copy peak, profiles/r01_v12_cold_calls_rejected.json)
+// and did not move the small-batch time, so everything stays inlined.)
 template <int C, bool COUNT>
 __device__ __forceinline__ void run_tile(const TC<C>& c) {
   switch (c.info->cls) {
@@ -1843,8 +1856,8 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     // A claim is a *chunk* of one entry: one tile for the heavy bins, G consecutive tiles for the
     // light ones (one atomic, one image lookup and one TileState fetch per chunk).  G grows with the
     // work per CTA so that small batches keep enough chunks per CTA for the dynamic schedule to
-    // balance the tail.  Each group of bins (passes that are not / are the image's last) forms three
-    // segments: heavy | light 2-D tiles | flat runs (which have their own tile count, p.n_flat_tiles).
+    // balance the tail.  The bins form six segments (bin_of): heavy, light 2-D tiles and flat runs
+    // (which have their own tile count, p.n_flat_tiles), each for non-final and final passes.
     const unsigned n_tiles_u = (unsigned)p.n_tiles, n_flat_u = (unsigned)p.n_flat_tiles;
     unsigned G = 1;
     const unsigned per_cta = (n_entries * n_tiles_u) / gridDim.x;  // tiles per CTA
@@ -1853,17 +1866,12 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     const unsigned cpi_flat = (n_flat_u + G - 1u) / G;   // ... of a flat bin
     constexpr int NSEG = 6;
     unsigned seg_entry0[NSEG], seg_begin[NSEG + 1];
-    {
-      const int H2 = NBINS / 2;
-      const int first_bin[NSEG] = {0, HEAVY_BINS, FLAT_BIN0, H2, H2 + HEAVY_BINS, H2 + FLAT_BIN0};
-      const int last_bin[NSEG] = {HEAVY_BINS - 1, FLAT_BIN0 - 1, H2 - 1, H2 + HEAVY_BINS - 1, H2 + FLAT_BIN0 - 1, NBINS - 1};
-      seg_begin[0] = 0;
-  #pragma unroll
-      for (int k = 0; k < NSEG; ++k) {
-        const unsigned cp = (k % 3 == 0) ? n_tiles_u : (k % 3 == 1) ? cpi : cpi_flat;
-        seg_entry0[k] = first_bin[k] ? bin_end[first_bin[k] - 1] : 0u;
-        seg_begin[k + 1] = seg_begin[k] + (bin_end[last_bin[k]] - seg_entry0[k]) * cp;
-      }
+    seg_begin[0] = 0;
+#pragma unroll
+    for (int k = 0; k < NSEG; ++k) {
+      const unsigned cp = (seg_kind(k) == 0) ? n_tiles_u : (seg_kind(k) == 1) ? cpi : cpi_flat;
+      seg_entry0[k] = seg_first(k) ? bin_end[seg_first(k) - 1] : 0u;
+      seg_begin[k + 1] = seg_begin[k] + (bin_end[seg_last(k)] - seg_entry0[k]) * cp;
     }
     const unsigned n_chunks = seg_begin[NSEG];
     TL_STAMP(13);
@@ -1878,7 +1886,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       int kind = 0;  // 0 heavy, 1 light, 2 flat
 #pragma unroll
       for (int k = 1; k < NSEG; ++k)
-        if (chunk >= seg_begin[k]) { sbeg = seg_begin[k]; sent = seg_entry0[k]; kind = k % 3; }
+        if (chunk >= seg_begin[k]) { sbeg = seg_begin[k]; sent = seg_entry0[k]; kind = seg_kind(k); }
       const unsigned cp = (kind == 0) ? n_tiles_u : (kind == 1) ? cpi : cpi_flat;
       const unsigned tiles = (kind == 2) ? n_flat_u : n_tiles_u;
       const unsigned loc = chunk - sbeg;
@@ -2233,7 +2241,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     for (int i = tid; i < STATE_VECS; i += NCONS)
       reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(fs)[i];
     const int fs_next_pass = fs->t.pass_kind;
-    const int fs_next_flat = (p.n_flat_tiles != p.n_tiles && (bin_of(fs->t) % (NBINS / 2)) >= FLAT_BIN0) ? CONT_FLAT : 0;
+    const int fs_next_flat = (p.n_flat_tiles != p.n_tiles && is_flat_bin(bin_of(fs->t))) ? CONT_FLAT : 0;
     // Publish the image's next pass: whichever CTAs hold the tickets of its chunks fetch the state
     // just written (and, after a WRITE_SCRATCH pass, the scratch image) with TMA loads.
     __threadfence();
