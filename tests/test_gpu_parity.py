@@ -317,3 +317,54 @@ def test_fast_executors_match_scalar_executor(A, shape):
             idx = list(range(3, 256, 37))
             want = oracle.apply_schedule(x.numpy()[idx], policy_of(layer), s[idx], elementwise=True)
             assert_same(fast[idx].cpu().numpy(), want, "oracle sample M=%d" % magnitude)
+
+
+def test_long_chains_every_pass_kind(A):
+    """Chains of six ops (up to five passes per image: COUNT and WRITE_SCRATCH passes published to
+    the continuation list and picked up by other CTAs of the same launch) against the oracle."""
+    x = random_images(192, 64, 80, 3, seed=31, kind="smooth")
+    layer = A.RandAugment(6, 10, elementwise=True)
+    for call in range(2):
+        y = run_layer(layer, x, training=True, seed=9, call_counter=call, record=True)
+        want = oracle.apply_schedule(x, policy_of(layer), layer.last_schedule, elementwise=True)
+        for b in range(x.shape[0]):
+            assert_same(y[b], want[b], "chain %r" % ([oracle.OP_NAMES[i] for i in layer.last_schedule[b, :, 0, 0]],))
+
+
+def test_large_batch_scheduler_paths(A):
+    """4096 x 224 x 224 x 3 (BASELINE configs[2] size): multi-tile claims and multi-tile continuation
+    tickets.  Sampled images against the oracle, run-to-run determinism, and shard invariance."""
+    g = torch.Generator().manual_seed(7)
+    x = torch.randint(0, 256, (4096, 224, 224, 3), dtype=torch.uint8, generator=g)
+    xg = x.cuda()
+    for layer in (A.RandAugment(2, 10, elementwise=True), A.AutoAugment(elementwise=True)):
+        y = layer(xg, training=True, seed=5, call_counter=1, record=True)
+        sched = layer.last_schedule
+        idx = list(range(0, 4096, 171))
+        want = oracle.apply_schedule(x.numpy()[idx], policy_of(layer), sched[idx], elementwise=True)
+        assert_same(y[idx].cpu().numpy(), want, type(layer).__name__ + " sample of 4096")
+        y2 = layer(xg, training=True, seed=5, call_counter=1)
+        assert torch.equal(y, y2), "two runs of the same call differ"
+        # the second half as its own shard: same pixels
+        half = layer(xg[2048:], training=True, seed=5, call_counter=1, batch_total=4096, image_index_base=2048)
+        assert torch.equal(half, y[2048:]), "shard differs from the whole batch"
+
+
+def test_concurrent_streams(A):
+    """Two streams run policy calls at the same time (their persistent kernels share the SMs, so not
+    every CTA of a launch is resident): nothing may be owned by a CTA that has not started.  Results
+    equal the single-stream run."""
+    x = random_images(512, 224, 224, 3, seed=41)
+    xg = to_gpu(x)
+    layer = A.RandAugment(3, 10, elementwise=True)
+    ref = [layer(xg, training=True, seed=2, call_counter=c) for c in range(4)]
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = {}
+    for rep in range(3):
+        for c in range(4):
+            with torch.cuda.stream(s1 if c % 2 == 0 else s2):
+                outs[c] = layer(xg, training=True, seed=2, call_counter=c)
+    torch.cuda.synchronize()
+    for c in range(4):
+        assert torch.equal(outs[c], ref[c]), "call %d differs when run concurrently" % c
