@@ -48,7 +48,8 @@ def build_variant(name, defines):
     """Debug / experiment build next to the production library: libchambers_aug_<name>.so compiled
     with extra -D flags (e.g. CHB_TIMELINE).  Select it at run time with CHB_LIB=<path>."""
     out = os.path.join(PKG_DIR, "libchambers_aug_%s.so" % name)
-    return build_library(force=True, out_path=out, extra=["-D" + d for d in defines], obj_tag="_" + name)
+    extra = [d if d.startswith("-") else "-D" + d for d in defines]  # raw nvcc flags pass through
+    return build_library(force=True, out_path=out, extra=extra, obj_tag="_" + name)
 
 
 def build_library(force=False, verbose=False, out_path=None, extra=(), obj_tag=""):

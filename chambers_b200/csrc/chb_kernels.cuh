@@ -64,6 +64,17 @@ struct Rect {
   int x0, x1, y0, y1;
 };
 
+// The value, but opaque to the optimiser at this point: everything an executor derives from it is
+// computed inside the executor.  (Without it the set-up of the rarely used executors -- float
+// conversions of the image size for the coordinate maps, row pitches -- is hoisted in front of the
+// executor dispatch and runs for every tile.)
+__device__ __forceinline__ int opaque(int v) {
+#ifndef CHB_NO_OPAQUE
+  asm volatile("" : "+r"(v));
+#endif
+  return v;
+}
+
 // Debug timeline (-DCHB_TIMELINE, tools/timeline.py): every pass CTA leaves two 16-word records,
 // [level][cta][producer | consumer][16], in KParams::timeline.  Stamps are %globaltimer (ns),
 // accumulators are clock64 cycles.  Compiled out of the production library.
@@ -508,7 +519,7 @@ struct alignas(16) SlotInfo {  // written by the producer, read by the consumers
   uint32_t expected;                 // COUNT / WRITE_SCRATCH: chunks of this image that report to tiles_done
   int32_t rpi;                       // warp-autonomous gather: tile rows per warp step (32 / quads per row)
   int32_t n_steps;                   //   steps of the tile: ceil(th / rpi)
-  uint32_t inv_n16, inv_qpr;         //   ceil(1024 / d) for d = 16-byte vectors / quads per tile row: lane / d == (lane * inv) >> 10
+  uint32_t inv_n16, inv_qpr;         //   inv_qpr = ceil(1024 / quads per tile row): lane / d == (lane * inv) >> 10 (GATHER_SHARP: ceil(2^32 / halo width))
   int32_t _pad;
   const uint8_t* src;                // source image of this pass (the batch or a scratch image)
   uint8_t* dst;                      // destination image (unused by COUNT passes)
@@ -524,7 +535,6 @@ struct alignas(128) PassSmem {
   TileState stg[NST];        // ring of prefetched TileStates, indexed by item number (see NST)
   alignas(128) uint8_t data[NU][UNIT_BYTES];
   alignas(128) uint8_t r[r_bytes(C)];
-  alignas(16) uint8_t wst[NCONS / 32][128 * C];  // per-warp staging of the warp-autonomous gather: rows x tw x C <= 128 C bytes
 };
 
 template <int C>
@@ -566,7 +576,7 @@ __device__ __forceinline__ void store_barrier(const TC<C>& c) {
 template <int C, bool COUNT>
 __device__ void exec_generic(const TC<C>& c) {
   const TileState& t = *c.t;
-  const int H = c.H, W = c.W;
+  const int H = opaque(c.H), W = opaque(c.W);
   const int rx0 = c.info->x0, ry0 = c.info->y0;
   const int rw = c.info->x1 - rx0;
   const int n = rw * (c.info->y1 - ry0);
@@ -1055,16 +1065,16 @@ __device__ void gather_fast(const TC<C>& c) {
 // ------------------------------------------------------------------ warp-autonomous executors
 // WRITE passes of gather tiles need no CTA-wide barrier: every consumer warp takes its own rows of
 // the tile, stores them itself and moves on to the next tile on its own.  (The same was tried for
-// flat runs -- each warp storing its 1.5 KB slice with its own TMA store, in place or through private
-// staging -- and lost 10-25 % against one 9 KB store per tile behind a CTA barrier: profiles/r01_v10.)
+// flat runs three ways -- each warp storing its 1.5 KB slice with its own TMA store, in place or
+// through private staging, or straight from registers with 16-byte vector stores -- and lost 7-25 %
+// against one 12 KB TMA store per tile behind a CTA barrier: profiles/r01_v10, r01_v13.)
 
 // Gather tile with one or two spatial entries, WRITE pass (the per-pixel arithmetic is gather_fast's).
-// A warp takes whole rows of the tile: 4 pixels per lane, 32 / (tw / 4) rows per step, steps 8 apart.
-// The step's rows go through `wst` (this warp's private staging, rows x tw x C bytes) so that they
-// leave as 16-byte vectors; only __syncwarp() orders the two.  PLAIN: the staged bytes are the
-// result (no LUT, no Color), so the 4 x C byte loads of a quad issue back to back.
+// A warp takes whole rows of the tile: 4 pixels (C words) per lane, 32 / (tw / 4) rows per step, steps
+// 8 apart; the words go straight to global memory.  PLAIN: the staged bytes are the result (no LUT,
+// no Color), so the 4 x C byte loads of a quad issue back to back.
 template <int C, bool TWO, bool PLAIN>
-__device__ __forceinline__ void gather_warp(const TC<C>& c, int warp, uint32_t wst) {
+__device__ __forceinline__ void gather_warp(const TC<C>& c, int warp) {
   const TileState& t = *c.t;
   const SlotInfo& in = *c.info;
   const int H = c.H, W = c.W;
@@ -1091,13 +1101,6 @@ __device__ __forceinline__ void gather_warp(const TC<C>& c, int warp, uint32_t w
   // lane / d == (lane * ceil(1024 / d)) >> 10 for lane < 32, d <= 32 (the producer computed the factors)
   const int sub = (int)(((uint32_t)c.lane * in.inv_qpr) >> 10), rq = c.lane - sub * qpr;
   const bool active = sub < rpi;
-  const int rowb = tw * C;              // bytes of a tile row: a whole number of 16-byte vectors
-  const int n16 = rowb >> 4;
-  const int nvec = rpi * n16;           // <= 32
-  const int vrow = (int)(((uint32_t)c.lane * in.inv_n16) >> 10), vq = c.lane - vrow * n16;
-  uint8_t* dbase = c.dst + ((size_t)in.y0 * W + in.x0) * C + (vq << 4);
-  const uint32_t st_w = wst + (uint32_t)(sub * rowb + (rq << 2) * C);
-  const uint32_t st_r = wst + (uint32_t)(vrow * rowb + (vq << 4));
   const int xq = in.x0 + (rq << 2);
   float ax[4], bx[4];
 #pragma unroll
@@ -1189,24 +1192,23 @@ __device__ __forceinline__ void gather_warp(const TC<C>& c, int warp, uint32_t w
           const int bi = i * C + ch;
           o[bi >> 2] = ((bi & 3) == 0) ? (v[i][ch] & 255u) : put_byte(o[bi >> 2], v[i][ch], bi & 3);
         }
+      // the lane's 4 pixels (C words) go straight to global memory: against staging the step's rows in
+      // shared memory and storing 16-byte vectors this was 4 % faster (no __syncwarp between steps)
+      uint32_t* gp = reinterpret_cast<uint32_t*>(c.dst + ((size_t)y * W + xq) * C);
 #pragma unroll
-      for (int w = 0; w < C; ++w) sts_u32(st_w + 4 * w, o[w]);
+      for (int w = 0; w < C; ++w) __stcg(gp + w, o[w]);
     }
-    __syncwarp();
-    const int r2 = g * rpi + vrow;
-    if (c.lane < nvec && r2 < th) *reinterpret_cast<uint4*>(dbase + (size_t)r2 * (W * C)) = lds_v4(st_r);
-    __syncwarp();
   }
 }
 
 template <int C>
-__device__ __forceinline__ void exec_gather_warp(const TC<C>& c, int warp, uint32_t wst) {
+__device__ __forceinline__ void exec_gather_warp(const TC<C>& c, int warp) {
   const TileState& t = *c.t;
   const bool plain = (t.kmode == K_NONE) && t.l1_id;
   if (t.n_sp == 2) {
-    if (plain) gather_warp<C, true, true>(c, warp, wst); else gather_warp<C, true, false>(c, warp, wst);
+    if (plain) gather_warp<C, true, true>(c, warp); else gather_warp<C, true, false>(c, warp);
   } else {
-    if (plain) gather_warp<C, false, true>(c, warp, wst); else gather_warp<C, false, false>(c, warp, wst);
+    if (plain) gather_warp<C, false, true>(c, warp); else gather_warp<C, false, false>(c, warp);
   }
 }
 
@@ -1215,7 +1217,7 @@ template <int C, bool COUNT>
 __device__ void gather_list(const TC<C>& c) {
   const TileState& t = *c.t;
   const SlotInfo& in = *c.info;
-  const int H = c.H, W = c.W;
+  const int H = opaque(c.H), W = opaque(c.W);
   const int n_sp = t.n_sp;
   const int bx0 = in.bx0, by0 = in.by0;
   const uint32_t box_w = (uint32_t)(in.bx1 - bx0), box_h = (uint32_t)(in.by1 - by0);
@@ -1420,7 +1422,7 @@ template <int C, bool COUNT>
 __device__ void exec_gather_sharp(const TC<C>& c) {
   const TileState& t = *c.t;
   const SlotInfo& in = *c.info;
-  const int H = c.H, W = c.W;
+  const int H = opaque(c.H), W = opaque(c.W);
   const int n_sp = t.n_sp;
   const int bx0 = in.bx0, by0 = in.by0;
   const uint32_t box_w = (uint32_t)(in.bx1 - bx0), box_h = (uint32_t)(in.by1 - by0);
@@ -1558,8 +1560,8 @@ template <int C, bool COUNT>
 __device__ void exec_sharp(const TC<C>& c) {
   const TileState& t = *c.t;
   const SlotInfo& in = *c.info;
-  const int H = c.H;
-  const int row = c.W * C;
+  const int H = opaque(c.H);
+  const int row = opaque(c.W) * C;
   const int sr0 = in.by0, nrows = in.rows;
   const int y0 = in.y0, y1 = in.y1;
   const uint32_t stage = c.data;
@@ -2191,7 +2193,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
         if (tid < CHB_MAX_CHAIN && sm->color_cnt[tid]) atomicAdd(&g->color_cnt[tid], sm->color_cnt[tid]);
       }
     } else if (cls == CLS_GATHER && (st.n_sp == 2 || (st.n_sp == 1 && st.sp[0].type == SP_GEOM))) {
-      exec_gather_warp<C>(c, warp, smem_addr(sm->wst[warp]));
+      exec_gather_warp<C>(c, warp);
     } else {
       run_tile<C, false>(c);
     }
