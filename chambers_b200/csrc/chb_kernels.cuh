@@ -69,11 +69,25 @@ struct Rect {
 // conversions of the image size for the coordinate maps, row pitches -- is hoisted in front of the
 // executor dispatch and runs for every tile.)
 __device__ __forceinline__ int opaque(int v) {
-#ifndef CHB_NO_OPAQUE
   asm volatile("" : "+r"(v));
-#endif
   return v;
 }
+// Where it pays was measured per executor (profiles/r01_v13_ab_experiments.txt, 5): the scalar, list
+// and gather+sharpness executors yes; in the Sharpness strip executor it cost the flat path 5-15 %.
+#ifndef CHB_OPQ_GEN
+#define CHB_OPQ_GEN 1
+#endif
+#ifndef CHB_OPQ_LIST
+#define CHB_OPQ_LIST 1
+#endif
+#ifndef CHB_OPQ_GS
+#define CHB_OPQ_GS 1
+#endif
+#ifndef CHB_OPQ_SHARP
+#define CHB_OPQ_SHARP 0
+#endif
+template <int ON>
+__device__ __forceinline__ int opaque_if(int v) { return ON ? opaque(v) : v; }
 
 // Debug timeline (-DCHB_TIMELINE, tools/timeline.py): every pass CTA leaves two 16-word records,
 // [level][cta][producer | consumer][16], in KParams::timeline.  Stamps are %globaltimer (ns),
@@ -576,7 +590,7 @@ __device__ __forceinline__ void store_barrier(const TC<C>& c) {
 template <int C, bool COUNT>
 __device__ void exec_generic(const TC<C>& c) {
   const TileState& t = *c.t;
-  const int H = opaque(c.H), W = opaque(c.W);
+  const int H = opaque_if<CHB_OPQ_GEN>(c.H), W = opaque_if<CHB_OPQ_GEN>(c.W);
   const int rx0 = c.info->x0, ry0 = c.info->y0;
   const int rw = c.info->x1 - rx0;
   const int n = rw * (c.info->y1 - ry0);
@@ -1217,7 +1231,7 @@ template <int C, bool COUNT>
 __device__ void gather_list(const TC<C>& c) {
   const TileState& t = *c.t;
   const SlotInfo& in = *c.info;
-  const int H = opaque(c.H), W = opaque(c.W);
+  const int H = opaque_if<CHB_OPQ_LIST>(c.H), W = opaque_if<CHB_OPQ_LIST>(c.W);
   const int n_sp = t.n_sp;
   const int bx0 = in.bx0, by0 = in.by0;
   const uint32_t box_w = (uint32_t)(in.bx1 - bx0), box_h = (uint32_t)(in.by1 - by0);
@@ -1422,7 +1436,7 @@ template <int C, bool COUNT>
 __device__ void exec_gather_sharp(const TC<C>& c) {
   const TileState& t = *c.t;
   const SlotInfo& in = *c.info;
-  const int H = opaque(c.H), W = opaque(c.W);
+  const int H = opaque_if<CHB_OPQ_GS>(c.H), W = opaque_if<CHB_OPQ_GS>(c.W);
   const int n_sp = t.n_sp;
   const int bx0 = in.bx0, by0 = in.by0;
   const uint32_t box_w = (uint32_t)(in.bx1 - bx0), box_h = (uint32_t)(in.by1 - by0);
@@ -1560,8 +1574,8 @@ template <int C, bool COUNT>
 __device__ void exec_sharp(const TC<C>& c) {
   const TileState& t = *c.t;
   const SlotInfo& in = *c.info;
-  const int H = opaque(c.H);
-  const int row = opaque(c.W) * C;
+  const int H = opaque_if<CHB_OPQ_SHARP>(c.H);
+  const int row = opaque_if<CHB_OPQ_SHARP>(c.W) * C;
   const int sr0 = in.by0, nrows = in.rows;
   const int y0 = in.y0, y1 = in.y1;
   const uint32_t stage = c.data;

@@ -86,6 +86,11 @@ def main():
         ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), bufs, args.iters, warm=1)
         report("RandAugment(2,10)", B, 224, 224, ms)
         return
+    if args.only == "identity":
+        layer = A.RandomChoice([A.RandomChance(A.Invert(), 0.0)], 1)
+        ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), bufs, args.iters, warm=1)
+        report("identity(copy)", B, 224, 224, ms)
+        return
     if args.only:
         layer = A.RandomChoice([getattr(A, args.only)(**magnitude_kwargs(args.only, 10))], 1)
         ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), bufs, args.iters, warm=1)
