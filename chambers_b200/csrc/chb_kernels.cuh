@@ -1878,14 +1878,22 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     unsigned G = 1;
     const unsigned per_cta = (n_entries * n_tiles_u) / gridDim.x;  // tiles per CTA
     if (per_cta >= 48u) G = 4; else if (per_cta >= 12u) G = 2;
-    const unsigned cpi = (n_tiles_u + G - 1u) / G;       // chunks per image of a light bin
-    const unsigned cpi_flat = (n_flat_u + G - 1u) / G;   // ... of a flat bin
+    // tiles per image and tiles per chunk of segment k.  At large batches a pass that is not the image's
+    // last is claimed whole: the CTA then needs no election to know that it completed the pass and
+    // finalises from its own shared-memory histogram (see the consumer loop).
+    const bool whole_nf = per_cta >= 96u;
+    auto seg_tiles = [&](int k) -> unsigned { return seg_kind(k) == 2 ? n_flat_u : n_tiles_u; };
+    auto seg_g = [&](int k) -> unsigned {
+      if (seg_kind(k) == 0) return 1u;
+      if (whole_nf && (k == 2 || k == 3)) return seg_tiles(k);
+      return G;
+    };
     constexpr int NSEG = 6;
     unsigned seg_entry0[NSEG], seg_begin[NSEG + 1];
     seg_begin[0] = 0;
 #pragma unroll
     for (int k = 0; k < NSEG; ++k) {
-      const unsigned cp = (seg_kind(k) == 0) ? n_tiles_u : (seg_kind(k) == 1) ? cpi : cpi_flat;
+      const unsigned cp = (seg_tiles(k) + seg_g(k) - 1u) / seg_g(k);
       seg_entry0[k] = seg_first(k) ? bin_end[seg_first(k) - 1] : 0u;
       seg_begin[k + 1] = seg_begin[k] + (bin_end[seg_last(k)] - seg_entry0[k]) * cp;
     }
@@ -1898,19 +1906,17 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     auto global_chunk = [&](unsigned chunk) -> Chunk {
       Chunk c = {-1, 0, 0, 1u, 0};
       if (chunk >= n_chunks) return c;
-      unsigned sbeg = 0, sent = seg_entry0[0];
-      int kind = 0;  // 0 heavy, 1 light, 2 flat
+      unsigned sbeg = 0, sent = seg_entry0[0], g = seg_g(0), tiles = seg_tiles(0);
 #pragma unroll
       for (int k = 1; k < NSEG; ++k)
-        if (chunk >= seg_begin[k]) { sbeg = seg_begin[k]; sent = seg_entry0[k]; kind = seg_kind(k); }
-      const unsigned cp = (kind == 0) ? n_tiles_u : (kind == 1) ? cpi : cpi_flat;
-      const unsigned tiles = (kind == 2) ? n_flat_u : n_tiles_u;
+        if (chunk >= seg_begin[k]) { sbeg = seg_begin[k]; sent = seg_entry0[k]; g = seg_g(k); tiles = seg_tiles(k); }
+      const unsigned cp = (tiles + g - 1u) / g;
       const unsigned loc = chunk - sbeg;
       const unsigned e_in = loc / cp;
       const unsigned ci = loc - e_in * cp;
       const unsigned entry = sent + e_in;
-      c.t0 = (int)(kind == 0 ? ci : ci * G);
-      c.t1 = (int)min(tiles, (unsigned)c.t0 + (kind == 0 ? 1u : G));
+      c.t0 = (int)(ci * g);
+      c.t1 = (int)min(tiles, ci * g + g);
       c.expected = cp;
       int bin = 0;
       unsigned first = 0;
@@ -2198,7 +2204,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
         cons_sync();
       }
       run_tile<C, true>(c);
-      if (is_last) {
+      if (is_last && expected != 1u) {
         cons_sync();
         for (int i = tid; i < C * 256; i += NCONS) {
           const uint32_t v = (&sm->hist[0][0])[i];
@@ -2233,18 +2239,29 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       bulk_wait_read0();
     }
     cons_sync();
-    if (tid == 0) {
-      __threadfence();  // cumulative: publishes the histogram atomics of the whole CTA (ordered by the barrier)
-      sm->ctl[1] = (atomicAdd(&g->tiles_done, 1u) == expected - 1u) ? 1 : 0;
-      __threadfence();
+    const bool sole = expected == 1u;  // this CTA ran the whole pass: no election, the counts are in shared memory
+    if (!sole) {
+      if (tid == 0) {
+        __threadfence();  // cumulative: publishes the histogram atomics of the whole CTA (ordered by the barrier)
+        sm->ctl[1] = (atomicAdd(&g->tiles_done, 1u) == expected - 1u) ? 1 : 0;
+        __threadfence();
+      }
+      cons_sync();
+      if (!sm->ctl[1]) { TL_ACC(13); continue; }
     }
-    cons_sync();
-    if (!sm->ctl[1]) { TL_ACC(13); continue; }
     ImgState* fs = reinterpret_cast<ImgState*>(sm->r);
     uint32_t* hmap = reinterpret_cast<uint32_t*>(sm->r + sizeof(ImgState));
     uint8_t* etab = sm->r + sizeof(ImgState) + MAXC * 256 * 4;
-    for (int i = tid; i < (int)(sizeof(ImgState) / 16); i += NCONS)
-      reinterpret_cast<uint4*>(fs)[i] = __ldcg(reinterpret_cast<const uint4*>(g) + i);
+    if (sole && pass_kind == PASS_COUNT) {
+      for (int i = tid; i < STATE_VECS; i += NCONS)
+        reinterpret_cast<uint4*>(fs)[i] = __ldcg(reinterpret_cast<const uint4*>(g) + i);
+      for (int i = tid; i < MAXC * 256; i += NCONS) (&fs->hist[0][0])[i] = (i < C * 256) ? (&sm->hist[0][0])[i] : 0u;
+      cons_sync();
+      if (tid < CHB_MAX_CHAIN) fs->color_cnt[tid] = sm->color_cnt[tid];
+    } else {
+      for (int i = tid; i < (int)(sizeof(ImgState) / 16); i += NCONS)
+        reinterpret_cast<uint4*>(fs)[i] = __ldcg(reinterpret_cast<const uint4*>(g) + i);
+    }
     cons_sync();
     if (pass_kind == PASS_COUNT) {
       if (tid == 0) fs->hist_valid = 1;
