@@ -1881,7 +1881,10 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     // tiles per image and tiles per chunk of segment k.  At large batches a pass that is not the image's
     // last is claimed whole: the CTA then needs no election to know that it completed the pass and
     // finalises from its own shared-memory histogram (see the consumer loop).
-    const bool whole_nf = per_cta >= 96u;
+#ifndef CHB_WHOLE_NF_MIN
+#define CHB_WHOLE_NF_MIN 96u
+#endif
+    const bool whole_nf = per_cta >= CHB_WHOLE_NF_MIN;
     auto seg_tiles = [&](int k) -> unsigned { return seg_kind(k) == 2 ? n_flat_u : n_tiles_u; };
     auto seg_g = [&](int k) -> unsigned {
       if (seg_kind(k) == 0) return 1u;
