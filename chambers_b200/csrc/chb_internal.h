@@ -29,7 +29,7 @@ static_assert(sizeof(DevOp) == 112, "DevOp layout");
 enum { BLEND_IMAGE2 = 0, BLEND_IMAGE1 = 1, BLEND_INTERP = 2, BLEND_EXTRAP = 3 };
 
 constexpr int MAXC = 4;
-// Work items of one level are ordered by the code they run (most expensive first): a pass CTA then
+// Work items are ordered by the code they run (bin_of, chb_kernels.cuh): a pass CTA then
 // executes long runs of the same tile executor instead of thrashing the instruction cache, and the
 // long tiles are scheduled first.
 constexpr int NBINS = 18;  // two groups (passes that are not / are the image's last) of 9 executor bins
@@ -107,7 +107,7 @@ struct KParams {
   int flat_units, flat_upt;           // flat runs: units per image (48 bytes for C = 3, else 16) and per tile
   int n_flat_tiles;                   // flat runs per image (tiles of <= 256 units; == n_tiles unless the batch is 16-byte aligned)
   int flags;                          // 1: in is 16-byte aligned, 2: out is, 4: images are whole 16-byte units, 8: rows are
-  unsigned long long* timeline;       // debug builds (-DCHB_TIMELINE): [levels][1024 CTAs][2][16] words, else NULL
+  unsigned long long* timeline;       // debug builds (-DCHB_TIMELINE): [1024 CTAs][2][16] words, else NULL
 };
 
 // Opaque copy of a CUtensorMap (cuda.h), passed to the pass kernel as a __grid_constant__ parameter.

@@ -2,33 +2,39 @@
 //
 // Work is cut far below one image so that a 256-image batch already fills 148 SMs evenly:
 //   plan_kernel   one CTA per image: decodes the image's op schedule from Philox4x32-10 (or a
-//                 replayed schedule) and folds the chain into a per-image pass state (ImgState).
-//   pass_kernel   persistent CTAs pull (image, tile) items of one *level* from an atomic counter.
-//                 A tile is ~10 KB of the image; level 0 is every image's first pass, level n the
-//                 n-th extra pass of the few images that need one.  Each CTA is a two-slot
-//                 producer / consumer pipeline: one warp claims items and drives the TMA loads
-//                 (cp.async.bulk + mbarrier), eight warps compute from shared memory and hand the
-//                 finished tile back to the TMA (bulk stores).
+//                 replayed schedule), folds the chain into a per-image pass state (ImgState) and
+//                 appends the image to the bin of the executor its first pass runs.
+//   pass_kernel   ONE persistent launch per call: 2 CTAs per SM claim chunks of (image, tile) work from
+//                 an atomic counter, bins in start order.  A tile is ~12 KB of the image.  Each CTA
+//                 is a producer / consumer pipeline over a ring of four 16 KB units: one warp claims
+//                 work and drives the TMA loads (cp.async.bulk[.tensor] + mbarrier), eight warps
+//                 compute from shared memory.  A pass that is not the image's last (COUNT,
+//                 WRITE_SCRATCH) ends with one CTA resuming the chain walk and publishing the image's
+//                 next pass in a global list that every producer holds a ticket into, so later passes
+//                 run inside the same launch, spread over all CTAs.
 //
 // The chain is evaluated lazily (chb_internal.h: ImgState).  Point-wise ops compose into 256-entry
 // LUTs, nearest-neighbour warps and CutOut go on a spatial list, Color / Sharpness / a bilinear warp
 // occupy the single "kernel" slot K.  Pixels are only touched by
 //   WRITE_OUT      the one pass every image has: src -> spatial list -> l1 -> K -> l2 -> out;
 //   COUNT          Equalize / AutoContrast need the histogram of the virtual image: tiles count into
-//                  shared memory, flush with global atomics, the last tile of the image turns the
-//                  histogram into a LUT (warp-scan CDF) and resumes the chain walk;
+//                  shared memory, the CTA that completes the pass turns the histogram into a LUT
+//                  (warp-scan CDF) and resumes the chain walk;
 //   WRITE_SCRATCH  an op needs a materialised neighbourhood of something that is itself a
 //                  neighbourhood op (e.g. Rotate after Sharpness): the virtual image is written to
-//                  an L2-resident scratch image and becomes the new src.
+//                  a scratch image (L2-resident when its next pass follows soon) and becomes the new src.
 // so a RandAugment image costs one HBM read and one HBM write unless its chain holds a histogram
-// op (one extra read, served from L2 for batches that fit) or a rare neighbourhood-of-neighbourhood
-// pair.
+// op (one extra read, served from L2 when the next pass follows soon) or a rare
+// neighbourhood-of-neighbourhood pair.
 //
 // Tile executors (all bit-exact twins of each other; the scalar one is the fallback for odd shapes):
-//   exec_flat     no spatial op: 48-byte (16-pixel) units, LDS.128 -> LUT/Color in registers -> STS.128
-//   exec_gather   spatial list: the source bounding box of a 64 x 56 tile is staged in shared memory
-//                 (one TMA copy per row), pixels are gathered from it into the output tile
+//   exec_flat     no spatial op: 48-byte (16-pixel) units, LDS.128 -> LUT/Color in registers -> STS.128 -> one TMA store
+//   gather_warp   one or two spatial entries, WRITE pass: the source bounding box of a 64 x 64 tile is
+//                 staged in shared memory (one tensor-map TMA box); each warp gathers whole rows and
+//                 stores them itself (no CTA barrier)
+//   exec_gather   the same staging for COUNT passes and longer spatial lists, CTA-wide
 //   exec_sharp    Sharpness: row strip + halo staged in shared memory, sliding 3x3 window per word column
+//   exec_gather_sharp   Sharpness of a gathered image
 //   exec_generic  anything, one pixel per thread straight from global memory
 #pragma once
 #include <string.h>
@@ -90,7 +96,7 @@ template <int ON>
 __device__ __forceinline__ int opaque_if(int v) { return ON ? opaque(v) : v; }
 
 // Debug timeline (-DCHB_TIMELINE, tools/timeline.py): every pass CTA leaves two 16-word records,
-// [level][cta][producer | consumer][16], in KParams::timeline.  Stamps are %globaltimer (ns),
+// [cta][producer | consumer][16], in KParams::timeline.  Stamps are %globaltimer (ns),
 // accumulators are clock64 cycles.  Compiled out of the production library.
 #ifdef CHB_TIMELINE
 __device__ __forceinline__ unsigned long long tl_now() {
@@ -489,7 +495,7 @@ __global__ void __launch_bounds__(PLAN_NT) plan_kernel(const KParams p, int C) {
   __shared__ uint32_t rnd[32][4], rndc[32][4];
   const int tid = threadIdx.x;
   const int img = blockIdx.x;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // level 0 may set itself up while we plan
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the pass kernel may set itself up while we plan
   // (the counters are zeroed by a memset node in front of this kernel)
   for (int i = tid; i < STATE_VECS; i += PLAN_NT) reinterpret_cast<uint4*>(&s)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
@@ -533,7 +539,8 @@ struct alignas(16) SlotInfo {  // written by the producer, read by the consumers
   uint32_t expected;                 // COUNT / WRITE_SCRATCH: chunks of this image that report to tiles_done
   int32_t rpi;                       // warp-autonomous gather: tile rows per warp step (32 / quads per row)
   int32_t n_steps;                   //   steps of the tile: ceil(th / rpi)
-  uint32_t inv_n16, inv_qpr;         //   inv_qpr = ceil(1024 / quads per tile row): lane / d == (lane * inv) >> 10 (GATHER_SHARP: ceil(2^32 / halo width))
+  uint32_t inv_qpr;                  //   ceil(1024 / quads per tile row): lane / d == (lane * inv) >> 10 (GATHER_SHARP: ceil(2^32 / halo width))
+  uint32_t _pad0;
   int32_t _pad;
   const uint8_t* src;                // source image of this pass (the batch or a scratch image)
   uint8_t* dst;                      // destination image (unused by COUNT passes)
@@ -1678,7 +1685,7 @@ __device__ __forceinline__ void plan_tile(const KParams& p, const TileState& t, 
   in.cls = CLS_GENERIC; in.img = img; in.tile = tile; in.pass_kind = pass_kind;
   in.bx0 = 0; in.bx1 = -1; in.by0 = 0; in.by1 = -1; in.bxb0 = 0; in.rowb = 0; in.pitch = 16; in.rows = 0;
   in.span = 1; in.sharp_rows = 1; in.fillc[0] = 0; in.fillc[1] = 0; in.paint = 0;
-  in.first = 1; in.last = 1; in.st_idx = 0; in.expected = 1u; in.rpi = 1; in.n_steps = 0; in.inv_n16 = 1024u; in.inv_qpr = 1024u; in._pad = 0;
+  in.first = 1; in.last = 1; in.st_idx = 0; in.expected = 1u; in.rpi = 1; in.n_steps = 0; in.inv_qpr = 1024u; in._pad0 = 0u; in._pad = 0;
   in.src = nullptr; in.dst = nullptr;
   d.tx_bytes = 0;
   d.src_sel = t.src_sel;
@@ -2071,10 +2078,8 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
                 const int tw = d.in.x1 - d.in.x0, th = d.in.y1 - d.in.y0;
                 const int qpr = max(1, tw >> 2);
                 const int rpi = max(1, 32 / qpr);
-                const int n16 = max(1, (tw * C) >> 4);
                 d.in.rpi = rpi;
                 d.in.n_steps = (th + rpi - 1) / rpi;
-                d.in.inv_n16 = (uint32_t)((1024 + n16 - 1) / n16);
                 d.in.inv_qpr = (uint32_t)((1024 + qpr - 1) / qpr);
               }
               sm->info[u] = d.in;

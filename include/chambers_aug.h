@@ -172,7 +172,7 @@ int chb_set_debug(chb_ctx* ctx, int force_generic);
 /* Profiling hook of debug builds (-DCHB_TIMELINE; the production library returns
  * CHB_ERR_UNSUPPORTED).  host_out == NULL: start recording per-CTA timestamps of the pass kernels.
  * Otherwise: synchronise the device, copy up to max_words 64-bit words of the records to host_out
- * ([level][1024 CTAs][producer | consumer][16]) and clear them; returns the words copied. */
+ * ([1024 CTAs][producer | consumer][16]) and clear them; returns the words copied. */
 int chb_debug_timeline(chb_ctx* ctx, uint64_t* host_out, int max_words);
 
 /* How an H x W image is cut into work items: tiles_x * tiles_y tiles of at most tw x th pixels
