@@ -2228,30 +2228,44 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     TL_ACC(7 + cls);  // cls 1..5 -> slots 8..12
     TL_ADD(5, 1);
     TL_STAMP(3);
-    // this warp is done with the unit(s): state, info and staged bytes
+    // This warp is done with the unit(s): state, info and staged bytes.  What the loop needs from
+    // the plan from here on is read again from shared memory instead of being kept alive across the
+    // executor: at the 96-register cap those values were spilled, and their reloads from local
+    // memory were 13 % of the gather tiles' stall samples and cost the flat path 10-20 %
+    // (profiles/r01_v13_ab_experiments.txt, 9).  pass_kind alone stays a live value: with it re-read
+    // too, test_fast_executors_match_scalar_executor hung although an instrumented build showed the
+    // re-read value always equal to the live one -- unexplained, so left alone.
     __syncwarp();
+    const uint32_t ia = smem_addr(&sm->info[cu & (NU - 1)]);
+    const int span_r = (int)lds_u32(ia + (uint32_t)offsetof(SlotInfo, span));
+    const int last_r = (int)lds_u32(ia + (uint32_t)offsetof(SlotInfo, last));
+    const int pass_r = pass_kind;
+    const int img_r = (int)lds_u32(ia + (uint32_t)offsetof(SlotInfo, img));
+    const unsigned expected_r = lds_u32(ia + (uint32_t)offsetof(SlotInfo, expected));
     if (lane == 0) {
-      mbar_arrive(empty0 + 8 * u);
-      if (span == 2) mbar_arrive(empty0 + 8 * (u + 1));
+      const uint32_t ur = cu & (NU - 1);
+      mbar_arrive(empty0 + 8 * ur);
+      if (span_r == 2) mbar_arrive(empty0 + 8 * (ur + 1));
     }
-    cu += span;
-    if (pass_kind == PASS_WRITE_OUT || !is_last) continue;
+    cu += span_r;
+    if (pass_r == PASS_WRITE_OUT || !last_r) continue;
 
     // ---- COUNT / WRITE_SCRATCH: the CTA that completes the image's last chunk resumes the chain walk
     TL_T0();
     // the finaliser scratch below aliases the output staging tiles; a scratch image must also
     // have landed in global memory before the pass is reported complete
-    if (pass_kind == PASS_WRITE_SCRATCH) {
+    if (pass_r == PASS_WRITE_SCRATCH) {
       if (lane == 0) { bulk_wait_all0(); fence_proxy_async_all(); }
     } else if (tid < 32) {
       bulk_wait_read0();
     }
     cons_sync();
-    const bool sole = expected == 1u;  // this CTA ran the whole pass: no election, the counts are in shared memory
+    ImgState* gr = p.states + img_r;
+    const bool sole = expected_r == 1u;  // this CTA ran the whole pass: no election, the counts are in shared memory
     if (!sole) {
       if (tid == 0) {
         __threadfence();  // cumulative: publishes the histogram atomics of the whole CTA (ordered by the barrier)
-        sm->ctl[1] = (atomicAdd(&g->tiles_done, 1u) == expected - 1u) ? 1 : 0;
+        sm->ctl[1] = (atomicAdd(&gr->tiles_done, 1u) == expected_r - 1u) ? 1 : 0;
         __threadfence();
       }
       cons_sync();
@@ -2260,27 +2274,27 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     ImgState* fs = reinterpret_cast<ImgState*>(sm->r);
     uint32_t* hmap = reinterpret_cast<uint32_t*>(sm->r + sizeof(ImgState));
     uint8_t* etab = sm->r + sizeof(ImgState) + MAXC * 256 * 4;
-    if (sole && pass_kind == PASS_COUNT) {
+    if (sole && pass_r == PASS_COUNT) {
       for (int i = tid; i < STATE_VECS; i += NCONS)
-        reinterpret_cast<uint4*>(fs)[i] = __ldcg(reinterpret_cast<const uint4*>(g) + i);
+        reinterpret_cast<uint4*>(fs)[i] = __ldcg(reinterpret_cast<const uint4*>(gr) + i);
       for (int i = tid; i < MAXC * 256; i += NCONS) (&fs->hist[0][0])[i] = (i < C * 256) ? (&sm->hist[0][0])[i] : 0u;
       cons_sync();
       if (tid < CHB_MAX_CHAIN) fs->color_cnt[tid] = sm->color_cnt[tid];
     } else {
       for (int i = tid; i < (int)(sizeof(ImgState) / 16); i += NCONS)
-        reinterpret_cast<uint4*>(fs)[i] = __ldcg(reinterpret_cast<const uint4*>(g) + i);
+        reinterpret_cast<uint4*>(fs)[i] = __ldcg(reinterpret_cast<const uint4*>(gr) + i);
     }
     cons_sync();
-    if (pass_kind == PASS_COUNT) {
+    if (pass_r == PASS_COUNT) {
       if (tid == 0) fs->hist_valid = 1;
     } else {
       if (tid == 0) fs->t.src_sel = fs->t.dst_sel;
       reset_view(fs, tid, NCONS);
     }
     cons_sync();
-    advance(fs, g, p, C, H, W, hmap, etab, tid, NCONS, [] { cons_sync(); });
+    advance(fs, gr, p, C, H, W, hmap, etab, tid, NCONS, [] { cons_sync(); });
     for (int i = tid; i < STATE_VECS; i += NCONS)
-      reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(fs)[i];
+      reinterpret_cast<uint4*>(gr)[i] = reinterpret_cast<const uint4*>(fs)[i];
     const int fs_next_pass = fs->t.pass_kind;
     const int fs_next_flat = (p.n_flat_tiles != p.n_tiles && is_flat_bin(bin_of(fs->t))) ? CONT_FLAT : 0;
     // Publish the image's next pass: whichever CTAs hold the tickets of its chunks fetch the state
@@ -2292,7 +2306,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
       const bool more = fs_next_pass != PASS_WRITE_OUT;  // the image will publish again
       const unsigned pos = atomicAdd(p.counters + NBINS + 2, 1u);
       __threadfence();
-      *reinterpret_cast<volatile int*>(p.cont + pos) = (img + 1) | fs_next_flat;
+      *reinterpret_cast<volatile int*>(p.cont + pos) = (img_r + 1) | fs_next_flat;
       if (!more) {
         __threadfence();
         atomicSub(p.counters + NBINS + 3, 1u);
