@@ -2232,16 +2232,17 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     // the plan from here on is read again from shared memory instead of being kept alive across the
     // executor: at the 96-register cap those values were spilled, and their reloads from local
     // memory were 13 % of the gather tiles' stall samples and cost the flat path 10-20 %
-    // (profiles/r01_v13_ab_experiments.txt, 9).  pass_kind alone stays a live value: with it re-read
-    // too, test_fast_executors_match_scalar_executor hung although an instrumented build showed the
-    // re-read value always equal to the live one -- unexplained, so left alone.
+    // (profiles/r01_v13_ab_experiments.txt, 9).  The second __syncwarp() matters: lane 0's arrival
+    // releases the unit, and without it the other lanes' reads were not ordered before that release --
+    // a lane could read the *next* tile's pass_kind, take the finaliser branch alone and hang the CTA.
     __syncwarp();
     const uint32_t ia = smem_addr(&sm->info[cu & (NU - 1)]);
     const int span_r = (int)lds_u32(ia + (uint32_t)offsetof(SlotInfo, span));
     const int last_r = (int)lds_u32(ia + (uint32_t)offsetof(SlotInfo, last));
-    const int pass_r = pass_kind;
+    const int pass_r = (int)lds_u32(ia + (uint32_t)offsetof(SlotInfo, pass_kind));
     const int img_r = (int)lds_u32(ia + (uint32_t)offsetof(SlotInfo, img));
     const unsigned expected_r = lds_u32(ia + (uint32_t)offsetof(SlotInfo, expected));
+    __syncwarp();  // every lane has its copy before lane 0 lets go of the unit
     if (lane == 0) {
       const uint32_t ur = cu & (NU - 1);
       mbar_arrive(empty0 + 8 * ur);
