@@ -619,14 +619,15 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     if (ok && ws->scratch) ok = encode_image_map(&tm_scr, ws->scratch, H, W * C, stride, (size_t)B * 2, &br, &bb);
     if (ok) { p.use_tmap = 1; p.box_rows = br; p.box_bytes = bb; }
   }
+  long long grid = (long long)ctx->num_sms * chb::pass_ctas_per_sm(C);
+  if ((long long)B * tp.n_tiles < grid) grid = (long long)B * tp.n_tiles;
+  p.nf_first = ((long long)B * tp.n_tiles < 96 * grid) ? 1 : 0;  // small batch (< 96 tiles per CTA): see bin_of
   p.cont = reinterpret_cast<int*>(ws->counters + 32);
   cudaError_t e = cudaMemsetAsync(ws->counters, 0, (32 + (size_t)B * CHB_MAX_CHAIN + 2048) * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "counter reset");
   e = chb::launch_plan(p, C, stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "plan kernel launch");
   ctx->launches += 1;
-  long long grid = (long long)ctx->num_sms * chb::pass_ctas_per_sm(C);
-  if ((long long)B * tp.n_tiles < grid) grid = (long long)B * tp.n_tiles;
   e = chb::launch_pass(p, tm_in, tm_scr, C, (int)grid, stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "pass kernel launch");
   ctx->launches += 1;

@@ -105,6 +105,7 @@ struct KParams {
   // per-launch constants of the tile planner
   int strip_rows;                     // rows of a strip tile: ceil(H / n_tiles)
   int flat_units, flat_upt;           // flat runs: units per image (48 bytes for C = 3, else 16) and per tile
+  int nf_first;                       // bin layout: 1 = every non-final pass first (small batches), 0 = heavy executors first
   int n_flat_tiles;                   // flat runs per image (tiles of <= 256 units; == n_tiles unless the batch is 16-byte aligned)
   int flags;                          // 1: in is 16-byte aligned, 2: out is, 4: images are whole 16-byte units, 8: rows are
   unsigned long long* timeline;       // debug builds (-DCHB_TIMELINE): [1024 CTAs][2][16] words, else NULL

@@ -227,20 +227,35 @@ __device__ __forceinline__ void reset_view(ImgState* s, int tid, int nt) {  // a
 }
 
 // Executor bin of an image's next pass (see NBINS).  Bins are laid out in the order the work should
-// start: the heavy executors first (their tiles cost microseconds each, so they must not be left for
-// the tail) -- passes that are not the image's last one before final ones, because the image's next
-// pass can only be published once they are done -- then the light 2-D tiles and the flat runs, again
-// non-final before final.  Within each segment the most expensive code comes first.
-//   0..3   heavy, non-final     4..7   heavy, final
-//   8..9   light, non-final    10..12  flat, non-final    13..14  light, final    15..17  flat, final
+// start, in six segments: {heavy, light 2-D tiles, flat runs} x {passes that are not the image's
+// last, final passes}.  Heavy executors (their tiles cost microseconds each) must not be left for the
+// tail; non-final passes come before final ones of the same weight because the image's next pass can
+// only be published once they are done.  Within a segment the most expensive code comes first.
+// Two layouts, chosen per call (KParams::nf_first):
+//   large batches   0..3 heavy nf | 4..7 heavy f | 8..9 light nf | 10..12 flat nf | 13..14 light f | 15..17 flat f
+//   small batches   0..3 heavy nf | 4..5 light nf | 6..8 flat nf | 9..12 heavy f  | 13..14 light f | 15..17 flat f
+// (small batches: every non-final pass first -- the second stage of those images is the critical path
+// of a 100 us kernel: 256 images 0.111 -> 0.104 ms; large batches lose 4 % that way,
+// profiles/r01_v13_ab_experiments.txt 10)
 constexpr int HEAVY_BINS = 4;
-// segment k: first / last bin and kind (0 heavy: one tile per claim, 1 light, 2 flat)
-__host__ __device__ constexpr int seg_first(int k) { return k == 0 ? 0 : k == 1 ? 4 : k == 2 ? 8 : k == 3 ? 10 : k == 4 ? 13 : 15; }
-__host__ __device__ constexpr int seg_last(int k) { return k == 0 ? 3 : k == 1 ? 7 : k == 2 ? 9 : k == 3 ? 12 : k == 4 ? 14 : 17; }
-__host__ __device__ constexpr int seg_kind(int k) { return k < 2 ? 0 : (k == 2 || k == 4) ? 1 : 2; }
+__host__ __device__ constexpr int seg_first(int k, bool nf) {
+  return nf ? (k == 0 ? 0 : k == 1 ? 4 : k == 2 ? 6 : k == 3 ? 9 : k == 4 ? 13 : 15)
+            : (k == 0 ? 0 : k == 1 ? 4 : k == 2 ? 8 : k == 3 ? 10 : k == 4 ? 13 : 15);
+}
+__host__ __device__ constexpr int seg_last(int k, bool nf) {
+  return nf ? (k == 0 ? 3 : k == 1 ? 5 : k == 2 ? 8 : k == 3 ? 12 : k == 4 ? 14 : 17)
+            : (k == 0 ? 3 : k == 1 ? 7 : k == 2 ? 9 : k == 3 ? 12 : k == 4 ? 14 : 17);
+}
+// 0 heavy (one tile per claim), 1 light, 2 flat
+__host__ __device__ constexpr int seg_kind(int k, bool nf) {
+  return nf ? ((k == 0 || k == 3) ? 0 : (k == 1 || k == 4) ? 1 : 2) : (k < 2 ? 0 : (k == 2 || k == 4) ? 1 : 2);
+}
+__host__ __device__ constexpr bool seg_nonfinal_light(int k, bool nf) { return nf ? (k == 1 || k == 2) : (k == 2 || k == 3); }
 constexpr int CONT_FLAT = 1 << 30;
-__device__ __forceinline__ bool is_flat_bin(int bin) { return (bin >= 10 && bin <= 12) || bin >= 15; }
-__device__ __forceinline__ int bin_of(const TileState& t) {
+__device__ __forceinline__ bool is_flat_bin(int bin, bool nf) {
+  return bin >= 15 || (nf ? (bin >= 6 && bin <= 8) : (bin >= 10 && bin <= 12));
+}
+__device__ __forceinline__ int bin_of(const TileState& t, bool nf) {
   bool any_geom = false;
   for (int k = 0; k < t.n_sp; ++k) any_geom = any_geom || (t.sp[k].type == SP_GEOM);
   const bool count = t.pass_kind == PASS_COUNT;
@@ -252,13 +267,18 @@ __device__ __forceinline__ int bin_of(const TileState& t) {
   else if (t.n_sp == 1 && (any_geom || count)) cost = t.kmode == K_COLOR ? 4 : 5;
   else if (count) cost = 6;
   else cost = t.kmode == K_COLOR ? 7 : 8;
+  if (nf) {
+    if (cost < HEAVY_BINS) return (fin ? 9 : 0) + cost;
+    if (cost < 6) return (fin ? 13 : 4) + (cost - 4);
+    return (fin ? 15 : 6) + (cost - 6);
+  }
   if (cost < HEAVY_BINS) return (fin ? 4 : 0) + cost;
   if (cost < 6) return (fin ? 13 : 8) + (cost - 4);
   return (fin ? 15 : 10) + (cost - 6);
 }
 // Queues image `img` for its first pass.
 __device__ __forceinline__ void enqueue_pass(const KParams& p, const TileState& t, int img) {
-  const int bin = bin_of(t);
+  const int bin = bin_of(t, p.nf_first != 0);
   const unsigned pos = atomicAdd(p.counters + bin, 1u);
   p.lists[(size_t)bin * p.B + pos] = img;
 }
@@ -1892,10 +1912,11 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
 #define CHB_WHOLE_NF_MIN 96u
 #endif
     const bool whole_nf = per_cta >= CHB_WHOLE_NF_MIN;
-    auto seg_tiles = [&](int k) -> unsigned { return seg_kind(k) == 2 ? n_flat_u : n_tiles_u; };
+    const bool nf = p.nf_first != 0;
+    auto seg_tiles = [&](int k) -> unsigned { return seg_kind(k, nf) == 2 ? n_flat_u : n_tiles_u; };
     auto seg_g = [&](int k) -> unsigned {
-      if (seg_kind(k) == 0) return 1u;
-      if (whole_nf && (k == 2 || k == 3)) return seg_tiles(k);
+      if (seg_kind(k, nf) == 0) return 1u;
+      if (whole_nf && seg_nonfinal_light(k, nf)) return seg_tiles(k);
       return G;
     };
     constexpr int NSEG = 6;
@@ -1904,8 +1925,8 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
 #pragma unroll
     for (int k = 0; k < NSEG; ++k) {
       const unsigned cp = (seg_tiles(k) + seg_g(k) - 1u) / seg_g(k);
-      seg_entry0[k] = seg_first(k) ? bin_end[seg_first(k) - 1] : 0u;
-      seg_begin[k + 1] = seg_begin[k] + (bin_end[seg_last(k)] - seg_entry0[k]) * cp;
+      seg_entry0[k] = seg_first(k, nf) ? bin_end[seg_first(k, nf) - 1] : 0u;
+      seg_begin[k + 1] = seg_begin[k] + (bin_end[seg_last(k, nf)] - seg_entry0[k]) * cp;
     }
     const unsigned n_chunks = seg_begin[NSEG];
     TL_STAMP(13);
@@ -2297,7 +2318,7 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     for (int i = tid; i < STATE_VECS; i += NCONS)
       reinterpret_cast<uint4*>(gr)[i] = reinterpret_cast<const uint4*>(fs)[i];
     const int fs_next_pass = fs->t.pass_kind;
-    const int fs_next_flat = (p.n_flat_tiles != p.n_tiles && is_flat_bin(bin_of(fs->t))) ? CONT_FLAT : 0;
+    const int fs_next_flat = (p.n_flat_tiles != p.n_tiles && is_flat_bin(bin_of(fs->t, p.nf_first != 0), p.nf_first != 0)) ? CONT_FLAT : 0;
     // Publish the image's next pass: whichever CTAs hold the tickets of its chunks fetch the state
     // just written (and, after a WRITE_SCRATCH pass, the scratch image) with TMA loads.
     __threadfence();

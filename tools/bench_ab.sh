@@ -1,4 +1,4 @@
-for v in base wn12 wn32 base wn12; do
+for v in ${VARIANTS:-base}; do
   lib=$PWD/chambers_b200/libchambers_aug.so; [ "$v" != base ] && lib=$PWD/chambers_b200/libchambers_aug_$v.so
   CHB_LIB=$lib python bench.py --steps 300 --warmup 20 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
 import sys, json
