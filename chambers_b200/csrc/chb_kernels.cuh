@@ -1904,7 +1904,13 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     const unsigned n_tiles_u = (unsigned)p.n_tiles, n_flat_u = (unsigned)p.n_flat_tiles;
     unsigned G = 1;
     const unsigned per_cta = (n_entries * n_tiles_u) / gridDim.x;  // tiles per CTA
-    if (per_cta >= 48u) G = 4; else if (per_cta >= 12u) G = 2;
+#ifndef CHB_G2_MIN
+#define CHB_G2_MIN 16u
+#endif
+#ifndef CHB_G4_MIN
+#define CHB_G4_MIN 48u
+#endif
+    if (per_cta >= CHB_G4_MIN) G = 4; else if (per_cta >= CHB_G2_MIN) G = 2;
     // tiles per image and tiles per chunk of segment k.  At large batches a pass that is not the image's
     // last is claimed whole: the CTA then needs no election to know that it completed the pass and
     // finalises from its own shared-memory histogram (see the consumer loop).
