@@ -31,6 +31,7 @@ struct Workspace {
   int* lists = nullptr;
   unsigned int* counters = nullptr;
   size_t cap_images = 0;
+  bool clean = false;                // counters + continuation list are zero (the pass kernel leaves them so)
   uint8_t* scratch = nullptr;
   size_t scratch_bytes = 0;
   uint8_t* inplace = nullptr;
@@ -39,6 +40,7 @@ struct Workspace {
 
 static const int kPipeMax = 8;      // e2e pipeline: at most this many streams / staging buffers
 static int g_pipe = 4;              // streams in use (CHB_E2E_STREAMS)
+static int g_self_clean = 1;         // CHB_SELF_CLEAN=0: zero the counters with a memset in front of every call instead
 static int g_chunk_kb = 2560;       // target chunk size of the host path in KiB (CHB_E2E_CHUNK_KB)
 
 struct chb_ctx {
@@ -370,6 +372,7 @@ extern "C" int chb_init(int device, chb_ctx** out) {
         qres == cudaDriverEntryPointSuccess)
       g_encode_tiled = (EncodeTiledFn)fn;
   }
+  if (const char* e = getenv("CHB_SELF_CLEAN")) g_self_clean = (e[0] != '0') ? 1 : 0;
   if (const char* e = getenv("CHB_E2E_STREAMS")) { int v = atoi(e); if (v >= 1 && v <= kPipeMax) g_pipe = v; }
   if (const char* e = getenv("CHB_E2E_CHUNK_KB")) { int v = atoi(e); if (v >= 64) g_chunk_kb = v; }
   const char* fg = getenv("CHB_FORCE_GENERIC");
@@ -532,6 +535,7 @@ static int get_workspace(chb_ctx* ctx, cudaStream_t stream, int B, size_t scratc
     // words, then one entry per possible pass after an image's first plus slack for void tickets
     CHB_CUDA(ctx, cudaMalloc(&ws->counters, (32 + nb * CHB_MAX_CHAIN + 2048) * sizeof(unsigned int)));
     ws->cap_images = nb;
+    ws->clean = false;
   }
   int r = grow(ctx, (void**)&ws->scratch, &ws->scratch_bytes, scratch_bytes);
   if (r != CHB_OK) return r;
@@ -623,14 +627,21 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   if ((long long)B * tp.n_tiles < grid) grid = (long long)B * tp.n_tiles;
   p.nf_first = ((long long)B * tp.n_tiles < 96 * grid) ? 1 : 0;  // small batch (< 96 tiles per CTA): see bin_of
   p.cont = reinterpret_cast<int*>(ws->counters + 32);
-  cudaError_t e = cudaMemsetAsync(ws->counters, 0, (32 + (size_t)B * CHB_MAX_CHAIN + 2048) * sizeof(unsigned int), stream);
-  if (e != cudaSuccess) return cuda_fail(ctx, e, "counter reset");
+  // The pass kernel's last CTA leaves counters and continuation list zeroed, so only a fresh (or
+  // possibly dirty) workspace needs a memset.
+  cudaError_t e = cudaSuccess;
+  if (!ws->clean || !g_self_clean) {
+    e = cudaMemsetAsync(ws->counters, 0, (32 + ws->cap_images * CHB_MAX_CHAIN + 2048) * sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "counter reset");
+  }
+  ws->clean = false;
   e = chb::launch_plan(p, C, stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "plan kernel launch");
   ctx->launches += 1;
   e = chb::launch_pass(p, tm_in, tm_scr, C, (int)grid, stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "pass kernel launch");
   ctx->launches += 1;
+  ws->clean = true;
   if (overlap) CHB_CUDA(ctx, cudaMemcpyAsync(d_out, ws->inplace, (size_t)B * img_bytes, cudaMemcpyDeviceToDevice, stream));
   return CHB_OK;
 }

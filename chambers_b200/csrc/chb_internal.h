@@ -96,8 +96,8 @@ struct KParams {
   unsigned long long scratch_stride;
   ImgState* states;                   // [B]
   int* lists;                         // [NBINS][B]: the images, binned by the executor of their first pass
-  unsigned int* counters;             // [NBINS] bin lengths, then: work counter, ticket counter, continuation
-                                      // entries allocated, images that may still publish a continuation
+  unsigned int* counters;             // 32 words: [NBINS] bin lengths, then: work counter, ticket counter, continuation
+                                      // entries allocated, images that may still publish a continuation, CTAs that have left
   int* cont;                          // continuation list: image + 1 per published pass, 0 = not yet (follows counters)
   int tiles_x, tiles_y, tw, th, n_tiles;
   int force_generic;                  // debugging: route every tile through the scalar executor

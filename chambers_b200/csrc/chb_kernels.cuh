@@ -2343,7 +2343,24 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     TL_ACC(13);
     TL_ADD(14, 1);
   }
-  if (tid < 32) bulk_wait_all0();  // every store of this CTA has landed before the grid retires
+  if (tid < 32) {
+    bulk_wait_all0();  // every store of this CTA has landed before the grid retires
+    // The last CTA out leaves the counters and the continuation list zeroed for the next call on this
+    // workspace (the host then needs no memset node in front of every call).  Every other CTA has
+    // stopped reading them: its producer sent END after its last look, and this is past END.
+    unsigned last = 0;
+    if (lane == 0) {
+      __threadfence();
+      last = (atomicAdd(p.counters + NBINS + 4, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    }
+    last = __shfl_sync(0xFFFFFFFFu, last, 0);
+    if (last) {
+      __threadfence();
+      const unsigned n_cont = __ldcg(p.counters + NBINS + 2);
+      for (unsigned i = (unsigned)lane; i < n_cont; i += 32u) p.cont[i] = 0;
+      p.counters[lane] = 0u;  // 32 counter words
+    }
+  }
   TL_STAMP(4);
   TL_FLUSH(1, tid == 0);
 }
