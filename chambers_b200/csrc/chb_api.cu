@@ -40,6 +40,7 @@ struct Workspace {
 
 static const int kPipeMax = 8;      // e2e pipeline: at most this many streams / staging buffers
 static int g_pipe = 4;              // streams in use (CHB_E2E_STREAMS)
+static long long g_nf_first_images = 6;  // a batch is also "small" below this many images per CTA (CHB_NF_FIRST_IMAGES)
 static int g_self_clean = 1;         // CHB_SELF_CLEAN=0: zero the counters with a memset in front of every call instead
 static int g_chunk_kb = 2560;       // target chunk size of the host path in KiB (CHB_E2E_CHUNK_KB)
 
@@ -372,6 +373,7 @@ extern "C" int chb_init(int device, chb_ctx** out) {
         qres == cudaDriverEntryPointSuccess)
       g_encode_tiled = (EncodeTiledFn)fn;
   }
+  if (const char* e = getenv("CHB_NF_FIRST_IMAGES")) g_nf_first_images = atoll(e);
   if (const char* e = getenv("CHB_SELF_CLEAN")) g_self_clean = (e[0] != '0') ? 1 : 0;
   if (const char* e = getenv("CHB_E2E_STREAMS")) { int v = atoi(e); if (v >= 1 && v <= kPipeMax) g_pipe = v; }
   if (const char* e = getenv("CHB_E2E_CHUNK_KB")) { int v = atoi(e); if (v >= 64) g_chunk_kb = v; }
@@ -626,6 +628,7 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   long long grid = (long long)ctx->num_sms * chb::pass_ctas_per_sm(C);
   if ((long long)B * tp.n_tiles < grid) grid = (long long)B * tp.n_tiles;
   p.nf_first = ((long long)B * tp.n_tiles < 96 * grid) ? 1 : 0;  // small batch (< 96 tiles per CTA): see bin_of
+  if (g_nf_first_images > 0 && (long long)B < g_nf_first_images * grid) p.nf_first = 1;
   p.cont = reinterpret_cast<int*>(ws->counters + 32);
   // The pass kernel's last CTA leaves counters and continuation list zeroed, so only a fresh (or
   // possibly dirty) workspace needs a memset.

@@ -1917,7 +1917,10 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
 #ifndef CHB_WHOLE_NF_MIN
 #define CHB_WHOLE_NF_MIN 96u
 #endif
-    const bool whole_nf = per_cta >= CHB_WHOLE_NF_MIN;
+#ifndef CHB_WHOLE_IMG_MIN
+#define CHB_WHOLE_IMG_MIN 6u
+#endif
+    const bool whole_nf = per_cta >= CHB_WHOLE_NF_MIN && n_entries >= CHB_WHOLE_IMG_MIN * gridDim.x;
     const bool nf = p.nf_first != 0;
     auto seg_tiles = [&](int k) -> unsigned { return seg_kind(k, nf) == 2 ? n_flat_u : n_tiles_u; };
     auto seg_g = [&](int k) -> unsigned {

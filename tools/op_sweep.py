@@ -86,6 +86,12 @@ def main():
         ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), bufs, args.iters, warm=1)
         report("RandAugment(2,10)", B, 224, 224, ms)
         return
+    if args.only == "config3":  # BASELINE.json configs[3]
+        b = make_bufs(512, 512, 512, 3, pool_bytes=2 << 30)
+        ra = A.RandAugment(3, 15, elementwise=True)._transform
+        ms = time_layer(lambda i, x, y: ra(x, seed=0, call_counter=i, out=y), b, args.iters, warm=2)
+        report("config: RandAugment(3,15) 512x512 B=512", 512, 512, 512, ms)
+        return
     if args.only == "identity":
         layer = A.RandomChoice([A.RandomChance(A.Invert(), 0.0)], 1)
         ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), bufs, args.iters, warm=1)
