@@ -55,7 +55,11 @@ struct alignas(16) TileState {  // what a tile needs; loaded whole by every tile
   int32_t pass_kind, src_sel, dst_sel, n_sp;
   int32_t kmode, l1_id, l2_id, sp_fast;  // sp_fast: every entry is constant-fill (bbox staging is valid)
   float kfactor;
-  int32_t _pad[3];
+  // a LUT that is the same for every channel and of the form (x & m) ^ c (Invert, Posterize, a full
+  // Solarize and their compositions) is applied with one logic op per word instead of lookups:
+  // bit 16 = valid, bits 8..15 = m, bits 0..7 = c
+  int32_t l1_aff, l2_aff;
+  int32_t _pad[1];
   Spatial sp[CHB_MAX_CHAIN];
   Spatial kgeo;  // K_BILINEAR: the warp (t, fill_mode, color[0] = fill)
   int32_t _pad2[2];

@@ -221,7 +221,7 @@ __device__ __forceinline__ void reset_view(ImgState* s, int tid, int nt) {  // a
     s->t.l2[t >> 8][t & 255] = (uint8_t)(t & 255);
   }
   if (tid == 0) {
-    s->t.n_sp = 0; s->t.kmode = K_NONE; s->t.l1_id = 1; s->t.l2_id = 1; s->t.sp_fast = 1;
+    s->t.n_sp = 0; s->t.kmode = K_NONE; s->t.l1_id = 1; s->t.l2_id = 1; s->t.sp_fast = 1; s->t.l1_aff = 0; s->t.l2_aff = 0;
     s->t.kfactor = 0.0f; s->hist_valid = 0;
   }
 }
@@ -436,6 +436,32 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
         s->tiles_done = 0u;
       }
       break;
+    }
+  }
+  sync();
+  // Classify the LUTs of the pass that runs next (see TileState::l1_aff): hmap[0..1] collect the votes.
+  if (s->t.l1_id && s->t.l2_id) {  // nothing to classify (uniform: read after the barrier above)
+    if (tid == 0) { s->t.l1_aff = 0; s->t.l2_aff = 0; }
+    sync();
+    return;
+  }
+  if (tid < 2) hmap[tid] = 1u;
+  sync();
+  {
+    const int c1 = s->t.l1[0][0], m1 = s->t.l1[0][255] ^ c1;
+    const int c2 = s->t.l2[0][0], m2 = s->t.l2[0][255] ^ c2;
+    bool ok1 = true, ok2 = true;
+    for (int t = tid; t < C * 256; t += nt) {
+      const int x = t & 255;
+      ok1 = ok1 && (s->t.l1[t >> 8][x] == ((x & m1) ^ c1));
+      ok2 = ok2 && (s->t.l2[t >> 8][x] == ((x & m2) ^ c2));
+    }
+    if (!ok1) hmap[0] = 0u;
+    if (!ok2) hmap[1] = 0u;
+    sync();
+    if (tid == 0) {
+      s->t.l1_aff = (hmap[0] && !s->t.l1_id) ? (0x10000 | (m1 << 8) | c1) : 0;
+      s->t.l2_aff = (hmap[1] && !s->t.l2_id) ? (0x10000 | (m2 << 8) | c2) : 0;
     }
   }
   sync();
@@ -817,6 +843,8 @@ __device__ void exec_flat(const TC<C>& c) {
   const int nloc = u1 - u0;
   const int kmode = t.kmode;
   const bool use1 = !t.l1_id, use2 = !t.l2_id;
+  const bool aff1 = (t.l1_aff & 0x10000) != 0;
+  const uint32_t am1 = (uint32_t)((t.l1_aff >> 8) & 0xFF) * 0x01010101u, ac1 = (uint32_t)(t.l1_aff & 0xFF) * 0x01010101u;
   const float f = t.kfactor;
   const uint32_t hl = c.r + (c.lane << 2);
   if (COUNT) {
@@ -837,7 +865,14 @@ __device__ void exec_flat(const TC<C>& c) {
         w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
       }
       if (kmode == K_NONE) {
-        if (!COUNT && use1) map_unit<C, UW>(w, c.l1a);
+        if (!COUNT && use1) {
+          if (aff1) {
+#pragma unroll
+            for (int j = 0; j < UW; ++j) w[j] = (w[j] & am1) ^ ac1;
+          } else {
+            map_unit<C, UW>(w, c.l1a);
+          }
+        }
       } else if (C == 3) {
         if (use1) map_unit<C, UW>(w, c.l1a);
         uint32_t o[UW];
@@ -1131,6 +1166,8 @@ __device__ __forceinline__ void gather_warp(const TC<C>& c, int warp) {
   const int by0m = eb.y0, by1m = eb.y1, bx0m = eb.x0, bx1m = eb.x1;
   const int kmode = t.kmode;
   const bool use1 = !t.l1_id, use2 = !t.l2_id;
+  const bool aff1 = (t.l1_aff & 0x10000) != 0;
+  const uint32_t am1 = (uint32_t)((t.l1_aff >> 8) & 0xFF), ac1 = (uint32_t)(t.l1_aff & 0xFF);
   const float f = t.kfactor;
   const uint32_t fill_a = in.fillc[0], fill_b = in.fillc[1];
   const uint32_t fa_addr = smem_addr(&in.fillc[0]), fb_addr = smem_addr(&in.fillc[1]);  // a miss is just another address
@@ -1194,10 +1231,17 @@ __device__ __forceinline__ void gather_warp(const TC<C>& c, int warp) {
         for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(adr[i] + ch);
       if (!PLAIN) {
         if (kmode == K_NONE) {
+          if (aff1) {  // (x & m) ^ c, the same for every channel: no lookups
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(c.l1a + ch * 256 + v[i][ch]);
+              for (int ch = 0; ch < C; ++ch) v[i][ch] = (v[i][ch] & am1) ^ ac1;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(c.l1a + ch * 256 + v[i][ch]);
+          }
         } else if (C == 3) {
           if (use1) {
 #pragma unroll
