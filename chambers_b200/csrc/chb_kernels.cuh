@@ -53,16 +53,17 @@ constexpr int UNIT_BYTES = 16 * 1024;            // staged source bytes of one u
 // by the consumers.  At most NU items are in flight (each holds a unit), so when item j's state is
 // fetched (one iteration early) the oldest item that can still be in use is j - NU: NU + 2 buffers.
 constexpr int NST = NU + 2;
-constexpr int LHIST_CH_BYTES = 64 * 32 * 4;      // lane-private u8x4 histogram of one channel
 constexpr int STATE_VECS = (int)(offsetof(ImgState, hist) / 16);   // everything but the histogram
 constexpr int TILE_VECS = (int)(sizeof(TileState) / 16);
 constexpr int FIN_BYTES = (int)sizeof(ImgState) + MAXC * 256 * 5;  // finaliser: state + hmap + etab
 // one output staging tile: 64 x 64 pixels (a flat run never exceeds that either)
 __host__ __device__ constexpr int ostage_bytes(int C) { return 4096 * C + 256; }
-// R region: two output tiles | lane-private histograms | finaliser scratch
+// R region: two output tiles | eight histogram copies of a COUNT pass | finaliser scratch
 __host__ __device__ constexpr int r_bytes(int C) {
   return (2 * ostage_bytes(C) > FIN_BYTES ? 2 * ostage_bytes(C) : FIN_BYTES + 127) / 128 * 128;
 }
+static_assert(8 * (1 * 1024 + 16) <= r_bytes(1) && 8 * (2 * 1024 + 16) <= r_bytes(2) && 8 * (3 * 1024 + 16) <= r_bytes(3) &&
+                  8 * (4 * 1024 + 16) <= r_bytes(4), "the histogram copies of exec_flat<COUNT> live in the R region");
 static_assert(offsetof(ImgState, hist) % 16 == 0, "hist must start on a 16-byte boundary");
 static_assert(offsetof(ImgState, next_op) == sizeof(TileState), "finaliser part follows the tile part");
 
@@ -798,36 +799,6 @@ __device__ __forceinline__ uint4 map_vec_phase(uint4 v, uint32_t lut, int ph) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Lane-private histogram: word (v >> 2) * 32 + lane of channel c holds four u8 counters (bins
-// v & ~3 .. v | 3) fed only by lane `lane` of any warp, so a lane always hits its own bank and no
-// two lanes of an instruction ever share an address.  A counter may take at most 255 increments
-// between two reductions.
-__device__ __forceinline__ void lhist_add(uint32_t ch_lane_base, uint32_t v) {
-  reds_add(ch_lane_base + ((v & 0xFCu) << 5), 1u << ((v & 3u) << 3));
-}
-template <int C>
-__device__ __forceinline__ void lhist_zero(uint32_t r, int tid) {
-  for (int i = tid; i < C * LHIST_CH_BYTES / 16; i += NCONS) sts_v4(r + i * 16, make_uint4(0u, 0u, 0u, 0u));
-}
-// Adds the lane-private counters into sm->hist (shared u32 bins).
-template <int C>
-__device__ __forceinline__ void lhist_reduce(PassSmem<C>* sm, uint32_t r, int tid) {
-  const int lane = tid & 31;
-  for (int t = tid; t < C * 64; t += NCONS) {
-    const int ch = t >> 6, row = t & 63;
-    const uint32_t base = r + ch * LHIST_CH_BYTES + row * 128;
-    uint32_t lo = 0, hi = 0;
-#pragma unroll 8
-    for (int l = 0; l < 32; ++l) {
-      const uint32_t w = lds_u32(base + (((l + lane) & 31) << 2));
-      lo += w & 0x00FF00FFu;
-      hi += (w >> 8) & 0x00FF00FFu;
-    }
-    uint32_t* h = &sm->hist[ch][row * 4];
-    h[0] += lo & 0xFFFFu; h[1] += hi & 0xFFFFu; h[2] += lo >> 16; h[3] += hi >> 16;
-  }
-}
-
 // =============================================================================== flat executor
 // No spatial op pending, K in {none, Color}: the tile is a contiguous run of units (48 bytes = 16
 // pixels for C == 3, else 16 bytes) whose channel phase is a compile-time constant.  The run sits in
@@ -846,17 +817,21 @@ __device__ void exec_flat(const TC<C>& c) {
   const bool aff1 = (t.l1_aff & 0x10000) != 0;
   const uint32_t am1 = (uint32_t)((t.l1_aff >> 8) & 0xFF) * 0x01010101u, ac1 = (uint32_t)(t.l1_aff & 0xFF) * 0x01010101u;
   const float f = t.kfactor;
-  const uint32_t hl = c.r + (c.lane << 2);
-  if (COUNT) {
+  // COUNT: eight copies of the u32 histogram in the R region, copy = lane & 7 (a value shared by a
+  // whole warp is a 4-way same-address conflict at worst; copies are skewed by 4 banks so that the
+  // same value in different copies falls in different banks).  Zeroed on the chunk's first tile,
+  // summed into sm->hist on its last: 3 instructions per byte and nothing per tile, against 7 per
+  // byte plus a zero / reduce pass per tile for the lane-private byte counters.
+  constexpr uint32_t HC_COPY_BYTES = (uint32_t)C * 1024u + 16u;
+  const uint32_t hl = c.r + (uint32_t)(c.lane & 7) * HC_COPY_BYTES;
+  if (COUNT && c.info->first) {
     stores_drained(c.tid);  // the R region may still be feeding a store of the previous item
+    cons_sync();
+    for (uint32_t i = (uint32_t)c.tid * 16u; i < 8u * HC_COPY_BYTES; i += NCONS * 16u) sts_v4(c.r + i, make_uint4(0u, 0u, 0u, 0u));
     cons_sync();
   }
   for (int base = 0; base < nloc; base += NCONS) {  // one unit per thread per round
     const int u = base + c.tid;
-    if (COUNT) {
-      lhist_zero<C>(c.r, c.tid);
-      cons_sync();
-    }
     if (u < nloc) {
       uint32_t w[UW];
 #pragma unroll
@@ -894,18 +869,23 @@ __device__ void exec_flat(const TC<C>& c) {
 #pragma unroll
         for (int j = 0; j < UW; ++j)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) lhist_add(hl + ((4 * j + b) % C) * LHIST_CH_BYTES, byte_of(w[j], b));
+          for (int b = 0; b < 4; ++b) reds_add(hl + (uint32_t)(((4 * j + b) % C) * 1024) + (byte_of(w[j], b) << 2), 1u);
       } else {
 #pragma unroll
         for (int q = 0; q < UW / 4; ++q)
           sts_v4(c.ostage + u * UB + q * 16, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
       }
     }
-    if (COUNT) {
-      cons_sync();
-      lhist_reduce<C>(c.sm, c.r, c.tid);
-      cons_sync();
+  }
+  if (COUNT && c.info->last) {
+    cons_sync();
+    for (int i = c.tid; i < C * 256; i += NCONS) {
+      uint32_t sum = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 8u; ++k) sum += lds_u32(c.r + k * HC_COPY_BYTES + (uint32_t)i * 4u);
+      (&c.sm->hist[0][0])[i] += sum;
     }
+    cons_sync();
   }
   if (!COUNT) {
     // CutOut rectangles (the spatial list holds nothing else in this class), in list order

@@ -92,6 +92,12 @@ def main():
         ms = time_layer(lambda i, x, y: ra(x, seed=0, call_counter=i, out=y), b, args.iters, warm=2)
         report("config: RandAugment(3,15) 512x512 B=512", 512, 512, 512, ms)
         return
+    if args.only in ("EqualizeConst", "AutoContrastConst"):  # adversarial histogram input: one value everywhere
+        cb = make_bufs(B, 224, 224, 3, kind="constant")
+        layer = A.RandomChoice([getattr(A, args.only[:-5])()], 1)
+        ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), cb, args.iters, warm=1)
+        report("op:%s(constant image)" % args.only[:-5], B, 224, 224, ms)
+        return
     if args.only == "identity":
         layer = A.RandomChoice([A.RandomChance(A.Invert(), 0.0)], 1)
         ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), bufs, args.iters, warm=1)
