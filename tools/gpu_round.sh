@@ -1,15 +1,12 @@
 #!/bin/bash
-# One GPU visit: full parity tests (memcheck of the first failure if any), headline bench, per-op sweep, timelines.
+# One GPU visit: full parity tests, headline bench, per-op sweep, timelines.
 # Usage: tools/gpu_round.sh [sweep-batch]
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/gpu.txt 2>&1
 (timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 -p no:cacheprovider > gpurun_out/pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest.log)
 grep -E "^(FAILED|ERROR)|passed|failed|exit" gpurun_out/pytest.log | cut -c1-300 | head -20
 if ! grep -q "pytest exit 0" gpurun_out/pytest.log; then
-  first=$(grep -E "^FAILED" gpurun_out/pytest.log | head -1 | sed -E 's/^FAILED ([^ ]+).*/\1/')
-  echo "memcheck of $first"
-  timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest "$first" -x -q -p no:cacheprovider > gpurun_out/memcheck.log 2>&1
-  grep -E "Invalid|at 0x|by thread|Address|chb_kernels|Saved host" gpurun_out/memcheck.log | head -30
+  grep -E "^(FAILED|ERROR)|Error|error" gpurun_out/pytest.log | head -20   # (compute-sanitizer is closed on this pool)
   exit 1
 fi
 (timeout 400 python bench.py --steps 200 --warmup 10 > gpurun_out/bench.log 2>&1; echo "bench exit $?" >> gpurun_out/bench.log)
