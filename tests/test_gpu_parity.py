@@ -368,3 +368,22 @@ def test_concurrent_streams(A):
     torch.cuda.synchronize()
     for c in range(4):
         assert torch.equal(outs[c], ref[c]), "call %d differs when run concurrently" % c
+
+
+def test_repeatability_stress(A):
+    """Race detector of last resort (the pass kernel schedules dynamically: claims, tickets, elections):
+    the same call must produce the same bytes every time, at a small and a large batch, on the default
+    stream and on a side stream, with chains of three ops (COUNT and WRITE_SCRATCH passes included)."""
+    side = torch.cuda.Stream()
+    for B, reps in ((192, 12), (2048, 4)):
+        x = to_gpu(random_images(B, 224, 224, 3, seed=B))
+        for layer in (A.RandAugment(3, 10, elementwise=True), A.AutoAugment(elementwise=True)):
+            for call in range(reps):
+                y0 = layer(x, training=True, seed=11, call_counter=call)
+                with torch.cuda.stream(side):
+                    side.wait_stream(torch.cuda.current_stream())
+                    y1 = layer(x, training=True, seed=11, call_counter=call)
+                torch.cuda.current_stream().wait_stream(side)
+                y2 = layer(x, training=True, seed=11, call_counter=call)
+                torch.cuda.synchronize()
+                assert torch.equal(y0, y1) and torch.equal(y0, y2), "%s B=%d call %d is not repeatable" % (type(layer).__name__, B, call)
