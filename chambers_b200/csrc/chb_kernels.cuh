@@ -2320,8 +2320,9 @@ pass_kernel(const KParams p, const __grid_constant__ TMap tm_in, const __grid_co
     if (!sole) {
       if (tid == 0) {
         __threadfence();  // cumulative: publishes the histogram atomics of the whole CTA (ordered by the barrier)
-        sm->ctl[1] = (atomicAdd(&gr->tiles_done, 1u) == expected_r - 1u) ? 1 : 0;
-        __threadfence();
+        const int elected = (atomicAdd(&gr->tiles_done, 1u) == expected_r - 1u) ? 1 : 0;
+        if (elected) __threadfence();  // acquire side: only the finaliser reads what the others published
+        sm->ctl[1] = elected;
       }
       cons_sync();
       if (!sm->ctl[1]) { TL_ACC(13); continue; }
