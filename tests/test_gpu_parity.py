@@ -387,3 +387,29 @@ def test_repeatability_stress(A):
                 y2 = layer(x, training=True, seed=11, call_counter=call)
                 torch.cuda.synchronize()
                 assert torch.equal(y0, y1) and torch.equal(y0, y2), "%s B=%d call %d is not repeatable" % (type(layer).__name__, B, call)
+
+
+def test_fuzz_shapes_magnitudes_chain_lengths(A):
+    """Seeded fuzz over what the scheduler's arithmetic depends on: image shape (tile counts, ragged tiles,
+    rows that are / are not whole 16-byte units), channel count, batch size (claims of 1 / 2 / 4 tiles,
+    more or fewer tiles than CTAs), magnitude and chain length; device coins, oracle replay."""
+    rng = np.random.default_rng(2026)
+    cases = [(16, 224, 224, 3, 4, 10.0), (3, 130, 192, 3, 3, 7.0), (7, 64, 80, 4, 2, 13.0), (5, 100, 36, 1, 4, 4.0),
+             (9, 48, 112, 2, 3, 10.0), (2, 257, 131, 3, 2, 10.0), (640, 32, 32, 3, 2, 10.0), (1, 384, 320, 3, 5, 10.0)]
+    for _ in range(6):
+        cases.append((int(rng.integers(1, 12)), int(rng.integers(17, 200)), int(rng.integers(17, 200)),
+                      int(rng.choice([1, 2, 3, 4])), int(rng.integers(1, 6)), float(rng.integers(0, 16))))
+    for (B, H, W, C, n, m) in cases:
+        x = random_images(B, H, W, C, seed=B * H + W, kind="smooth" if (H + W) % 2 else "uniform")
+        if C == 3:
+            layer = A.RandAugment(n, m, elementwise=True)
+        else:
+            names = [nm for nm in oracle.OP_NAMES if nm not in ("Color", "Contrast")]
+            layer = A.RandomChoice([getattr(A, nm)(**oracle.magnitude_kwargs(nm, m)) for nm in names], n, elementwise=True)
+        y = run_layer(layer, x, training=True, seed=77, call_counter=3, record=True) if C == 3 else \
+            run_layer(layer, x, seed=77, call_counter=3, record=True)
+        inner = layer._transform if hasattr(layer, "_transform") else layer
+        sched = layer.last_schedule if layer.last_schedule is not None else inner.last_schedule
+        want = oracle.apply_schedule(x, policy_of(layer), sched, elementwise=True)
+        for b in range(B):
+            assert_same(y[b], want[b], "case %r image %d chain %r" % ((B, H, W, C, n, m), b, [oracle.OP_NAMES[i] if C == 3 else i for i in sched[b, :, 0, 0]]))
