@@ -48,14 +48,33 @@ def deserialize(spec):
 
 # ------------------------------------------------------------------------- seeding and phase
 _state = threading.local()
-_global = {"seed": 0, "layer_counter": itertools.count(), "learning_phase": False}
+# seed None = set_random_seed was never called: like the reference's unseeded TF generator, every
+# process then draws its own stream (os.urandom, resolved once, at the first layer that needs it).
+_global = {"seed": None, "layer_counter": itertools.count(), "learning_phase": False}
+_seed_lock = threading.Lock()
 
 
 def set_random_seed(seed):
     """Twin of chambers.utils.set_random_seed (utils/generic.py:43-51) for this path: fixes the
-    Philox key of every layer created or first used afterwards (keyed by creation order)."""
-    _global["seed"] = int(seed) & ((1 << 64) - 1)
-    _global["layer_counter"] = itertools.count()
+    Philox key of every layer CREATED afterwards (the seed is captured in ``Layer.__init__``).  A
+    layer's key is a function of (seed, creation index since the last call of this function), so a
+    program that reseeds with the same value and rebuilds its layers gets the same streams again --
+    the behaviour of ``tf.random.set_seed``, whose op counter restarts as well.  The flip side is the
+    same as in TensorFlow: a layer kept alive across a reseed with the SAME value shares its key with
+    the layer created at the same position afterwards; rebuild the layers after reseeding.  Ranks of
+    a data-parallel job must pass ``image_index_base`` (``chambers_b200.sharding.shard_kwargs``) so
+    that equal local indices on different ranks draw different schedules."""
+    with _seed_lock:
+        _global["seed"] = int(seed) & ((1 << 64) - 1)
+        _global["layer_counter"] = itertools.count()
+
+
+def _resolved_seed():
+    with _seed_lock:
+        if _global["seed"] is None:
+            import os
+            _global["seed"] = int.from_bytes(os.urandom(8), "little")
+        return _global["seed"]
 
 
 def set_learning_phase(value):
@@ -97,8 +116,9 @@ class Layer:
                 raise TypeError("Keyword argument not understood: " + ", ".join(sorted(unknown)))
         self.name = name if name is not None else _auto_name(type(self).__name__)
         self._layer_id = next(_global["layer_counter"])
-        self._base_seed = _global["seed"]
+        self._base_seed = _resolved_seed()
         self._calls = 0
+        self._calls_lock = threading.Lock()
         self.last_schedule = None
 
     # -- Keras surface
@@ -124,8 +144,9 @@ class Layer:
         if seed is None:
             seed = _splitmix64(self._base_seed ^ ((self._layer_id + 1) * 0xD1B54A32D192ED03 & ((1 << 64) - 1)))
         if call_counter is None:
-            call_counter = self._calls
-            self._calls += 1
+            with self._calls_lock:  # a layer may be shared by tf.data-style worker threads
+                call_counter = self._calls
+                self._calls += 1
         return int(seed) & ((1 << 64) - 1), int(call_counter) & 0xFFFFFFFF
 
 
@@ -189,7 +210,6 @@ def run_policy(inputs, transforms, n_draws, elementwise, seed, call_counter, bat
     is_torch = torch is not None and isinstance(inputs, torch.Tensor)
     if is_torch and inputs.is_cuda:
         dev = inputs.device.index if inputs.device.index is not None else torch.cuda.current_device()
-        ctx = _lib.context(dev)
         x = inputs.contiguous()
         if out is None:
             out = torch.empty_like(x)
@@ -204,6 +224,9 @@ def run_policy(inputs, transforms, n_draws, elementwise, seed, call_counter, bat
         if record:
             d_record = torch.zeros(sched_shape, dtype=torch.int32, device=x.device)
         with torch.cuda.device(dev):
+            # (the context is created inside the guard: chb_init makes `dev` current only for its own
+            # duration, and torch's notion of the current device stays the caller's)
+            ctx = _lib.context(dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = lib.chb_policy_apply(
                 ctx, x.data_ptr(), out.data_ptr(), B, H, W, C, ctypes.byref(pol), int(batch_total),

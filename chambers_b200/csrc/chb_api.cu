@@ -96,6 +96,25 @@ static bool encode_image_map(chb::TMap* out, const void* base, int H, int rowbyt
   return r == CUDA_SUCCESS;
 }
 
+// Every entry point that touches the device makes ctx->device current for its own duration and puts
+// the caller's current device back on every exit path (a caller with several GPUs in one process
+// must not find its current device changed by a chb_* call).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    if (prev == device) return cudaSuccess;
+    e = cudaSetDevice(device);
+    switched = (e == cudaSuccess);
+    return e;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 static int fail(chb_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg; else g_init_error = msg;
   return code;
@@ -353,7 +372,8 @@ extern "C" int chb_init(int device, chb_ctx** out) {
                 std::string("chb_init: no CUDA device (") + cudaGetErrorString(e) +
                     "); libchambers_aug has no CPU fallback");
   if (device < 0 || device >= n) return fail(nullptr, CHB_ERR_INVALID, "chb_init: bad device index");
-  CHB_CUDA(nullptr, cudaSetDevice(device));
+  DeviceGuard guard;
+  CHB_CUDA(nullptr, guard.enter(device));
   cudaDeviceProp prop;
   CHB_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
@@ -385,7 +405,8 @@ extern "C" int chb_init(int device, chb_ctx** out) {
 
 extern "C" void chb_destroy(chb_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard;
+  guard.enter(ctx->device);
   cudaDeviceSynchronize();
   for (PolicyEntry* pe : ctx->cache) { cudaFree(pe->dev); cudaFree(pe->optab); delete pe; }
   for (Workspace* ws : ctx->workspaces) {
@@ -411,7 +432,8 @@ extern "C" int chb_debug_timeline(chb_ctx* ctx, uint64_t* host_out, int max_word
   if (!ctx) return CHB_ERR_INVALID;
 #ifdef CHB_TIMELINE
   const size_t kTimelineWords = (size_t)1024 * 2 * 16;
-  CHB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard guard;
+  CHB_CUDA(ctx, guard.enter(ctx->device));
   if (!ctx->timeline) {
     CHB_CUDA(ctx, cudaMalloc(&ctx->timeline, kTimelineWords * 8));
     CHB_CUDA(ctx, cudaMemset(ctx->timeline, 0, kTimelineWords * 8));
@@ -559,7 +581,8 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   if (r != CHB_OK) return r;
   if ((long long)H * W * C > 0x3FFFFFFFll) return fail(ctx, CHB_ERR_UNSUPPORTED, "image larger than 1 GiB");
   if (H >= (1 << 22) || W >= (1 << 22)) return fail(ctx, CHB_ERR_UNSUPPORTED, "image side of 4M pixels or more");
-  CHB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard guard;
+  CHB_CUDA(ctx, guard.enter(ctx->device));
   PolicyEntry* pe = nullptr;
   r = get_policy(ctx, pol, K, H, W, C, batch_total, stream, &pe);  // validates ops even when B == 0
   if (r != CHB_OK) return r;
@@ -571,9 +594,10 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     return fail(ctx, CHB_ERR_UNSUPPORTED, "batch * tiles exceeds the 32-bit work counter");
   const int chain = pol->n_draws * K;
   // An op triggers an extra pass over the pixels only if it is a histogram op (COUNT) or finds the
-  // kernel slot K occupied / frozen by an earlier op (WRITE_SCRATCH).  Every pass after an image's
-  // first is run by the CTA that completed the previous one (chb_kernels.cuh), so a call is one plan
-  // launch and one pass launch whatever the chain length.
+  // kernel slot K occupied / frozen by an earlier op (WRITE_SCRATCH).  The CTA that completes such a
+  // pass publishes the image's next pass in the continuation list, where every CTA of the same
+  // launch holds a ticket (chb_kernels.cuh), so a call is one plan launch and one pass launch
+  // whatever the chain length.
   // tiles read neighbours of their own region: an in-place call goes through a temporary.
   const bool overlap = (d_in < d_out + (size_t)B * img_bytes) && (d_out < d_in + (size_t)B * img_bytes);
   const size_t stride = (img_bytes + 255) / 256 * 256;
@@ -737,7 +761,8 @@ extern "C" int chb_policy_apply_host(chb_ctx* ctx, const uint8_t* h_in, uint8_t*
   int K = 1;
   int r = validate_policy(ctx, policy, K);
   if (r != CHB_OK) return r;
-  CHB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard guard;
+  CHB_CUDA(ctx, guard.enter(ctx->device));
   const size_t img = (size_t)H * W * C;
   if (B == 0 || img == 0) {
     // still validate the ops the way a real call would

@@ -77,9 +77,16 @@ SINGLE_OPS = [
 
 
 @pytest.mark.parametrize("name,kwargs", SINGLE_OPS, ids=lambda v: str(v) if isinstance(v, str) else "-".join("%s" % x for x in v.values()))
-@pytest.mark.parametrize("shape,kind", [((5, 37, 53, 3), "uniform"), ((3, 224, 224, 3), "smooth"), ((2, 96, 64, 3), "lowentropy")])
+@pytest.mark.parametrize("shape,kind", [((5, 37, 53, 3), "uniform"), ((3, 224, 224, 3), "smooth"), ((2, 96, 64, 3), "lowentropy"),
+                                        # one value everywhere: Equalize's step == 0 and AutoContrast's hi == lo identity
+                                        # branches (image_augmentations.py:76-78; tfa equalize `step == 0`)
+                                        ((2, 224, 224, 3), "constant"), ((3, 48, 32, 3), "constant"),
+                                        # fewer than 255 pixels per channel: (sum - last) // 255 == 0 whatever the content
+                                        ((4, 9, 16, 3), "uniform")])
 def test_single_op_layers(A, name, kwargs, shape, kind):
     x = random_images(*shape, seed=11, kind=kind)
+    if kind == "constant":
+        x[1] = 255 - x[0]  # a second constant value (and one image per branch of the solarize / posterize maps)
     layer = getattr(A, name)(**kwargs)
     for call in range(2):  # two calls: both sign flips / different centres are likely to occur
         y = run_layer(layer, x, seed=99, call_counter=call, record=True)
@@ -413,3 +420,115 @@ def test_fuzz_shapes_magnitudes_chain_lengths(A):
         want = oracle.apply_schedule(x, policy_of(layer), sched, elementwise=True)
         for b in range(B):
             assert_same(y[b], want[b], "case %r image %d chain %r" % ((B, H, W, C, n, m), b, [oracle.OP_NAMES[i] if C == 3 else i for i in sched[b, :, 0, 0]]))
+
+
+def test_c_abi_policy_entry_points(A):
+    """chb_randaugment / chb_autoaugment / chb_apply_op called through ctypes exactly as INTEGRATION.md
+    section 2 binds them, against chb_policy_apply (the entry point the Python layers use)."""
+    import ctypes
+    from chambers_b200 import _lib
+    lib = _lib.load()
+    x = to_gpu(random_images(48, 64, 80, 3, seed=5, kind="smooth"))
+    dev = torch.cuda.current_device()
+    ctx = _lib.context(dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    n_sched = 48 * 3 * 2 * _lib.CHB_SCHED_FIELDS
+
+    def call(fn, *args):
+        out = torch.empty_like(x)
+        rec = torch.zeros(n_sched, dtype=torch.int32, device=x.device)
+        _lib.check(ctx, fn(ctx, x.data_ptr(), out.data_ptr(), 48, 64, 80, 3, *args, 48, 1000, 0xABCDEF, 7, None, rec.data_ptr(), stream))
+        torch.cuda.synchronize()
+        return out, rec.cpu().numpy()
+
+    for ew in (0, 1):
+        got, rec = call(lib.chb_randaugment, 3, ctypes.c_double(7.0), ew)
+        layer = A.RandAugment(3, 7.0, elementwise=bool(ew))
+        want = layer(x, training=True, seed=0xABCDEF, call_counter=7, image_index_base=1000, batch_total=48, record=True)
+        assert torch.equal(got, want), "chb_randaugment elementwise=%d" % ew
+        assert (rec[:48 * 3 * 5].reshape(48, 3, 1, 5) == layer.last_schedule).all()
+        got, rec = call(lib.chb_autoaugment, ew)
+        layer = A.AutoAugment(elementwise=bool(ew))
+        want = layer(x, training=True, seed=0xABCDEF, call_counter=7, image_index_base=1000, batch_total=48, record=True)
+        assert torch.equal(got, want), "chb_autoaugment elementwise=%d" % ew
+        assert (rec[:48 * 2 * 5].reshape(48, 1, 2, 5) == layer.last_schedule).all()
+    for layer in (A.Rotate(25.0, fill_value=9.0), A.Equalize(), A.CutOut(20, 7), A.Sharpness(1.7), A.TranslateX(11.0)):
+        op = _lib.ChbOp()
+        layer._fill_op(op)
+        op.probability = -1.0
+        got, _ = call(lib.chb_apply_op, ctypes.byref(op))
+        want = layer(x, seed=0xABCDEF, call_counter=7, image_index_base=1000, batch_total=48)
+        assert torch.equal(got, want), "chb_apply_op %s" % type(layer).__name__
+    # the oracle on the direct entry point as well (not only through the layers)
+    got, rec = call(lib.chb_randaugment, 2, ctypes.c_double(10.0), 1)
+    pol = oracle.randaugment_policy(2, 10)
+    want = oracle.apply_schedule(x.cpu().numpy(), pol, rec[:48 * 2 * 5].reshape(48, 2, 1, 5), elementwise=True)
+    assert_same(got.cpu().numpy(), want, "chb_randaugment vs oracle")
+
+
+def test_config3_full_shape_sampled(A):
+    """BASELINE.json configs[3] as specified: RandAugment(N=3, M=15) on 512 x 512 x 512 x 3 (64 tiles per image
+    in the tile engine, whole-pass claims); a sample of the images against the oracle, shard invariance on the
+    second half, and run-to-run determinism."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 256, (512, 512, 512, 3), dtype=torch.uint8, generator=g)
+    xg = x.cuda()
+    layer = A.RandAugment(3, 15, elementwise=True)
+    y = layer(xg, training=True, seed=15, call_counter=2, record=True)
+    sched = layer.last_schedule
+    idx = [0, 63, 147, 148, 255, 296, 400, 511]
+    want = oracle.apply_schedule(x.numpy()[idx], policy_of(layer), sched[idx], elementwise=True)
+    got = y[idx].cpu().numpy()
+    for k, b in enumerate(idx):
+        assert_same(got[k], want[k], "image %d chain %r" % (b, [oracle.OP_NAMES[i] for i in sched[b, :, 0, 0]]))
+    assert torch.equal(layer(xg, training=True, seed=15, call_counter=2), y)
+    half = layer(xg[256:], training=True, seed=15, call_counter=2, batch_total=512, image_index_base=256)
+    assert torch.equal(half, y[256:])
+
+
+def test_host_path_chunk_pipeline(A):
+    """chb_policy_apply_host with many chunks (> 2 * streams + 1: every staging slot is reused, the
+    last chunk is ragged): bit-identical to the device path, elementwise and batch mode (Contrast's
+    constant and the batch-level schedule must be the same in every chunk; CutOut centres are keyed by
+    the global image index), record on the host path then replay on both."""
+    B = 157  # 157 x 150528 B = 23.6 MB -> 10 chunks of 16 images, the last one of 13
+    x = random_images(B, 224, 224, 3, seed=77, kind="smooth")
+    xg = to_gpu(x)
+    kw = dict(interpolation="nearest", fill_mode="constant", fill_value=128.0)
+    for ew in (True, False):
+        chain = A.Sequential([A.Contrast(1.5), A.CutOut(40, 128), A.Rotate(20.0, **kw)])
+        for layer in (A.RandomChoice([chain, A.Equalize(), A.Sharpness(1.9)], 2, elementwise=ew),
+                      A.RandAugment(2, 10, elementwise=ew)._transform):
+            dev_out = layer(xg, seed=5, call_counter=9, image_index_base=300, batch_total=1000, record=True)
+            dev_sched = layer.last_schedule
+            host_out = layer(x, seed=5, call_counter=9, image_index_base=300, batch_total=1000, record=True)
+            host_sched = layer.last_schedule
+            assert (host_sched == dev_sched).all(), "recorded schedules differ (elementwise=%s)" % ew
+            assert (host_out == dev_out.cpu().numpy()).all(), "host path != device path (elementwise=%s)" % ew
+            # replay what was recorded, on the host path (rows sliced per chunk) and on the device
+            rep_host = layer(x, replay=host_sched, batch_total=1000)
+            rep_dev = layer(xg, replay=host_sched, batch_total=1000)
+            assert (rep_host == host_out).all() and torch.equal(rep_dev, dev_out), "replay differs (elementwise=%s)" % ew
+
+
+def test_multi_gpu_fixed_batch_is_shard_invariant(A):
+    """BASELINE.json configs[2]: AutoAugment on a FIXED 4096 x 224 x 224 x 3 batch sharded over 2 / 4 / 8
+    visible GPUs -- the concatenated shards equal the 1-GPU result bit for bit (RNG keyed by global image
+    index, Contrast constant by batch_total).  One process driving several devices also exercises the
+    current-device guard of the C ABI."""
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least 2 visible GPUs")
+    from chambers_b200.sharding import shard_bounds, shard_kwargs
+    g = torch.Generator().manual_seed(11)
+    x = torch.randint(0, 256, (4096, 224, 224, 3), dtype=torch.uint8, generator=g)
+    for layer in (A.AutoAugment(elementwise=True), A.RandAugment(2, 10, elementwise=False)):
+        whole = layer(x.cuda(0), training=True, seed=21, call_counter=4).cpu()
+        for world in [w for w in (2, 4, 8) if w <= n_dev]:
+            parts = []
+            for r in range(world):
+                a, b = shard_bounds(4096, r, world)
+                parts.append(layer(x[a:b].cuda(r), training=True, seed=21, call_counter=4, **shard_kwargs(4096, r, world)))
+            assert torch.cuda.current_device() == 0, "a chb_* call changed the caller's current device"
+            got = torch.cat([p.cpu() for p in parts])
+            assert torch.equal(got, whole), "%s: %d shards differ from 1 GPU" % (type(layer).__name__, world)
