@@ -91,6 +91,8 @@ SIGNATURES = {
     "chb_policy_apply_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChbPolicy), _i64, _i64,
                                    _u64, _u32, _vp, _vp]),
     "chb_set_debug": (_i, [_vp, _i]),
+    "chb_set_engine": (_i, [_vp, _i]),
+    "chb_last_engine": (_i, [_vp]),
     "chb_debug_timeline": (_i, [_vp, _vp, _i]),
     "chb_tile_plan": (_i, [_i, _i] + [ctypes.POINTER(_i)] * 4),
 }
@@ -153,3 +155,17 @@ def tile_plan(H, W):
 def set_debug(device, force_generic):
     """Route every tile through the scalar executor (tests cross-check it against the fast ones)."""
     check(context(device), load().chb_set_debug(context(device), 1 if force_generic else 0))
+
+
+ENGINES = {"auto": 0, "tiles": 1, "resident": 2}
+
+
+def set_engine(device, engine):
+    """Select the engine of (this thread, device): "auto" | "tiles" | "resident" (chb_set_engine)."""
+    check(context(device), load().chb_set_engine(context(device), ENGINES[engine]))
+
+
+def last_engine(device):
+    """Engine the last device call of (this thread, device) ran on: "tiles" | "resident"."""
+    v = int(load().chb_last_engine(context(device)))
+    return {1: "tiles", 2: "resident"}.get(v, "none")

@@ -51,6 +51,9 @@ struct chb_ctx {
   std::string err;
   int64_t launches = 0;
   int force_generic = 0;  // CHB_FORCE_GENERIC=1: every tile through the scalar executor (debugging)
+  int engine = 0;         // CHB_ENGINE_*: 0 = resident where eligible, else tiles
+  int res_smem = 0;       // dynamic shared memory of a resident CTA (0: engine unavailable)
+  int last_engine = 0;    // engine the last device call ran on (CHB_ENGINE_TILES / CHB_ENGINE_RESIDENT)
   unsigned long long* timeline = nullptr;  // debug builds only (chb_debug_timeline)
   std::vector<Workspace*> workspaces;
   std::vector<PolicyEntry*> cache;
@@ -386,6 +389,13 @@ extern "C" int chb_init(int device, chb_ctx** out) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   e = chb::configure_kernels();
   if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "configure_kernels"); delete ctx; return r; }
+  ctx->res_smem = (int)prop.sharedMemPerBlockOptin;  // the resident kernels have no static shared memory
+  e = chb::configure_resident(ctx->res_smem);
+  if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "configure_resident"); delete ctx; return r; }
+  if (const char* en = getenv("CHB_ENGINE")) {
+    if (!strcmp(en, "tiles")) ctx->engine = CHB_ENGINE_TILES;
+    else if (!strcmp(en, "resident")) ctx->engine = CHB_ENGINE_RESIDENT;
+  }
   if (!g_encode_tiled) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -427,6 +437,15 @@ extern "C" int chb_set_debug(chb_ctx* ctx, int force_generic) {
   ctx->force_generic = force_generic ? 1 : 0;
   return CHB_OK;
 }
+
+extern "C" int chb_set_engine(chb_ctx* ctx, int engine) {
+  if (!ctx) return CHB_ERR_INVALID;
+  if (engine < CHB_ENGINE_AUTO || engine > CHB_ENGINE_RESIDENT) return fail(ctx, CHB_ERR_INVALID, "chb_set_engine: unknown engine");
+  ctx->engine = engine;
+  return CHB_OK;
+}
+
+extern "C" int chb_last_engine(const chb_ctx* ctx) { return ctx ? ctx->last_engine : 0; }
 
 extern "C" int chb_debug_timeline(chb_ctx* ctx, uint64_t* host_out, int max_words) {
   if (!ctx) return CHB_ERR_INVALID;
@@ -569,6 +588,32 @@ static int get_workspace(chb_ctx* ctx, cudaStream_t stream, int B, size_t scratc
   return CHB_OK;
 }
 
+// Can this call run on the image-resident engine (chb_resident.cuh)?  The image, the control block and
+// a working region (histogram copies / the halo band of a gathered Sharpness) must fit one SM's shared
+// memory; rows and images are whole 16-byte units at 16-byte aligned addresses (bulk copies, vector
+// loads); every geometric op of the table is nearest / constant-fill (what the policies build,
+// augmentation_schemes.py:7-9) -- bilinear warps and the other fill modes stay on the tile engine.
+static bool resident_eligible(const chb_ctx* ctx, const PolicyEntry* pe, const uint8_t* d_in, const uint8_t* d_out,
+                              int H, int W, int C) {
+  if (ctx->engine == CHB_ENGINE_TILES || ctx->force_generic || ctx->res_smem <= 0) return false;
+  const size_t img_bytes = (size_t)H * W * C;
+  const size_t row = (size_t)W * C;
+  if ((row & 15) != 0 || img_bytes == 0) return false;
+  if ((((uintptr_t)d_in) & 15) != 0 || (((uintptr_t)d_out) & 15) != 0) return false;
+  if (img_bytes > (size_t)chb::resident_max_chunk_bytes()) return false;
+  const size_t fixed = chb::resident_ctl_bytes() + (img_bytes + 127) / 128 * 128;
+  if (fixed > (size_t)ctx->res_smem) return false;
+  const size_t aux = (size_t)ctx->res_smem - fixed;
+  const size_t hist_copy = (size_t)C * 1024 + 16;
+  if (aux < hist_copy + 4 * (row + 16) || aux < 16 * 1024) return false;
+  for (const DevOp& d : pe->host) {
+    const bool geo = d.kind == CHB_OP_SHEAR_X || d.kind == CHB_OP_SHEAR_Y || d.kind == CHB_OP_TRANSLATE_X ||
+                     d.kind == CHB_OP_TRANSLATE_Y || d.kind == CHB_OP_ROTATE;
+    if (geo && (d.interp != CHB_INTERP_NEAREST || d.fill_mode != CHB_FILL_CONSTANT)) return false;
+  }
+  return true;
+}
+
 static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int B, int H, int W, int C,
                          const chb_policy* pol, int64_t batch_total, int64_t image_index_base,
                          uint64_t seed, uint32_t call_counter, const int32_t* d_replay,
@@ -602,6 +647,41 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   const bool overlap = (d_in < d_out + (size_t)B * img_bytes) && (d_out < d_in + (size_t)B * img_bytes);
   const size_t stride = (img_bytes + 255) / 256 * 256;
   Workspace* ws = nullptr;
+  // The resident engine reads an image completely before it writes any byte of it and never reads
+  // another image's bytes: d_in == d_out needs no temporary there (a partial overlap still does).
+  const bool resident = resident_eligible(ctx, pe, d_in, d_out, H, W, C);
+  if (ctx->engine == CHB_ENGINE_RESIDENT && !resident)
+    return fail(ctx, CHB_ERR_UNSUPPORTED, "CHB_ENGINE_RESIDENT: this call is not eligible for the image-resident engine");
+  if (resident) {
+    const bool temp = overlap && d_in != d_out;
+    int grid = ctx->num_sms < B ? ctx->num_sms : B;
+    r = get_workspace(ctx, stream, 1, chain >= 2 ? (size_t)grid * stride : 0, temp ? (size_t)B * img_bytes : 0, &ws);
+    if (r != CHB_OK) return r;
+    chb::KParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = d_in; p.out = temp ? ws->inplace : d_out; p.B = B; p.H = H; p.W = W;
+    p.ops = pe->dev; p.optab = pe->optab; p.T = pol->n_table; p.n_draws = pol->n_draws; p.K = K;
+    p.elementwise = pol->elementwise ? 1 : 0;
+    p.seed = seed; p.call_counter = call_counter; p.image_index_base = (unsigned long long)image_index_base;
+    p.replay = d_replay; p.record = d_record;
+    p.scratch = ws->scratch; p.scratch_stride = stride;
+    p.counters = ws->counters;
+    p.res_smem_bytes = ctx->res_smem;
+    cudaError_t e = cudaSuccess;
+    if (!ws->clean || !g_self_clean) {
+      e = cudaMemsetAsync(ws->counters, 0, (32 + ws->cap_images * CHB_MAX_CHAIN + 2048) * sizeof(unsigned int), stream);
+      if (e != cudaSuccess) return cuda_fail(ctx, e, "counter reset");
+    }
+    ws->clean = false;
+    e = chb::launch_resident(p, C, grid, stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "resident kernel launch");
+    ctx->launches += 1;
+    ctx->last_engine = CHB_ENGINE_RESIDENT;
+    ws->clean = true;
+    if (temp) CHB_CUDA(ctx, cudaMemcpyAsync(d_out, ws->inplace, (size_t)B * img_bytes, cudaMemcpyDeviceToDevice, stream));
+    return CHB_OK;
+  }
+  ctx->last_engine = CHB_ENGINE_TILES;
   r = get_workspace(ctx, stream, B, chain >= 2 ? (size_t)B * 2 * stride : 0,
                     overlap ? (size_t)B * img_bytes : 0, &ws);
   if (r != CHB_OK) return r;

@@ -113,6 +113,7 @@ struct KParams {
   int n_flat_tiles;                   // flat runs per image (tiles of <= 256 units; == n_tiles unless the batch is 16-byte aligned)
   int flags;                          // 1: in is 16-byte aligned, 2: out is, 4: images are whole 16-byte units, 8: rows are
   unsigned long long* timeline;       // debug builds (-DCHB_TIMELINE): [1024 CTAs][2][16] words, else NULL
+  int res_smem_bytes;                 // resident engine: dynamic shared memory of a CTA (control + image + aux region)
 };
 
 // Opaque copy of a CUtensorMap (cuda.h), passed to the pass kernel as a __grid_constant__ parameter.
@@ -131,5 +132,10 @@ cudaError_t launch_plan(const KParams& p, int C, cudaStream_t stream);
 cudaError_t launch_pass(const KParams& p, const TMap& tm_in, const TMap& tm_scr, int C, int grid, cudaStream_t stream);
 cudaError_t configure_kernels();
 int pass_ctas_per_sm(int C);
+// Image-resident engine (chb_resident.cuh): one CTA per SM, the whole image in shared memory.
+cudaError_t launch_resident(const KParams& p, int C, int grid, cudaStream_t stream);
+cudaError_t configure_resident(int smem_bytes);
+size_t resident_ctl_bytes();  // shared memory in front of the image buffer
+int resident_max_chunk_bytes();
 
 }  // namespace chb

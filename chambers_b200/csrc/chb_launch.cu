@@ -9,6 +9,11 @@ namespace chb {
   int ctas_per_sm_c##C();
 CHB_DECL(1) CHB_DECL(2) CHB_DECL(3) CHB_DECL(4)
 #undef CHB_DECL
+#define CHB_DECL_RES(C)                                                        \
+  cudaError_t launch_resident_c##C(const KParams&, int, cudaStream_t);         \
+  cudaError_t configure_resident_c##C(int);
+CHB_DECL_RES(1) CHB_DECL_RES(2) CHB_DECL_RES(3) CHB_DECL_RES(4)
+#undef CHB_DECL_RES
 
 // 2-D tiles of 64 x 64 pixels, ragged at the right / bottom edge (64-pixel columns keep every tile
 // row a whole number of 16-byte units for C = 1..4, and 64 x 64, 64 x 32 and 32 x 32 tiles are all
@@ -50,6 +55,24 @@ cudaError_t launch_pass(const KParams& p, const TMap& a, const TMap& b, int C, i
     case 2: return launch_pass_c2(p, a, b, grid, stream);
     case 3: return launch_pass_c3(p, a, b, grid, stream);
     case 4: return launch_pass_c4(p, a, b, grid, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t configure_resident(int smem_bytes) {
+  cudaError_t e;
+  if ((e = configure_resident_c1(smem_bytes)) != cudaSuccess) return e;
+  if ((e = configure_resident_c2(smem_bytes)) != cudaSuccess) return e;
+  if ((e = configure_resident_c3(smem_bytes)) != cudaSuccess) return e;
+  return configure_resident_c4(smem_bytes);
+}
+
+cudaError_t launch_resident(const KParams& p, int C, int grid, cudaStream_t stream) {
+  switch (C) {
+    case 1: return launch_resident_c1(p, grid, stream);
+    case 2: return launch_resident_c2(p, grid, stream);
+    case 3: return launch_resident_c3(p, grid, stream);
+    case 4: return launch_resident_c4(p, grid, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -1,0 +1,6 @@
+// resident_kernel<2> instantiation (see chb_resident.cuh).
+#include "chb_resident.cuh"
+namespace chb {
+cudaError_t launch_resident_c2(const KParams& p, int grid, cudaStream_t stream) { return launch_resident_c<2>(p, grid, stream); }
+cudaError_t configure_resident_c2(int smem_bytes) { return configure_resident_c<2>(smem_bytes); }
+}  // namespace chb

@@ -1,0 +1,6 @@
+// resident_kernel<4> instantiation (see chb_resident.cuh).
+#include "chb_resident.cuh"
+namespace chb {
+cudaError_t launch_resident_c4(const KParams& p, int grid, cudaStream_t stream) { return launch_resident_c<4>(p, grid, stream); }
+cudaError_t configure_resident_c4(int smem_bytes) { return configure_resident_c<4>(smem_bytes); }
+}  // namespace chb

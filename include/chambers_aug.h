@@ -169,6 +169,18 @@ int chb_policy_apply_host(chb_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, int
  * the vectorised ones (same results, used by the tests to cross-check the two on the device). */
 int chb_set_debug(chb_ctx* ctx, int force_generic);
 
+/* Engine selection.  The library holds two engines with identical results:
+ *   CHB_ENGINE_RESIDENT  one CTA per SM keeps a whole image in shared memory for its entire op chain
+ *                        (images of up to ~190 KB whose rows are whole 16-byte units, nearest /
+ *                        constant-fill geometric ops: every BASELINE 224 x 224 x 3 configuration);
+ *   CHB_ENGINE_TILES     the tile-parallel engine: any shape, any fill mode, bilinear warps.
+ * CHB_ENGINE_AUTO (default) takes the resident engine whenever a call is eligible.  Forcing
+ * CHB_ENGINE_RESIDENT makes ineligible calls fail with CHB_ERR_UNSUPPORTED (tests use it to be sure
+ * which engine they compare).  Environment: CHB_ENGINE=tiles|resident at chb_init. */
+enum chb_engine { CHB_ENGINE_AUTO = 0, CHB_ENGINE_TILES = 1, CHB_ENGINE_RESIDENT = 2 };
+int chb_set_engine(chb_ctx* ctx, int engine);
+int chb_last_engine(const chb_ctx* ctx); /* engine of the last device call: CHB_ENGINE_TILES / _RESIDENT */
+
 /* Profiling hook of debug builds (-DCHB_TIMELINE; the production library returns
  * CHB_ERR_UNSUPPORTED).  host_out == NULL: start recording per-CTA timestamps of the pass kernels.
  * Otherwise: synchronise the device, copy up to max_words 64-bit words of the records to host_out

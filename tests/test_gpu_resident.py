@@ -1,0 +1,208 @@
+"""GPU parity tests of the image-resident engine (chb_resident.cuh), forced with chb_set_engine so a
+silent fall-back to the tile engine cannot hide it: against the oracle on identical schedules, and bit
+for bit against the tile engine of the same library (two independent executions of the same lazy
+chain state)."""
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import random_images
+from test_gpu_parity import assert_same, policy_of, to_gpu, _replay_all_pairs
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def A():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    from chambers_b200 import build, augmentations
+    build.build_library()
+    return augmentations
+
+
+class engine:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        from chambers_b200 import _lib
+        self.dev = torch.cuda.current_device()
+        _lib.set_engine(self.dev, self.name)
+
+    def __exit__(self, *a):
+        from chambers_b200 import _lib
+        _lib.set_engine(self.dev, "auto")
+
+
+def both_engines(layer, xg, **kw):
+    from chambers_b200 import _lib
+    with engine("resident"):
+        r = layer(xg, **kw)
+        assert _lib.last_engine(torch.cuda.current_device()) == "resident"
+    with engine("tiles"):
+        t = layer(xg, **kw)
+        assert _lib.last_engine(torch.cuda.current_device()) == "tiles"
+    torch.cuda.synchronize()
+    return r, t
+
+
+def test_auto_engine_choice(A):
+    from chambers_b200 import _lib
+    dev = torch.cuda.current_device()
+    ra = A.RandAugment(2, 10, elementwise=True)
+    ra(to_gpu(random_images(4, 224, 224, 3)), training=True)
+    assert _lib.last_engine(dev) == "resident"          # every BASELINE 224 x 224 x 3 configuration
+    ra(to_gpu(random_images(2, 512, 512, 3)), training=True)
+    assert _lib.last_engine(dev) == "tiles"             # 768 KB does not fit an SM
+    ra(to_gpu(random_images(2, 37, 53, 3)), training=True)
+    assert _lib.last_engine(dev) == "tiles"             # rows are not whole 16-byte units
+    A.Rotate(10.0, interpolation="bilinear")(to_gpu(random_images(2, 64, 64, 3)))
+    assert _lib.last_engine(dev) == "tiles"
+    A.Rotate(10.0, fill_mode="reflect")(to_gpu(random_images(2, 64, 64, 3)))
+    assert _lib.last_engine(dev) == "tiles"
+    with engine("resident"):
+        with pytest.raises(_lib.ChambersAugError):
+            ra(to_gpu(random_images(2, 37, 53, 3)), training=True)
+
+
+@pytest.mark.parametrize("magnitude,shape", [(10, (224, 224)), (15, (224, 224)), (10, (64, 64)), (3, (96, 160)), (10, (16, 16)),
+                                             (10, (250, 256)), (15, (2, 32)), (10, (1, 48))])
+def test_all_256_op_pairs(A, magnitude, shape):
+    """Every ordered pair of the 16 ops: resident == tiles everywhere, and both == oracle on a sample
+    (all 256 for the small shapes)."""
+    H, W = shape
+    s, rng = _replay_all_pairs()
+    s[..., 3] = rng.integers(0, H, size=s.shape[:3])
+    s[..., 4] = rng.integers(0, W, size=s.shape[:3])
+    x = random_images(256, H, W, 3, seed=H * 7 + W, kind="smooth" if magnitude == 3 else "uniform")
+    xg = to_gpu(x)
+    layer = A.RandAugment(2, magnitude, elementwise=True)
+    r, t = both_engines(layer, xg, training=True, replay=s)
+    same = (r == t).flatten(1).all(dim=1).cpu().numpy()
+    bad = [(oracle.OP_NAMES[s[b, 0, 0, 0]], oracle.OP_NAMES[s[b, 1, 0, 0]]) for b in np.nonzero(~same)[0]]
+    assert not bad, "resident != tiles for pairs %r" % (bad[:16],)
+    idx = list(range(256)) if H * W <= 64 * 64 else list(range(5, 256, 23))
+    want = oracle.apply_schedule(x[idx], policy_of(layer), s[idx], elementwise=True)
+    got = r[idx].cpu().numpy()
+    for k, b in enumerate(idx):
+        assert_same(got[k], want[k], "pair %s -> %s" % (oracle.OP_NAMES[s[b, 0, 0, 0]], oracle.OP_NAMES[s[b, 1, 0, 0]]))
+
+
+def test_triples_and_long_chains(A):
+    for n, B, shape in ((3, 768, (48, 64)), (6, 192, (64, 80)), (4, 64, (224, 224))):
+        x = random_images(B, shape[0], shape[1], 3, seed=n, kind="smooth" if n == 6 else "uniform")
+        xg = to_gpu(x)
+        layer = A.RandAugment(n, 15 if n == 3 else 10, elementwise=True)
+        with engine("resident"):
+            y = layer(xg, training=True, seed=3, call_counter=n, record=True)
+        sched = layer.last_schedule
+        with engine("tiles"):
+            t = layer(xg, training=True, replay=sched)
+        bad = np.nonzero(~(y == t).flatten(1).all(dim=1).cpu().numpy())[0]
+        assert bad.size == 0, "resident != tiles for chains %r" % ([[oracle.OP_NAMES[i] for i in sched[b, :, 0, 0]] for b in bad[:6]],)
+        idx = list(range(B)) if shape[0] < 100 else list(range(0, B, 7))
+        want = oracle.apply_schedule(x[idx], policy_of(layer), sched[idx], elementwise=True)
+        got = y[idx].cpu().numpy()
+        for k, b in enumerate(idx):
+            assert_same(got[k], want[k], "chain %r" % ([oracle.OP_NAMES[i] for i in sched[b, :, 0, 0]],))
+
+
+def test_autoaugment_and_batch_mode(A, c1_batch):
+    x = np.concatenate([c1_batch[:25], c1_batch[:25]])
+    s = np.zeros((50, 1, 2, 5), np.int32)
+    s[:, 0, :, 0] = np.tile(np.arange(25), 2)[:, None]
+    s[..., 1] = 1
+    s[:25, :, :, 2] = 1
+    layer = A.AutoAugment(elementwise=True)
+    with engine("resident"):
+        y = layer(to_gpu(x), training=True, replay=s).cpu().numpy()
+    want = oracle.apply_schedule(x, policy_of(layer), s, elementwise=True)
+    for b in range(50):
+        assert_same(y[b], want[b], "sub-policy %d" % s[b, 0, 0, 0])
+    for batch_layer in (A.AutoAugment(), A.RandAugment(2, 10)):
+        for call in range(6):
+            with engine("resident"):
+                y = batch_layer(to_gpu(c1_batch), training=True, seed=4, call_counter=call, record=True).cpu().numpy()
+            want = oracle.apply_schedule(c1_batch, policy_of(batch_layer), batch_layer.last_schedule, False)
+            assert_same(y, want, "%s batch mode call %d" % (type(batch_layer).__name__, call))
+
+
+@pytest.mark.parametrize("C,W", [(1, 48), (2, 40), (4, 36)])
+def test_other_channel_counts(A, C, W):
+    x = random_images(80, 30, W, C, seed=C)
+    names = [n for n in oracle.OP_NAMES if n not in ("Color", "Contrast")]
+    layers = [getattr(A, n)(**oracle.magnitude_kwargs(n, 10)) for n in names]
+    choice = A.RandomChoice(layers, 3, elementwise=True)
+    with engine("resident"):
+        y = choice(to_gpu(x), seed=1, call_counter=0, record=True).cpu().numpy()
+    want = oracle.apply_schedule(x, policy_of(choice), choice.last_schedule, elementwise=True)
+    for b in range(x.shape[0]):
+        assert_same(y[b], want[b], "C=%d chain %r" % (C, [names[i] for i in choice.last_schedule[b, :, 0, 0]]))
+
+
+def test_identity_branches_and_single_ops(A):
+    """Constant images (Equalize step == 0, AutoContrast hi == lo), tiny images (fewer than 255 pixels),
+    standalone op layers (batch mode: one sign flip per call, CutOut centres per image)."""
+    for shape, kind in (((3, 224, 224, 3), "constant"), ((4, 9, 16, 3), "uniform"), ((3, 64, 48, 3), "lowentropy"), ((2, 224, 224, 3), "smooth")):
+        x = random_images(*shape, seed=13, kind=kind)
+        if kind == "constant":
+            x[1] = 255 - x[0]
+            x[2] = 0
+        for name in oracle.OP_NAMES:
+            layer = getattr(A, name)(**oracle.magnitude_kwargs(name, 10))
+            for call in range(2):
+                with engine("resident"):
+                    y = layer(to_gpu(x), seed=99, call_counter=call, record=True).cpu().numpy()
+                want = oracle.apply_schedule(x, policy_of(layer), layer.last_schedule, elementwise=False)
+                assert_same(y, want, "%s %s call %d" % (name, kind, call))
+
+
+def test_in_place_sharding_determinism(A):
+    g = torch.Generator().manual_seed(7)
+    x = torch.randint(0, 256, (1500, 224, 224, 3), dtype=torch.uint8, generator=g)
+    xg = x.cuda()
+    for layer in (A.RandAugment(2, 10, elementwise=True), A.AutoAugment(elementwise=True)):
+        with engine("resident"):
+            y = layer(xg, training=True, seed=5, call_counter=1, record=True)
+            sched = layer.last_schedule
+            y2 = layer(xg, training=True, seed=5, call_counter=1)
+            assert torch.equal(y, y2), "two runs of the same call differ"
+            half = layer(xg[700:], training=True, seed=5, call_counter=1, batch_total=1500, image_index_base=700)
+            assert torch.equal(half, y[700:]), "shard differs from the whole batch"
+            t = xg.clone()
+            out = layer._transform(t, seed=5, call_counter=1, out=t)   # d_in == d_out: no temporary on this engine
+            assert out.data_ptr() == t.data_ptr() and torch.equal(t, y)
+            big = torch.empty(1501 * 224 * 224 * 3, dtype=torch.uint8, device="cuda")
+            src = big[: 1500 * 224 * 224 * 3].view(1500, 224, 224, 3)
+            dst = big[224 * 224 * 3:].view(1500, 224, 224, 3)          # partial overlap, one image ahead
+            src.copy_(xg)
+            layer._transform(src, seed=5, call_counter=1, out=dst)
+            assert torch.equal(dst, y)
+        idx = list(range(0, 1500, 97))
+        want = oracle.apply_schedule(x.numpy()[idx], policy_of(layer), sched[idx], elementwise=True)
+        assert_same(y[idx].cpu().numpy(), want, type(layer).__name__ + " sample of 1500")
+
+
+def test_concurrent_streams_and_repeatability(A):
+    x = to_gpu(random_images(400, 224, 224, 3, seed=41))
+    layer = A.RandAugment(3, 10, elementwise=True)
+    with engine("resident"):
+        ref = [layer(x, training=True, seed=2, call_counter=c) for c in range(4)]
+        torch.cuda.synchronize()
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        outs = {}
+        for rep in range(3):
+            for c in range(4):
+                with torch.cuda.stream(s1 if c % 2 == 0 else s2):
+                    outs[c] = layer(x, training=True, seed=2, call_counter=c)
+        torch.cuda.synchronize()
+        for c in range(4):
+            assert torch.equal(outs[c], ref[c]), "call %d differs when run concurrently" % c
+        for rep in range(10):  # back-to-back calls on one stream (programmatic dependent launch, self-cleaned counter)
+            ys = [layer(x, training=True, seed=2, call_counter=c) for c in range(4)]
+            torch.cuda.synchronize()
+            for c in range(4):
+                assert torch.equal(ys[c], ref[c])
