@@ -91,6 +91,9 @@ SIGNATURES = {
     "chb_policy_apply_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChbPolicy), _i64, _i64,
                                    _u64, _u32, _vp, _vp]),
     "chb_set_debug": (_i, [_vp, _i]),
+    "chb_imagenet_normalize": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp]),
+    "chb_resize_min_max_shape": (_i, [_i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "chb_resize": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "chb_set_engine": (_i, [_vp, _i]),
     "chb_last_engine": (_i, [_vp]),
     "chb_debug_timeline": (_i, [_vp, _vp, _i]),
@@ -157,7 +160,18 @@ def set_debug(device, force_generic):
     check(context(device), load().chb_set_debug(context(device), 1 if force_generic else 0))
 
 
+NORM_MODES = {"caffe": 0, "tf": 1, "torch": 2}
 ENGINES = {"auto": 0, "tiles": 1, "resident": 2}
+
+
+def resize_min_max_shape(H, W, min_side, max_side):
+    """(new_height, new_width) of ResizingMinMax (chb_resize_min_max_shape; host arithmetic, no GPU)."""
+    oh, ow = _i(), _i()
+    rc = load().chb_resize_min_max_shape(int(H), int(W), int(min_side or 0), int(max_side or 0),
+                                         ctypes.byref(oh), ctypes.byref(ow))
+    if rc != 0:
+        raise ValueError("Must specify either 'min_side' or 'max_side'.")
+    return oh.value, ow.value
 
 
 def set_engine(device, engine):

@@ -1,5 +1,6 @@
 """Drop-in surface of ``chambers.augmentations`` for the RandAugment / AutoAugment hot path
-(export list of /root/reference/chambers/augmentations/__init__.py:14-39).
+(export list of /root/reference/chambers/augmentations/__init__.py:14-39, including the two chambers
+layers either side of the path, ``ImageNetNormalization`` and ``ResizingMinMax``).
 
 The stock Keras preprocessing re-exports of the reference (``RandomRotation`` ... ``CenterCrop``,
 ``__init__.py:1-13``) are Keras code, not chambers code, and are out of scope.
@@ -28,6 +29,8 @@ from .image_augmentations import (  # noqa: F401
     TranslateX,
     TranslateY,
     CutOut,
+    ImageNetNormalization,
+    ResizingMinMax,
 )
 from .augmentation_schemes import (  # noqa: F401
     AutoAugment,

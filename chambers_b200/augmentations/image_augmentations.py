@@ -384,3 +384,97 @@ class RandomChoice(Layer):
         config = dict(config)
         config["transforms"] = [deserialize(t) for t in config["transforms"]]
         return cls(**config)
+
+
+# ------------------------------------------------------------------ neighbours of the policy path
+def _device_call(inputs, out_dtype_of, out_shape, launch):
+    """Shared plumbing of the two front-end layers: torch CUDA tensors run stream-ordered on their
+    device; numpy / CPU torch inputs are copied to the current device and back (synchronous).  There
+    is no CPU implementation."""
+    import numpy as np
+    from .base import torch
+    if torch is None:
+        raise _lib.ChambersAugError(4, "torch is required as the device-memory provider")
+    is_torch = isinstance(inputs, torch.Tensor)
+    x = inputs if is_torch else torch.from_numpy(np.ascontiguousarray(inputs))
+    if x.dtype not in (torch.uint8, torch.float32):
+        x = x.to(torch.float32)  # the reference casts whatever it is given to float32
+    on_device = x.is_cuda
+    if not on_device:
+        if not torch.cuda.is_available():
+            _lib.context(0)  # raises with the real reason (no device / wrong arch)
+        x = x.cuda(non_blocking=True)
+    x = x.contiguous()
+    dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    out = torch.empty(out_shape, dtype=out_dtype_of(x), device=x.device)
+    with torch.cuda.device(dev):
+        ctx = _lib.context(dev)
+        _lib.check(ctx, launch(ctx, x, out, torch.cuda.current_stream(dev).cuda_stream))
+    if on_device:
+        return out
+    res = out.cpu()
+    return res if is_torch else res.numpy()
+
+
+@register
+class ImageNetNormalization(Layer):
+    """image_augmentations.py:620-682: float32 ImageNet input normalisation, modes "caffe" (RGB->BGR,
+    minus the BGR means), "tf" (x / 127.5 - 1) and "torch" ((x / 255 - mean) / std)."""
+
+    def __init__(self, mode="caffe", name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        if mode not in {"caffe", "tf", "torch"}:
+            raise ValueError("Unknown mode " + str(mode))
+        self.mode = mode
+
+    def call(self, inputs, **kwargs):
+        from .base import torch
+        shape = tuple(int(d) for d in inputs.shape)
+        n = 1
+        for d in shape:
+            n *= d
+        lib = _lib.load()
+
+        def launch(ctx, x, out, stream):
+            return lib.chb_imagenet_normalize(ctx, x.data_ptr(), 1 if x.dtype == torch.float32 else 0, out.data_ptr(),
+                                              n, shape[3], _lib.NORM_MODES[self.mode], stream)
+        return _device_call(inputs, lambda x: torch.float32, shape, launch)
+
+    def get_config(self):
+        return dict(list(super().get_config().items()) + [("mode", self.mode)])
+
+
+@register
+class ResizingMinMax(Layer):
+    """image_augmentations.py:685-748: resize so that the smallest side equals ``min_side`` or the
+    largest equals ``max_side`` (whichever scales down more when both are given), keeping the aspect
+    ratio.  Bilinear output is float32 (tf.image.resize), nearest keeps the input type."""
+
+    def __init__(self, min_side=None, max_side=None, interpolation="bilinear", name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        if min_side is None and max_side is None:
+            raise ValueError("Must specify either 'min_side' or 'max_side'.")
+        self.min_side = min_side
+        self.max_side = max_side
+        self.interpolation = interpolation
+
+    def call(self, inputs, **kwargs):
+        from .base import torch
+        if str(self.interpolation).lower() not in ("bilinear", "nearest"):
+            raise ValueError("Unsupported interpolation %r (bilinear | nearest)" % (self.interpolation,))
+        nearest = str(self.interpolation).lower() == "nearest"
+        B, H, W, C = (int(d) for d in inputs.shape)
+        oh, ow = _lib.resize_min_max_shape(H, W, self.min_side, self.max_side)
+        lib = _lib.load()
+
+        def launch(ctx, x, out, stream):
+            return lib.chb_resize(ctx, x.data_ptr(), 1 if x.dtype == torch.float32 else 0, out.data_ptr(), B, H, W, C,
+                                  oh, ow, 1 if nearest else 0, stream)
+        return _device_call(inputs, (lambda x: x.dtype) if nearest else (lambda x: torch.float32), (B, oh, ow, C), launch)
+
+    def compute_output_shape(self, input_shape):
+        return [input_shape[0], self.min_side, self.max_side, input_shape[3]]  # as the reference states it (:737-738)
+
+    def get_config(self):
+        config = [("min_side", self.min_side), ("max_side", self.max_side), ("interpolation", self.interpolation)]
+        return dict(list(super().get_config().items()) + config)

@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libchambers_aug.so")
 SOURCES = ["chb_kernels_c1.cu", "chb_kernels_c2.cu", "chb_kernels_c3.cu", "chb_kernels_c4.cu",
            "chb_resident_c1.cu", "chb_resident_c2.cu", "chb_resident_c3.cu", "chb_resident_c4.cu",
-           "chb_plan.cu", "chb_launch.cu", "chb_api.cu"]
+           "chb_plan.cu", "chb_launch.cu", "chb_frontend.cu", "chb_api.cu"]
 HEADERS = [os.path.join(CSRC, "chb_internal.h"), os.path.join(CSRC, "chb_kernels.cuh"),
            os.path.join(CSRC, "chb_device.cuh"), os.path.join(CSRC, "chb_resident.cuh"),
            os.path.join(ROOT, "include", "chambers_aug.h")]

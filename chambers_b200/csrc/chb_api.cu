@@ -798,6 +798,60 @@ extern "C" int chb_apply_op(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, i
                        call_counter, d_replay, d_record, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------- neighbours of the policy path
+extern "C" int chb_imagenet_normalize(chb_ctx* ctx, const void* d_in, int in_is_f32, float* d_out, int64_t n_values,
+                                      int C, int mode, void* stream) {
+  if (!ctx) return CHB_ERR_INVALID;
+  if (mode != CHB_NORM_CAFFE && mode != CHB_NORM_TF && mode != CHB_NORM_TORCH)
+    return fail(ctx, CHB_ERR_INVALID, "Unknown mode");  // image_augmentations.py:624-625
+  if (n_values < 0 || C < 1) return fail(ctx, CHB_ERR_INVALID, "negative size");
+  if (mode != CHB_NORM_TF && C != 3)
+    return fail(ctx, CHB_ERR_INVALID, "caffe / torch normalisation broadcast 3-element constants: C must be 3");
+  if (n_values % C) return fail(ctx, CHB_ERR_INVALID, "n_values is not a whole number of pixels");
+  if (n_values == 0) return CHB_OK;
+  if (!d_in || !d_out) return fail(ctx, CHB_ERR_INVALID, "NULL pointer");
+  DeviceGuard guard;
+  CHB_CUDA(ctx, guard.enter(ctx->device));
+  cudaError_t e = chb::launch_normalize(d_in, in_is_f32, d_out, (unsigned long long)n_values, C, mode, ctx->num_sms,
+                                        (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "normalize kernel launch");
+  ctx->launches += 1;
+  return CHB_OK;
+}
+
+extern "C" int chb_resize_min_max_shape(int H, int W, int min_side, int max_side, int* out_h, int* out_w) {
+  if (min_side <= 0 && max_side <= 0) return CHB_ERR_INVALID;  // :704-705
+  const float height = (float)H, width = (float)W;              // :711-712
+  float scale;
+  if (min_side > 0 && max_side > 0) {                           // :714-719
+    const float a = (float)max_side / fmaxf(width, height), b = (float)min_side / fminf(width, height);
+    scale = fminf(a, b);
+  } else if (min_side > 0) {
+    scale = (float)min_side / fminf(width, height);             // :720-723
+  } else {
+    scale = (float)max_side / fmaxf(width, height);             // :724-727
+  }
+  volatile float nh = height * scale, nw = width * scale;       // :729-730, float32 products, truncating casts
+  if (out_h) *out_h = (int)nh;
+  if (out_w) *out_w = (int)nw;
+  return CHB_OK;
+}
+
+extern "C" int chb_resize(chb_ctx* ctx, const void* d_in, int in_is_f32, void* d_out, int B, int H, int W, int C,
+                          int out_h, int out_w, int nearest, void* stream) {
+  if (!ctx) return CHB_ERR_INVALID;
+  if (B < 0 || H < 0 || W < 0 || C < 1 || out_h < 0 || out_w < 0) return fail(ctx, CHB_ERR_INVALID, "negative shape");
+  if ((long long)B * out_h * out_w * C == 0) return CHB_OK;
+  if (H == 0 || W == 0) return fail(ctx, CHB_ERR_INVALID, "cannot resize an empty image");
+  if (!d_in || !d_out) return fail(ctx, CHB_ERR_INVALID, "NULL pointer");
+  DeviceGuard guard;
+  CHB_CUDA(ctx, guard.enter(ctx->device));
+  cudaError_t e = chb::launch_resize(d_in, in_is_f32, d_out, B, H, W, C, out_h, out_w, nearest, ctx->num_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "resize kernel launch");
+  ctx->launches += 1;
+  return CHB_OK;
+}
+
 // ------------------------------------------------------------------------------ e2e pipeline
 static int ensure_staging(chb_ctx* ctx, size_t img_bytes, size_t sched_bytes) {
   for (int i = 0; i < g_pipe; ++i)

@@ -135,6 +135,11 @@ int pass_ctas_per_sm(int C);
 // Image-resident engine (chb_resident.cuh): one CTA per SM, the whole image in shared memory.
 cudaError_t launch_resident(const KParams& p, int C, int grid, cudaStream_t stream);
 cudaError_t configure_resident(int smem_bytes);
+// The layers either side of the policy path (chb_frontend.cu).
+cudaError_t launch_normalize(const void* in, int in_is_f32, float* out, unsigned long long n, int C, int mode, int num_sms,
+                             cudaStream_t stream);
+cudaError_t launch_resize(const void* in, int in_is_f32, void* out, int B, int IH, int IW, int C, int OH, int OW, int nearest,
+                          int num_sms, cudaStream_t stream);
 size_t resident_ctl_bytes();  // shared memory in front of the image buffer
 int resident_max_chunk_bytes();
 

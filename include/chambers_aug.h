@@ -169,6 +169,26 @@ int chb_policy_apply_host(chb_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, int
  * the vectorised ones (same results, used by the tests to cross-check the two on the device). */
 int chb_set_debug(chb_ctx* ctx, int force_generic);
 
+/* ImageNetNormalization(mode)(x), image_augmentations.py:620-682 -- the layer every chambers backbone
+ * applies right after the augmentation policy (vision_transformer.py:655).  d_in: NHWC uint8
+ * (in_is_f32 == 0) or float32 (in_is_f32 != 0) with n_values = B*H*W*C elements; d_out: float32 of the
+ * same shape.  tf: x / 127.5 - 1 (:660-665); torch: (x / 255 - mean) / std per channel (:652-657);
+ * caffe: channels reversed (RGB -> BGR), minus the BGR means (:647-650).  torch / caffe need C == 3
+ * (the reference broadcasts 3-element constants).  Checked against the reference's own golden
+ * vectors (test_units/augmentations/test_image_augmentations.py:21-64). */
+enum chb_norm_mode { CHB_NORM_CAFFE = 0, CHB_NORM_TF = 1, CHB_NORM_TORCH = 2 };
+int chb_imagenet_normalize(chb_ctx* ctx, const void* d_in, int in_is_f32, float* d_out, int64_t n_values, int C,
+                           int mode, void* stream);
+
+/* ResizingMinMax(min_side, max_side, interpolation)(x), image_augmentations.py:685-748.
+ * chb_resize_min_max_shape is the size arithmetic of :711-730 (float32 scale, truncating casts);
+ * min_side / max_side <= 0 mean None; returns CHB_ERR_INVALID if both are.  chb_resize is the
+ * tf.image.resize call behind Keras' Resizing (:732-735): bilinear (float32 output whatever the
+ * input) or nearest (output of the input's type), half-pixel centres, no antialiasing. */
+int chb_resize_min_max_shape(int H, int W, int min_side, int max_side, int* out_h, int* out_w);
+int chb_resize(chb_ctx* ctx, const void* d_in, int in_is_f32, void* d_out, int B, int H, int W, int C, int out_h,
+               int out_w, int nearest, void* stream);
+
 /* Engine selection.  The library holds two engines with identical results:
  *   CHB_ENGINE_RESIDENT  one CTA per SM keeps a whole image in shared memory for its entire op chain
  *                        (images of up to ~190 KB whose rows are whole 16-byte units, nearest /

@@ -34,3 +34,6 @@ from . import switches  # noqa: F401
 from .ops import *  # noqa: F401,F403
 from .policy import *  # noqa: F401,F403
 from .philox import *  # noqa: F401,F403
+from .frontend import (  # noqa: F401
+    imagenet_normalization, resizing_min_max, resizing_min_max_shape, resize_bilinear, resize_nearest,
+)

@@ -103,12 +103,55 @@ def test_c_autoaugment_table_matches_python_layers(lib):
 
 def test_export_list_matches_reference():
     from chambers_b200 import augmentations as A
-    # chambers/augmentations/__init__.py:14-39 minus the two non-policy layers (next rows)
+    # every chambers-owned name of chambers/augmentations/__init__.py:14-39 (the Keras re-exports of
+    # :1-13 are Keras code); ImageNetNormalization and ResizingMinMax included
     names = ["RandomChoice", "RandomChance", "AutoContrast", "Equalize", "Invert", "Rotate", "Posterize",
              "Solarize", "SolarizeAdd", "Color", "Contrast", "Brightness", "Sharpness", "ShearX", "ShearY",
-             "TranslateX", "TranslateY", "CutOut", "AutoAugment", "RandAugment"]
+             "TranslateX", "TranslateY", "CutOut", "AutoAugment", "RandAugment", "ImageNetNormalization",
+             "ResizingMinMax"]
     for n in names:
         assert hasattr(A, n), n
+    import os
+    ref_init = "/root/reference/chambers/augmentations/__init__.py"
+    if os.path.exists(ref_init):  # in the build container: the list above is the reference's own
+        import ast
+        tree = ast.parse(open(ref_init).read())
+        ours = set()
+        for node in tree.body:
+            if isinstance(node, ast.ImportFrom) and node.module in ("image_augmentations", "augmentation_schemes") and node.level == 1:
+                ours.update(a.name for a in node.names)
+        assert ours == set(names), ours ^ set(names)
+
+
+def test_frontend_layers_host_logic():
+    """ImageNetNormalization / ResizingMinMax: constructor errors, configs, and the resize size
+    arithmetic of the C ABI (host code, no GPU) against the reference's four shape tests
+    (test_units/augmentations/test_image_augmentations.py:66-80) and the oracle."""
+    import json
+    from chambers_b200 import augmentations as A, _lib
+    with pytest.raises(ValueError):
+        A.ImageNetNormalization(mode="keras")
+    with pytest.raises(ValueError):
+        A.ResizingMinMax()
+    n = A.ImageNetNormalization()
+    assert n.mode == "caffe" and n.get_config() == {"name": n.name, "mode": "caffe"}
+    r = A.ResizingMinMax(min_side=100, max_side=50, interpolation="nearest")
+    assert r.get_config() == {"name": r.name, "min_side": 100, "max_side": 50, "interpolation": "nearest"}
+    assert A.deserialize(A.serialize(r)).get_config()["max_side"] == 50
+    assert r.compute_output_shape([8, 4, 3, 3]) == [8, 100, 50, 3]
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "imagenet_norm_ref.json")))
+    for name, case in ref["shapes"].items():
+        _, H, W, C = case["input_shape"]
+        kw = case["kwargs"]
+        got = _lib.resize_min_max_shape(H, W, kw.get("min_side"), kw.get("max_side"))
+        assert list(got) == case["output_shape"][1:3], (name, got)
+        assert oracle.resizing_min_max_shape(H, W, **kw) == got
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        H, W = (int(v) for v in rng.integers(1, 3000, size=2))
+        mn = int(rng.integers(1, 1200)) if rng.random() < 0.7 else None
+        mx = int(rng.integers(1, 1200)) if (mn is None or rng.random() < 0.6) else None
+        assert _lib.resize_min_max_shape(H, W, mn, mx) == oracle.resizing_min_max_shape(H, W, mn, mx), (H, W, mn, mx)
 
 
 def test_constructors_and_configs():

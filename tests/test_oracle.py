@@ -222,3 +222,42 @@ def test_apply_schedule_modes(c1_batch):
     # elementwise result of image b depends only on image b
     y1 = oracle.apply_schedule(x[2:3], pol, s[2:3], elementwise=True)
     assert (y1[0] == y[2]).all()
+
+
+def test_imagenet_normalization_matches_the_reference_golden_vectors():
+    """PINNED: the reference's own float32 golden vectors (test_units/augmentations/
+    test_image_augmentations.py:21-64, extracted by tests/golden/make_imagenet_norm_fixture.py),
+    asserted with exact equality exactly as the reference's tests do (assertAllEqual)."""
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "imagenet_norm_ref.json")))
+    img = np.array(ref["image"], dtype=np.uint8)
+    x = np.stack([img, img, img], axis=-1)[None]          # IMG, :14-15
+    for mode in ("caffe", "tf", "torch"):
+        got = oracle.imagenet_normalization(x, mode)
+        assert got.dtype == np.float32 and got.shape == x.shape
+        target = np.array(ref["targets"][mode], dtype=np.float32)
+        assert np.array_equal(got[0, ..., 0], target), mode
+    # caffe reverses the channels before subtracting the BGR means
+    y = np.arange(2 * 3 * 5 * 3, dtype=np.uint8).reshape(2, 3, 5, 3)
+    c = oracle.imagenet_normalization(y, "caffe")
+    assert np.array_equal(c[..., 0], y[..., 2].astype(np.float32) - np.float32(103.939))
+    assert np.array_equal(c[..., 2], y[..., 0].astype(np.float32) - np.float32(123.68))
+    with pytest.raises(ValueError):
+        oracle.imagenet_normalization(y, "keras")
+
+
+def test_resizing_min_max_shapes_match_the_reference_tests():
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "imagenet_norm_ref.json")))
+    for name, case in ref["shapes"].items():
+        x = np.zeros(case["input_shape"], np.uint8)
+        out = oracle.resizing_min_max(x, **case["kwargs"])
+        assert list(out.shape) == case["output_shape"], name
+        assert out.dtype == np.float32
+    # identity-size bilinear resize reproduces the input; nearest picks existing pixels
+    x = np.random.default_rng(1).integers(0, 256, size=(2, 7, 9, 3), dtype=np.uint8)
+    assert np.array_equal(oracle.resize_bilinear(x, 7, 9), x.astype(np.float32))
+    n = oracle.resize_nearest(x, 14, 18)
+    assert n.dtype == np.uint8 and np.array_equal(n[:, ::2, ::2], x)
