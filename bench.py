@@ -52,41 +52,64 @@ def parse():
     ap.add_argument("--policy", default="randaugment", choices=["randaugment", "autoaugment"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="--batch is the WHOLE batch, sharded over --gpus ranks (BASELINE.json configs[2]: "
+                         "--policy autoaugment --batch 4096 --strong); prints a position-weighted checksum of the "
+                         "output that is the same for every GPU count iff the pixels are")
     return ap.parse_args()
 
 
+def n_pool_for(batch):
+    return max(2, POOL_BYTES // (2 * batch * H * W * C))
+
+
+def host_batch(batch, rank=0):
+    """The bytes every arm consumes: i.i.d. uniform uint8 from torch's CPU generator (seed SEED + rank).
+    Step i reads this batch rolled by (i % n_pool) images -- the native arm's buffer pool."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(SEED + rank)
+    return torch.randint(0, 256, (batch, H, W, C), dtype=torch.uint8, generator=g)
+
+
 # ----------------------------------------------------------------------------- CPU baseline
+_WORKER_BATCH = {}
+
+
 def _cpu_worker(job):
+    """One shard of one step on one host core: the oracle port on the native arm's exact bytes
+    (host_batch, rolled like the native arm's pool) and the schedule the device decodes for the
+    same (seed, call counter, global image index)."""
     import numpy as np
     import oracle
-    seed, start, n, policy_name, elementwise, batch_total = job
-    rng = np.random.default_rng(seed + start)
-    x = rng.integers(0, 256, size=(n, H, W, C), dtype=np.uint8)
+    step, start, n, policy_name, elementwise, batch = job
+    if batch not in _WORKER_BATCH:
+        _WORKER_BATCH[batch] = host_batch(batch).numpy()
+    base = _WORKER_BATCH[batch]
+    idx = (np.arange(start, start + n) - (step % n_pool_for(batch))) % batch  # torch.roll(shift, 0): out[i] = in[i - shift]
+    x = base[idx]
     pol = oracle.randaugment_policy(N_TRANSFORMS, MAGNITUDE) if policy_name == "randaugment" else oracle.autoaugment_policy()
-    sched = oracle.decode_schedule(pol, SEED, 0, start, n, H, W, bool(elementwise))
+    sched = oracle.decode_schedule(pol, SEED, step, start, n, H, W, bool(elementwise))
     t0 = time.perf_counter()
-    if elementwise:
-        oracle.apply_schedule(x, pol, sched, True)
-    else:
-        # batch mode shares one schedule row; Contrast's constant needs the whole batch size, which
-        # the oracle derives from the array it is given -- fine for a throughput baseline.
-        oracle.apply_schedule(x, pol, sched, False)
+    # (batch mode: Contrast's constant needs the whole batch size, which the oracle derives from the
+    # array it is given -- a shard sees its own size; fine for a throughput baseline)
+    oracle.apply_schedule(x, pol, sched, bool(elementwise))
     return n, time.perf_counter() - t0
 
 
 def cpu_port_throughput(batch, policy_name, elementwise, min_seconds=8.0, max_batches=64):
-    """images/s of the oracle port over all host cores (process pool over batch shards)."""
+    """images/s of the oracle port over all host cores (process pool over batch shards), whole batches
+    of the native arm's bytes."""
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
     ctx = mp.get_context("spawn")
     done = 0
     steps = []
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(1, 0, 1, policy_name, elementwise, batch)] * cores)  # warm the workers
+        pool.map(_cpu_worker, [(0, 0, 1, policy_name, elementwise, batch)] * cores)  # warm the workers (imports, the batch)
         t_start = time.perf_counter()
         for step in range(max_batches):
             per = (batch + cores - 1) // cores
-            jobs = [(SEED, s, min(per, batch - s), policy_name, elementwise, batch) for s in range(0, batch, per)]
+            jobs = [(step, s, min(per, batch - s), policy_name, elementwise, batch) for s in range(0, batch, per)]
             t0 = time.perf_counter()
             pool.map(_cpu_worker, jobs)
             steps.append(time.perf_counter() - t0)
@@ -167,13 +190,16 @@ class ClockSampler:
 
 def measured_traffic(args):
     """DRAM bytes (read + write) of one step, from an `ncu` capture of this command (tools/gpu_traffic.sh);
-    None if no capture of this workload is committed."""
-    try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        key = "%s_b%d" % (args.policy, args.batch)
-        return rec[key]["dram_bytes_per_step"]
-    except Exception:
-        return None
+    (None, None) if no capture of this workload is committed.  The second value is the record itself:
+    it says how much of the written output had left L2 inside the kernels' duration."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            rec = json.load(open(os.path.join(ROOT, "profiles", name)))
+            key = "%s_b%d" % (args.policy, args.batch)
+            return rec[key]["dram_bytes_per_step"], dict(rec[key], source="profiles/" + name)
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_peak():
@@ -188,48 +214,64 @@ def measured_peak():
 
 # ------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank):
+    """The reference arm: the reference's CPU implementation of the path on this box's host cores.
+    TensorFlow 2.6 / tensorflow-addons cannot be installed here, so this is the oracle
+    port (numpy restatement, kind "port"), on the native arm's exact bytes, the whole batch per step."""
     if rank != 0:
         return
     per_step = []
     cores = len(os.sched_getaffinity(0))
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
-    sample = min(args.batch, max(8 * cores, 64))  # images per step: a bounded sample of the 256-image batch
+    batch = args.batch
     with ctx.Pool(cores) as pool:
-        per = (sample + cores - 1) // cores
-        jobs = [(SEED, s, min(per, sample - s), args.policy, args.elementwise, args.batch) for s in range(0, sample, per)]
-        for _ in range(max(args.warmup, 1)):
-            pool.map(_cpu_worker, jobs)
+        per = (batch + cores - 1) // cores
+        pool.map(_cpu_worker, [(0, 0, 1, args.policy, args.elementwise, batch)] * cores)
+        for w in range(max(args.warmup, 1)):
+            pool.map(_cpu_worker, [(w, s, min(per, batch - s), args.policy, args.elementwise, batch) for s in range(0, batch, per)])
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for i in range(args.steps):
             t1 = time.perf_counter()
+            jobs = [(args.warmup + i, s, min(per, batch - s), args.policy, args.elementwise, batch) for s in range(0, batch, per)]
             pool.map(_cpu_worker, jobs)
             per_step.append(time.perf_counter() - t1)
         total = time.perf_counter() - t0
-    value = sample * args.steps / total
+    value = batch * args.steps / total
     line = {
         "impl": "reference", "metric": "augmented images/sec", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args, sample_note="each step = a %d-image sample of the batch" % sample),
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "%d steps x %d images of the workload batch; numpy restatement of the reference "
-                                   "(TensorFlow 2.6 / tensorflow-addons are not installable here), process pool over "
-                                   "all host cores" % (args.steps, sample)},
+                         "sample": "%d steps x the whole %d-image batch (the native arm's bytes and schedules); numpy "
+                                   "restatement of the reference (TensorFlow 2.6 / tensorflow-addons are not installable "
+                                   "here), process pool over all host cores" % (args.steps, batch)},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+def workload_name(args):
+    pol = "RandAugment(N=%d,M=%d)" % (N_TRANSFORMS, MAGNITUDE) if args.policy == "randaugment" else "AutoAugment(V0)"
+    mode = "elementwise" if args.elementwise else "batchwise"
+    cfg = ""
+    if args.policy == "randaugment" and args.batch == 256 and not args.strong:
+        cfg = " (BASELINE.json configs[1])"
+    elif args.policy == "autoaugment" and args.batch == 4096 and args.strong:
+        cfg = " (BASELINE.json configs[2])"
+    per = "whole batch, sharded over the GPUs" if args.strong else "per GPU"
+    return "%s %s on %dx%dx%dx%d uint8 %s%s" % (pol, mode, args.batch, H, W, C, per, cfg)
+
+
 def workload_config(args, sample_note=None):
+    world = max(args.gpus, 1)
+    per_gpu = (args.batch + world - 1) // world if args.strong else args.batch
     cfg = {
-        "workload": "%s %s on %dx%dx%dx%d uint8 per GPU (BASELINE.json configs[1])" % (
-            "RandAugment(N=%d,M=%d)" % (N_TRANSFORMS, MAGNITUDE) if args.policy == "randaugment" else "AutoAugment(V0)",
-            "elementwise" if args.elementwise else "batchwise", args.batch, H, W, C),
-        "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus, "image": [H, W, C],
-        "elementwise": bool(args.elementwise), "parallelism": "batch-sharded x%d, no collective" % args.gpus,
+        "workload": workload_name(args),
+        "batch_per_gpu": per_gpu, "global_batch": args.batch if args.strong else args.batch * world, "image": [H, W, C],
+        "elementwise": bool(args.elementwise), "parallelism": "batch-sharded x%d, no collective" % world,
         "l2": "in/out buffers rotate through a %d MiB pool per GPU (> 126 MB L2)" % (POOL_BYTES >> 20),
-        "input": "i.i.d. uniform uint8, torch.Generator seed 0",
+        "input": "i.i.d. uniform uint8, torch CPU generator seed %d (+ rank); step i reads the batch rolled by i %% pool images" % SEED,
     }
     if sample_note:
         cfg["sample"] = sample_note
@@ -252,11 +294,24 @@ def run_native(args, rank, local_rank, world):
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch
+    from chambers_b200.sharding import shard_bounds
     img_bytes = H * W * C
-    n_pool = max(2, POOL_BYTES // (2 * B * img_bytes))
-    g = torch.Generator(device="cpu").manual_seed(SEED + rank)
-    host_pool = torch.randint(0, 256, (B, H, W, C), dtype=torch.uint8, generator=g).pin_memory()
+    if args.strong:
+        # BASELINE.json configs[2]: ONE fixed batch, rank r augments its contiguous slice; the schedule RNG is
+        # keyed by the global image index, so the concatenated output does not depend on the GPU count
+        total = args.batch
+        start, stop = shard_bounds(total, rank, world)
+        whole = host_batch(total)
+        host_pool = whole[start:stop].contiguous().pin_memory()
+        B = stop - start
+        skw = shard_kwargs(total, rank, world)
+    else:
+        B = args.batch
+        total = B * world
+        start = rank * B
+        host_pool = host_batch(B, rank).pin_memory()
+        skw = shard_kwargs(total, rank, world)
+    n_pool = n_pool_for(max(B, 1))
     ins = []
     for i in range(n_pool):
         t = host_pool.to(dev, non_blocking=True)
@@ -269,7 +324,6 @@ def run_native(args, rank, local_rank, world):
     else:
         layer = A.AutoAugment(elementwise=bool(args.elementwise))
     choice = layer._transform
-    skw = shard_kwargs(B * world, rank, world)
 
     def step(i):
         choice(ins[i % n_pool], seed=SEED, call_counter=i, out=outs[i % n_pool], **skw)
@@ -295,6 +349,7 @@ def run_native(args, rank, local_rank, world):
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = _lib.kernel_launches(local_rank) - launches0
+    engine = _lib.last_engine(local_rank)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -317,31 +372,51 @@ def run_native(args, rank, local_rank, world):
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * e2e_steps / float(tt), "unit": "images/s",
+        e2e = {"value": total * e2e_steps / float(tt), "unit": "images/s",
                "h2d_bytes_per_step": B * img_bytes, "d2h_bytes_per_step": B * img_bytes,
                "steps": e2e_steps, "api": "RandomChoice.__call__(pinned host tensor) -> chb_policy_apply_host"}
 
+    # position-weighted checksum of the whole job's output for call 0 (strong scaling: equal for every GPU count
+    # iff the concatenated pixels are equal)
+    checksum = None
+    if args.strong:
+        out0 = choice(ins[0], seed=SEED, call_counter=0, **skw).view(-1).to(torch.int64)
+        idx = torch.arange(out0.numel(), device=dev, dtype=torch.int64) + start * img_bytes
+        part = torch.stack([(out0 * (idx % 65521 + 1)).sum(), out0.sum()])
+        if world > 1:
+            dist.all_reduce(part)
+        checksum = "%016x-%x" % (int(part[0]) & ((1 << 64) - 1), int(part[1]))
+
     if rank != 0:
         return
-    value = world * B * args.steps / (elapsed_ms * 1e-3)
+    value = total * args.steps / (elapsed_ms * 1e-3)
     ms_per_step = elapsed_ms / args.steps
     peak, peak_src = measured_peak()
-    alg_bytes = 2.0 * B * img_bytes  # per launch: one read + one write of every image
+    alg_bytes = 2.0 * B * img_bytes  # per launch on one GPU: one read + one write of every image
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic, traffic_rec = measured_traffic(args)
+    kernel = ("chb::resident_kernel<3> (one launch per step: schedule decode, chain walk and every pass of an image "
+              "on one CTA)" if engine == "resident" else "chb::plan_kernel + chb::pass_kernel<3> (one step)")
     line = {
         "metric": "augmented images/sec", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args),
         "clocks": clocks,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": measured_traffic(args), "peak_source": peak_src,
-                     "kernel": "chb::plan_kernel + chb::pass_kernel<3> (one step)",
+                     "traffic": traffic, "traffic_record": traffic_rec, "peak_source": peak_src,
+                     "kernel": kernel, "engine": engine,
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "frac_of_spec_8TBs": achieved / 8000.0},
+                     "frac_of_spec_8TBs": achieved / 8000.0,
+                     "note": "a 256-image step moves 77 MB, less than the 126 MB L2: the input pool rotation makes every "
+                             "read an HBM read, but part of a step's output is still in L2 when its kernel ends "
+                             "(traffic_record.write vs algorithmic_bytes / 2), so at this batch the figure is an "
+                             "HBM-read + L2-write roofline; the 4096 / 8192-image sweeps (profiles/) are pure HBM"},
         "e2e": e2e,
     }
+    if checksum is not None:
+        line["output_checksum_call0"] = checksum
     if world == 1 and not args.no_cpu_baseline:
         v, cores, n_done, _ = cpu_port_throughput(B, args.policy, args.elementwise)
         line["cpu_baseline"] = {

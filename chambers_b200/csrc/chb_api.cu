@@ -601,7 +601,8 @@ static bool resident_eligible(const chb_ctx* ctx, const PolicyEntry* pe, const u
   if ((row & 15) != 0 || img_bytes == 0) return false;
   if ((((uintptr_t)d_in) & 15) != 0 || (((uintptr_t)d_out) & 15) != 0) return false;
   if (img_bytes > (size_t)chb::resident_max_chunk_bytes()) return false;
-  const size_t fixed = chb::resident_ctl_bytes() + (img_bytes + 127) / 128 * 128;
+  const size_t fixed = chb::resident_ctl_bytes() + (pe->host.size() * (sizeof(DevOp) + 256) + 127) / 128 * 128 +
+                       (img_bytes + 127) / 128 * 128;
   if (fixed > (size_t)ctx->res_smem) return false;
   const size_t aux = (size_t)ctx->res_smem - fixed;
   const size_t hist_copy = (size_t)C * 1024 + 16;

@@ -44,6 +44,13 @@
 namespace chb {
 namespace {
 
+// Loads of the policy table (DevOp / value maps).  The tile engine reads them from global memory
+// through the read-only path; the resident engine (chb_resident.cuh) stages the table in shared
+// memory and defines CHB_LDP as a plain load before including this file.
+#ifndef CHB_LDP
+#define CHB_LDP(ptr) __ldg(ptr)
+#endif
+
 constexpr int NCONS = 256;                       // consumer threads of a pass CTA (8 warps)
 constexpr int NT = NCONS + 32;                   // + one producer warp
 constexpr int PLAN_NT = 128;                     // threads per plan CTA
@@ -307,18 +314,18 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
       break;
     }
     const DevOp* op = p.ops + pe.table_index;
-    const int kind = __ldg(&op->kind);
+    const int kind = CHB_LDP(&op->kind);
     const bool frozen = (kmode == K_SHARP || kmode == K_BILINEAR);  // K has consumed the spatial list
     uint8_t(*last_lut)[256] = (kmode == K_NONE) ? s->t.l1 : s->t.l2;
     bool boundary = false;
 
     if (is_pointwise(kind)) {
       const uint8_t* tab = p.optab + (size_t)pe.table_index * 256;
-      for (int t = tid; t < C * 256; t += nt) last_lut[t >> 8][t & 255] = __ldg(tab + last_lut[t >> 8][t & 255]);
+      for (int t = tid; t < C * 256; t += nt) last_lut[t >> 8][t & 255] = CHB_LDP(tab + last_lut[t >> 8][t & 255]);
       if (!frozen)
         for (int t = tid; t < n_sp * C; t += nt) {
           const int k = t / C, c = t - k * C;
-          s->t.sp[k].color[c] = __ldg(tab + s->t.sp[k].color[c]);
+          s->t.sp[k].color[c] = CHB_LDP(tab + s->t.sp[k].color[c]);
         }
       if (tid == 0) {
         if (kmode == K_NONE) s->t.l1_id = 0; else s->t.l2_id = 0;
@@ -359,11 +366,11 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
         s->next_op = pi + 1;
       }
     } else if (kind == CHB_OP_COLOR) {
-      const int mode = __ldg(&op->blend_mode);
+      const int mode = CHB_LDP(&op->blend_mode);
       if (mode == BLEND_IMAGE2 || C != 3) {  // factor 1: blend returns the image itself (:30-31)
         if (tid == 0) s->next_op = pi + 1;
       } else if (kmode == K_NONE) {
-        const float f = (mode == BLEND_IMAGE1) ? 0.0f : __ldg(&op->factor);
+        const float f = (mode == BLEND_IMAGE1) ? 0.0f : CHB_LDP(&op->factor);
         if (tid < n_sp) {  // spatial colours are pixels too
           int* col = s->t.sp[tid].color;
           uint32_t R, G, B;
@@ -375,13 +382,13 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
         boundary = true;
       }
     } else if (kind == CHB_OP_SHARPNESS) {
-      const int mode = __ldg(&op->blend_mode);
+      const int mode = CHB_LDP(&op->blend_mode);
       if (mode == BLEND_IMAGE2) {
         if (tid == 0) s->next_op = pi + 1;
       } else if (kmode == K_NONE) {
         if (tid == 0) {
           s->t.kmode = K_SHARP;
-          s->t.kfactor = (mode == BLEND_IMAGE1) ? 0.0f : __ldg(&op->factor);  // factor 0: deg exactly
+          s->t.kfactor = (mode == BLEND_IMAGE1) ? 0.0f : CHB_LDP(&op->factor);  // factor 0: deg exactly
           s->hist_valid = 0; s->next_op = pi + 1;
         }
       } else {
@@ -392,7 +399,7 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
         boundary = true;
       } else if (tid == 0) {
         // tfa.image.random_cutout: rows [cy-h, cy+h) x cols [cx-h, cx+h), clipped (oracle/ops.py cutout)
-        const int h = __ldg(&op->ip0), colr = __ldg(&op->ip1);
+        const int h = CHB_LDP(&op->ip0), colr = CHB_LDP(&op->ip1);
         Spatial& e = s->t.sp[n_sp];
         e.type = SP_MASK; e.fill_mode = CHB_FILL_CONSTANT;
         e.y0 = max(0, pe.cy - h); e.y1 = min(H, pe.cy + h);
@@ -403,14 +410,14 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
     } else if (kind == CHB_OP_SHEAR_X || kind == CHB_OP_SHEAR_Y || kind == CHB_OP_TRANSLATE_X ||
                kind == CHB_OP_TRANSLATE_Y || kind == CHB_OP_ROTATE) {
       const float* tsrc = op->coef[pe.negate ? 1 : 0];
-      const int fill_mode = __ldg(&op->fill_mode), fill = __ldg(&op->fill_u8);
-      if (__ldg(&op->interp) == CHB_INTERP_NEAREST) {
+      const int fill_mode = CHB_LDP(&op->fill_mode), fill = CHB_LDP(&op->fill_u8);
+      if (CHB_LDP(&op->interp) == CHB_INTERP_NEAREST) {
         if (frozen) {
           boundary = true;
         } else if (tid == 0) {
           Spatial& e = s->t.sp[n_sp];
           e.type = SP_GEOM; e.fill_mode = fill_mode;
-          for (int q = 0; q < 8; ++q) e.t[q] = __ldg(tsrc + q);
+          for (int q = 0; q < 8; ++q) e.t[q] = CHB_LDP(tsrc + q);
           for (int c = 0; c < MAXC; ++c) e.color[c] = fill;
           if (fill_mode != CHB_FILL_CONSTANT) s->t.sp_fast = 0;
           s->t.n_sp = n_sp + 1; s->hist_valid = 0; s->next_op = pi + 1;
@@ -422,7 +429,7 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
         } else if (tid == 0) {
           Spatial& e = s->t.kgeo;
           e.type = SP_GEOM; e.fill_mode = fill_mode;
-          for (int q = 0; q < 8; ++q) e.t[q] = __ldg(tsrc + q);
+          for (int q = 0; q < 8; ++q) e.t[q] = CHB_LDP(tsrc + q);
           for (int c = 0; c < MAXC; ++c) e.color[c] = fill;
           s->t.kmode = K_BILINEAR; s->hist_valid = 0; s->next_op = pi + 1;
         }
@@ -498,7 +505,7 @@ __device__ void decode_image(const KParams& p, ImgState* s, uint32_t (*rnd)[4], 
       }
       for (int j = 0; j < p.K; ++j) {
         const int opi = choice * p.K + j;
-        const int kind = __ldg(&p.ops[opi].kind);
+        const int kind = CHB_LDP(&p.ops[opi].kind);
         int applied, negate, cy, cx;
         if (p.replay) {
           const int32_t* r = p.replay + rbase + (size_t)j * CHB_SCHED_FIELDS;
@@ -508,7 +515,7 @@ __device__ void decode_image(const KParams& p, ImgState* s, uint32_t (*rnd)[4], 
           cx = r[4];
         } else {
           const int slot = slot0 + 1 + j;
-          applied = (kind >= 0) && ((int)(rnd[slot][0] >> 8) < __ldg(&p.ops[opi].thr24));
+          applied = (kind >= 0) && ((int)(rnd[slot][0] >> 8) < CHB_LDP(&p.ops[opi].thr24));
           negate = rnd[slot][1] < 0x80000000u;
           cy = (int)__umulhi(rndc[slot][2], (uint32_t)H);
           cx = (int)__umulhi(rndc[slot][3], (uint32_t)W);

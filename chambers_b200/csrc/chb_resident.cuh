@@ -24,6 +24,8 @@
 // rows are whole 16-byte units, every geometric op is nearest / constant-fill (what the policies
 // use, augmentation_schemes.py:7-9).  Everything else stays on the tile engine (chb_kernels.cuh).
 #pragma once
+// the policy table is staged in shared memory: plain loads (see chb_kernels.cuh)
+#define CHB_LDP(ptr) (*(ptr))
 #include "chb_kernels.cuh"
 
 namespace chb {
@@ -36,12 +38,17 @@ constexpr int RES_MIN_AUX = 16 * 1024;
 
 struct alignas(128) ResCtl {
   unsigned long long full[RES_MAXCHUNK];
-  int32_t next_img, n_claimed, _p1, _p2;
+  int32_t next_img, n_claimed, n_prefetched, _p2;
+  // work splits that depend only on the shape (computed once per launch by thread 0)
+  int32_t sharp_rows;                  // res_sharp: rows per sub-strip
+  int32_t gs_band[2], gs_rows[2];      // res_gather_sharp, WRITE / COUNT: output rows per band, rows per sub-strip
+  int32_t _p4[3];
   uint32_t fillc[2];                   // colour bytes of the last / last-but-one spatial entry ("a miss is just another address")
   uint32_t _p3[2];
   uint32_t rnd[32][4], rndc[32][4];
   uint32_t hmap[MAXC * 256];
   uint8_t etab[MAXC * 256];
+  KParams kp;                          // the launch parameters with ops / optab pointing at the shared-memory copy
   ImgState st;
 };
 
@@ -58,31 +65,44 @@ struct RC {
   uint8_t* dst;        // global destination of a WRITE pass
   int H, W, row, img_bytes, tid, lane;
   uint32_t l1a, l2a;   // shared addresses of the two LUTs
-  uint32_t hcopy;      // this lane's histogram copy
-  int ncopy;
+  uint32_t hcopy;      // shared address of this lane's histogram copy (word 0)
+  int ncopy;           // histogram copies: 32, 16, 8 or 4
+  uint32_t hshift;     // log2(ncopy * 4): byte shift of a counter-pair row
 };
 
+// Histogram of a COUNT pass: `ncopy` copies of packed 16-bit counters in the aux region, copy =
+// lane & (ncopy - 1).  Counter of (channel ch, value v) in copy k: half (v & 1) of the 32-bit word
+//     ((ch * 128 + (v >> 1)) * ncopy + k)
+// so with ncopy == 32 every lane of a warp owns one shared-memory bank: a red.shared of 32 random
+// values is ONE conflict-free wavefront (the 8 skewed u32 copies of the first version averaged 3.5:
+// profiles/r02_v1_ncu_op_Equalize.txt, 52 % of the wavefronts were bank conflicts and mio_throttle
+// was the top stall).  A copy counts at most (pixels / ncopy) * (32 / 32) ... <= 4 x 6656 values for
+// ncopy >= 4 (images of <= 192 KB), so 16 bits never overflow.  ncopy = 32 needs C x 16 KB.
 template <int C>
-__host__ __device__ constexpr uint32_t hc_copy_bytes() { return (uint32_t)C * 1024u + 16u; }
+__host__ __device__ constexpr uint32_t hist_bytes(int ncopy) { return (uint32_t)C * 512u * (uint32_t)ncopy; }
 
-// Histogram copies in the aux region: copy = lane & (ncopy - 1), skewed by four banks each.
 template <int C>
 __device__ __forceinline__ void hist_zero(const RC<C>& c) {
-  const uint32_t n = (uint32_t)c.ncopy * hc_copy_bytes<C>();
+  const uint32_t n = hist_bytes<C>(c.ncopy);
   for (uint32_t i = (uint32_t)c.tid * 16u; i < n; i += RNT * 16u) sts_v4(c.aux + i, make_uint4(0u, 0u, 0u, 0u));
   __syncthreads();
 }
 template <int C>
-__device__ __forceinline__ void hist_add(const RC<C>& c, int ch, uint32_t v) {
-  reds_add(c.hcopy + (uint32_t)ch * 1024u + ((v & 255u) << 2), 1u);
+__device__ __forceinline__ void hist_add(const RC<C>& c, int ch, uint32_t v) {  // v: a zero-extended byte
+  reds_add(c.hcopy + (((uint32_t)ch * 128u + (v >> 1)) << c.hshift), 1u + (v & 1u) * 0xFFFFu);
 }
 // Sums the copies into st.hist (which advance() zeroed when it asked for the COUNT pass).
 template <int C>
 __device__ __forceinline__ void hist_reduce(const RC<C>& c) {
   __syncthreads();
   for (int i = c.tid; i < C * 256; i += RNT) {
+    const uint32_t rowa = c.aux + ((uint32_t)(i >> 1) << c.hshift);
+    const uint32_t sh = (uint32_t)(i & 1) * 16u;
     uint32_t sum = 0;
-    for (int k = 0; k < c.ncopy; ++k) sum += lds_u32(c.aux + (uint32_t)k * hc_copy_bytes<C>() + (uint32_t)i * 4u);
+    for (int k = 0; k < c.ncopy; ++k) {
+      const uint32_t kk = (uint32_t)(k + c.lane) & (uint32_t)(c.ncopy - 1);  // staggered: a row of copies is one bank per lane
+      sum += (lds_u32(rowa + kk * 4u) >> sh) & 0xFFFFu;
+    }
     (&c.ctl->st.hist[0][0])[i] += sum;
   }
   __syncthreads();
@@ -102,8 +122,12 @@ __device__ __forceinline__ void wait_image(const RC<C>& c) {
 // transformed in place as their load chunks arrive, one unit per thread per step of RNT units; a
 // step leaves as one bulk store.  CutOut rectangles are painted over the step before it is stored.
 //   store   0: in place only (materialisation)  1: bulk-store every step to c.dst
+__device__ __forceinline__ void bulk_wait_read1() {  // all but this thread's most recent store have finished reading shared memory
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+
 template <int C, bool COUNT>
-__device__ void res_flat(const RC<C>& c, int store) {
+__device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
   constexpr int UW = (C == 3) ? 12 : 4;
   constexpr int UB = UW * 4;
   const TileState& t = *c.t;
@@ -115,6 +139,23 @@ __device__ void res_flat(const RC<C>& c, int store) {
   const float f = t.kfactor;
   const int n_paint = COUNT ? 0 : t.n_sp;  // this class holds masks only
   const bool touch = COUNT || use1 || kmode != K_NONE;  // else the staged bytes already are the result
+  // WRITE_OUT: the chunks of a step are free once the step's store has read them -- the next image's
+  // chunks go into them right away (thread 0 issues both, in order), so a flat image's store and the
+  // next image's load overlap the remaining steps instead of starting at the image boundary.
+  const uint8_t* next_src = nullptr;
+  int n_released = 0;  // thread 0: chunks of the next image already issued
+  if (!COUNT && store && c.tid == 0 && c.ctl->n_claimed < c.p->B)
+    next_src = c.p->in + (size_t)c.ctl->n_claimed * (size_t)c.img_bytes;
+  const int n_chunks = (c.img_bytes + RES_CHUNK - 1) / RES_CHUNK;
+  auto release_upto = [&](int bytes_done) {  // thread 0: every chunk that lies below bytes_done is free
+    while (n_released < n_chunks && min((n_released + 1) * RES_CHUNK, c.img_bytes) <= bytes_done) {
+      const uint32_t bytes = (uint32_t)min(RES_CHUNK, c.img_bytes - n_released * RES_CHUNK);
+      mbar_arrive_expect_tx(c.full0 + 8u * (uint32_t)n_released, bytes);
+      bulk_load(c.img + (uint32_t)n_released * RES_CHUNK, next_src + (size_t)n_released * RES_CHUNK, bytes,
+                c.full0 + 8u * (uint32_t)n_released);
+      ++n_released;
+    }
+  };
   if (COUNT) hist_zero(c);
   for (int base = 0; base < n_units; base += RNT) {
     const int wu = base + (c.tid & ~31);
@@ -191,9 +232,18 @@ __device__ void res_flat(const RC<C>& c, int store) {
         if (c.tid == 0) {
           bulk_store(c.dst + (size_t)base * UB, c.img + (uint32_t)base * UB, (uint32_t)(u1 - base) * UB);
           bulk_commit();
+          if (next_src) {
+            bulk_wait_read1();        // the previous step's store has read its bytes
+            release_upto(base * UB);
+          }
         }
       }
     }
+  }
+  if (!COUNT && store && c.tid == 0 && next_src) {
+    bulk_wait_read0();
+    release_upto(c.img_bytes);
+    c.ctl->n_prefetched = n_released;
   }
   if (COUNT) hist_reduce(c);
   else __syncthreads();
@@ -214,12 +264,22 @@ struct UnitWalk {
   }
 };
 
+// src_index (chb_kernels.cuh) without its integer epilogue: returns round(v) + SRC_K in `raw` -- the
+// callers fold the constant into their base address -- and tests the range in the float domain:
+// round-half-away(v) lies in [0, n) exactly when -0.5 < v < n - 0.5 (nmh = float(n) - 0.5, exact for
+// n < 2^22).  fl_rz(v + (2^22 + 0.5)) has ulp 0.5 there, so (bits >> 1) - (0x4A800000 >> 1) = floor(v + 0.5).
+constexpr uint32_t SRC_K = 0x4A800000u >> 1;
+__device__ __forceinline__ bool src_raw(float v, float nmh, uint32_t& raw) {
+  raw = __float_as_uint(__fadd_rz(v, 4194304.5f)) >> 1;
+  return (v > -0.5f) && (v < nmh);
+}
+
 // One or two spatial entries (all a RandAugment(N=2) chain can produce), K in {none, Color}: the
 // per-pixel arithmetic of the tile engine's gather_warp (exact float32 coordinates, src_index), the
 // source being the resident image.  A thread takes one unit (16 pixels for C = 3) at a time, four
 // pixels in flight, and stores the unit's 48 bytes from registers.
 template <int C, bool COUNT, bool TWO>
-__device__ void res_gather_fast(const RC<C>& c) {
+__device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
   constexpr int UW = (C == 3) ? 12 : 4;
   constexpr int PPU = UW * 4 / C;  // pixels per unit: 16, 8, 16, 4
   const TileState& t = *c.t;
@@ -239,6 +299,9 @@ __device__ void res_gather_fast(const RC<C>& c) {
   const uint32_t fill_a = c.ctl->fillc[0], fill_b = c.ctl->fillc[1];
   const uint32_t fa_addr = smem_addr(&c.ctl->fillc[0]), fb_addr = smem_addr(&c.ctl->fillc[1]);
   const int pitch = c.row;
+  const float wmh = __fadd_rn((float)W, -0.5f), hmh = __fadd_rn((float)H, -0.5f);
+  // source byte of raw indices (rx, ry): img + (ry - K) * pitch + (rx - K) * C
+  const uint32_t base_raw = c.img - SRC_K * (uint32_t)pitch - SRC_K * (uint32_t)C;
   uint32_t n_fill_a = 0, n_fill_b = 0;
   for (UnitWalk q(c.tid, W / PPU); q.y < H; q.next()) {
     const int y = q.y, x0 = q.ux * PPU;
@@ -253,29 +316,27 @@ __device__ void res_gather_fast(const RC<C>& c) {
       for (int i = 0; i < 4; ++i) {
         int ix = x0 + 4 * g + i, iy = y;
         bool hit_a, hit_b = false;
+        uint32_t rx = (uint32_t)ix + SRC_K, ry = (uint32_t)iy + SRC_K;
         if (a_geom) {
           const float fx = small_uint_to_float((uint32_t)ix);
-          int jx, jy;
-          const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(t0, fx), t1y), t2), W, jx);
-          const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(t3, fx), t4y), t5), H, jy);
+          const bool inx = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(t0, fx), t1y), t2), wmh, rx);
+          const bool iny = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(t3, fx), t4y), t5), hmh, ry);
           hit_a = !(inx && iny);
-          ix = jx; iy = jy;
         } else {
           hit_a = (iy >= ea.y0) && (iy < ea.y1) && (ix >= ea.x0) && (ix < ea.x1);
         }
         if (TWO && !hit_a) {
+          ix = (int)(rx - SRC_K); iy = (int)(ry - SRC_K);
           if (b_geom) {
             const float gx = small_uint_to_float((uint32_t)ix), gy = small_uint_to_float((uint32_t)iy);
-            int jx, jy;
-            const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[0], gx), __fmul_rn(eb.t[1], gy)), eb.t[2]), W, jx);
-            const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[3], gx), __fmul_rn(eb.t[4], gy)), eb.t[5]), H, jy);
+            const bool inx = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[0], gx), __fmul_rn(eb.t[1], gy)), eb.t[2]), wmh, rx);
+            const bool iny = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[3], gx), __fmul_rn(eb.t[4], gy)), eb.t[5]), hmh, ry);
             hit_b = !(inx && iny);
-            ix = jx; iy = jy;
           } else {
             hit_b = (iy >= eb.y0) && (iy < eb.y1) && (ix >= eb.x0) && (ix < eb.x1);
           }
         }
-        adr[i] = !(hit_a || hit_b) ? c.img + (uint32_t)(iy * pitch + ix * C) : (hit_a ? fa_addr : fb_addr);
+        adr[i] = !(hit_a || hit_b) ? base_raw + ry * (uint32_t)pitch + rx * (uint32_t)C : (hit_a ? fa_addr : fb_addr);
         hit |= (hit_a ? 1u : 0u) << i | (hit_b ? 16u : 0u) << i;
       }
       uint32_t v[4][C];
@@ -344,7 +405,7 @@ __device__ void res_gather_fast(const RC<C>& c) {
           for (int ch = 0; ch < C; ++ch) {
             const int bi = i * C + ch;
             const int wi = g * C + (bi >> 2);
-            o[wi] = ((bi & 3) == 0) ? (v[i][ch] & 255u) : put_byte(o[wi], v[i][ch], bi & 3);
+            o[wi] = ((bi & 3) == 0) ? v[i][ch] : put_byte(o[wi], v[i][ch], bi & 3);  // (every v is a zero-extended byte)
           }
       }
     }
@@ -363,7 +424,7 @@ __device__ void res_gather_fast(const RC<C>& c) {
 // General form: any list of constant-fill warps and masks, K in {none, Color}; one pixel per thread
 // at a time, byte stores (chains of three and more spatial ops are rare and this path is not tuned).
 template <int C, bool COUNT>
-__device__ void res_gather_list(const RC<C>& c) {
+__device__ __forceinline__ void res_gather_list(const RC<C>& c) {
   const TileState& t = *c.t;
   const int H = opaque(c.H), W = opaque(c.W);
   const int n_sp = t.n_sp;
@@ -417,7 +478,7 @@ __device__ void res_gather_list(const RC<C>& c) {
 }
 
 template <int C, bool COUNT>
-__device__ void res_gather(const RC<C>& c) {
+__device__ __forceinline__ void res_gather(const RC<C>& c) {
   const TileState& t = *c.t;
   wait_image(c);
   if (COUNT) hist_zero(c);
@@ -431,7 +492,7 @@ __device__ void res_gather(const RC<C>& c) {
 // l1 applied to the resident source in place (a Sharpness tap reads every byte nine times); the view
 // then continues with l1 = identity.
 template <int C>
-__device__ void res_bake_l1(const RC<C>& c) {
+__device__ __forceinline__ void res_bake_l1(const RC<C>& c) {
   TileState& t = c.ctl->st.t;
   if (t.l1_id) return;
   wait_image(c);
@@ -448,7 +509,9 @@ __device__ void res_bake_l1(const RC<C>& c) {
 }
 
 // Rows per sub-strip so that (word columns x sub-strips) fills the CTA: minimise rounds * (rows + 2).
+// Runs on one thread once per launch (the results live in ResCtl).
 __device__ __forceinline__ int res_sharp_split(int columns, int inner) {
+  if (inner <= 0) return 1;
   int best_s = 1, best_cost = 0x7FFFFFFF;
   for (int S = 1; S <= 64 && S <= inner; ++S) {
     const int rounds = (columns * S + RNT - 1) / RNT;
@@ -458,11 +521,80 @@ __device__ __forceinline__ int res_sharp_split(int columns, int inner) {
   return (inner + best_s - 1) / best_s;
 }
 
+// tfa.image.sharpness (oracle/ops.py sharpness) down one word column (4 output bytes), streaming: the
+// float32 chain of an output byte, (((((((p00 + p01) + p02) + p10) + c11 * 5/13) + p12) + p20) + p21) + p22
+// with p = value * 1/13, is carried in two partial sums per byte -- T (the row above is in) and A (the
+// byte's own row is in) -- so a row is loaded, converted and multiplied once and only 8 accumulators
+// stay live across rows (the tile engine's sharp_walk keeps the 30 products of three rows: it needs
+// 90+ registers, this one fits the 64 of a 1024-thread CTA).  Products are one FFMA each: the byte
+// is placed in the mantissa of 2^23 (one PRMT), and fma(2^23 + v, k, -2^23 * k) rounds the exact
+// v * k once -- the same float32 as float(v) * k.
+//   col      shared address of this column's word in the row ABOVE the first output row
+//   n        output rows; bmask bit b: byte b lies in the first / last pixel of the image row
+template <int C, class Emit>
+__device__ __forceinline__ void sharp_stream(uint32_t col, int pitch, int n, bool has_prev, bool has_next, uint32_t bmask,
+                                             float f, Emit emit) {
+  constexpr int NB = 4 + 2 * C;  // window bytes per row
+  const float k1 = __int_as_float(0x3d9d89d9);  // float32(1)/float32(13)
+  const float k5 = __int_as_float(0x3ec4ec4f);  // float32(5)/float32(13)
+  const float nk1 = -8388608.0f * k1, nk5 = -8388608.0f * k5;  // exact (powers of two)
+  float T[4], A[4], xm_mid[4];
+  float p[NB], xm[4];
+  auto load_row = [&](uint32_t ra) {
+    const uint32_t w1 = lds_u32(ra);
+    const uint32_t w0 = has_prev ? lds_u32(ra - 4) : 0u;
+    const uint32_t w2 = has_next ? lds_u32(ra + 4) : 0u;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int wb = 4 - C + j;  // byte index in the 12-byte (w0, w1, w2) window
+      const uint32_t wsel = (wb < 4) ? w0 : (wb < 8) ? w1 : w2;
+      const float m = __uint_as_float(__byte_perm(wsel, 0x4B000000u, 0x7440u | (uint32_t)(wb & 3)));  // 2^23 + v
+      p[j] = __fmaf_rn(m, k1, nk1);
+      if (j >= C && j < C + 4) xm[j - C] = m;
+    }
+  };
+  // row above the first output row: T only
+  load_row(col);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) T[b] = __fadd_rn(__fadd_rn(p[b], p[b + C]), p[b + 2 * C]);
+  uint32_t ra = col + pitch;
+  for (int r = 0; r <= n; ++r, ra += pitch) {
+    load_row(ra);
+    if (r > 0) {  // this row completes output row r - 1
+      uint32_t o = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        float acc = __fadd_rn(A[b], p[b]);
+        acc = __fadd_rn(acc, p[b + C]);
+        acc = __fadd_rn(acc, p[b + 2 * C]);
+        const float orig = __fadd_rn(xm_mid[b], -8388608.0f);
+        float deg = __fadd_rn(__fadd_rz(acc, 8388608.0f), -8388608.0f);  // float(trunc(acc))
+        deg = ((bmask >> b) & 1u) ? orig : deg;                           // border pixels keep the original
+        const uint32_t res = sharp_blend(deg, orig, f);
+        o = (b == 0) ? res : put_byte(o, res, b);
+      }
+      emit(r - 1, o);
+    }
+    if (r < n) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        // the byte's own row: + left, + centre * 5/13, + right
+        float acc = __fadd_rn(T[b], p[b]);
+        acc = __fadd_rn(acc, __fmaf_rn(xm[b], k5, nk5));
+        A[b] = __fadd_rn(acc, p[b + 2 * C]);
+        xm_mid[b] = xm[b];
+        // and it is the row above output row r + 1
+        T[b] = __fadd_rn(__fadd_rn(p[b], p[b + C]), p[b + 2 * C]);
+      }
+    }
+  }
+}
+
 // K == Sharpness, no spatial op pending: the column walk of the tile engine (sharp_walk) straight on
 // the resident image; a thread owns one word column of a run of rows and stores its words itself
 // (adjacent lanes, adjacent words).
 template <int C, bool COUNT>
-__device__ void res_sharp(const RC<C>& c) {
+__device__ __forceinline__ void res_sharp(const RC<C>& c) {
   res_bake_l1(c);
   wait_image(c);
   if (COUNT) hist_zero(c);
@@ -489,7 +621,7 @@ __device__ void res_sharp(const RC<C>& c) {
       emit(H - 1, xw, (C == 3) ? (xw % 3) : 0, lds_u32(c.img + (uint32_t)((H - 1) * row + (xw << 2))));
   const int inner = H - 2;
   if (inner > 0) {
-    const int R = res_sharp_split(wpr, inner);
+    const int R = c.ctl->sharp_rows;
     const int n_strips = (inner + R - 1) / R;
     const int n_items = wpr * n_strips;
     for (int item = c.tid; item < n_items; item += RNT) {
@@ -502,8 +634,8 @@ __device__ void res_sharp(const RC<C>& c) {
         if (xb0 + b < C || xb0 + b >= row - C) bmask |= 1u << b;
       const int ph = (C == 3) ? (xw % 3) : 0;
       const uint32_t col = c.img + (uint32_t)((y_begin - 1) * row + xb0);
-      sharp_walk<C>(col, row, y_end - y_begin, xw > 0, xw + 1 < wpr, bmask, f,
-                    [&](int r, uint32_t o) { emit(y_begin + r, xw, ph, o); });
+      sharp_stream<C>(col, row, y_end - y_begin, xw > 0, xw + 1 < wpr, bmask, f,
+                      [&](int r, uint32_t o) { emit(y_begin + r, xw, ph, o); });
     }
   }
   if (COUNT) hist_reduce(c);
@@ -515,7 +647,7 @@ __device__ void res_sharp(const RC<C>& c) {
 // out so that the row's first pixel starts on a word: 4 - C pad bytes, the left halo pixel, the
 // row, the right halo pixel.
 template <int C, bool COUNT>
-__device__ void res_gather_sharp(RC<C> c) {
+__device__ __forceinline__ void res_gather_sharp(RC<C> c) {
   wait_image(c);
   const TileState& t = *c.t;
   const int H = c.H, W = c.W, row = c.row;
@@ -525,13 +657,13 @@ __device__ void res_gather_sharp(RC<C> c) {
   const int vw = W + 2;
   const int vpitch = (4 + (W + 1) * C + 3) & ~3;
   uint32_t vbuf = c.aux;
-  int vbytes = c.aux_bytes;
-  if (COUNT) {  // one histogram copy in front of the band buffer
-    c.ncopy = 1; c.hcopy = c.aux;
+  if (COUNT) {  // four histogram copies in front of the band buffer
+    c.ncopy = 4; c.hshift = 4u; c.hcopy = c.aux + (uint32_t)(c.lane & 3) * 4u;
     hist_zero(c);
-    vbuf += hc_copy_bytes<C>(); vbytes -= (int)hc_copy_bytes<C>();
+    vbuf += hist_bytes<C>(4);
   }
-  const int band = max(1, vbytes / vpitch - 2);  // output rows per band
+  const int band = c.ctl->gs_band[COUNT ? 1 : 0];  // output rows per band (aux capacity)
+  const int band_rows = c.ctl->gs_rows[COUNT ? 1 : 0];
   const int wpr = row >> 2;
   const Spatial& e0 = t.sp[0];
   const bool one = (n_sp == 1);
@@ -608,7 +740,7 @@ __device__ void res_gather_sharp(RC<C> c) {
     const int in0 = max(ya, 1), in1 = min(yb, H - 1);
     const int inner = in1 - in0;
     if (inner > 0) {
-      const int R = res_sharp_split(wpr, inner);
+      const int R = band_rows;
       const int n_strips = (inner + R - 1) / R;
       const int n_items = wpr * n_strips;
       for (int item = c.tid; item < n_items; item += RNT) {
@@ -621,8 +753,8 @@ __device__ void res_gather_sharp(RC<C> c) {
           if (xb < C || xb >= row - C) bmask |= 1u << b;
         }
         const uint32_t col = vbuf + (uint32_t)((y_begin - 1 - (ya - 1)) * vpitch + 4 + (xw << 2));
-        sharp_walk<C>(col, vpitch, y_end - y_begin, true, true, bmask, f,
-                      [&](int r, uint32_t o) { emit(y_begin + r, xw, o); });
+        sharp_stream<C>(col, vpitch, y_end - y_begin, true, true, bmask, f,
+                        [&](int r, uint32_t o) { emit(y_begin + r, xw, o); });
       }
     }
     __syncthreads();  // the next band overwrites the buffer
@@ -654,7 +786,10 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   const int H = p.H, W = p.W;
   const int img_bytes = H * W * C;
   const int n_chunks = (img_bytes + RES_CHUNK - 1) / RES_CHUNK;
-  const uint32_t img_off = (uint32_t)((sizeof(ResCtl) + 127) / 128 * 128);
+  // shared memory: control block | policy table (DevOp[n_ops], value maps [n_ops][256]) | image | aux region
+  const int n_pol = p.T * p.K;
+  const uint32_t pol_off = (uint32_t)((sizeof(ResCtl) + 127) / 128 * 128);
+  const uint32_t img_off = pol_off + (uint32_t)((n_pol * (int)(sizeof(DevOp) + 256) + 127) / 128 * 128);
   const uint32_t aux_off = img_off + (uint32_t)((img_bytes + 127) / 128 * 128);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   RC<C> c;
@@ -665,42 +800,72 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   c.full0 = smem_addr(&ctl->full[0]);
   c.H = H; c.W = W; c.row = W * C; c.img_bytes = img_bytes; c.tid = tid; c.lane = tid & 31;
   c.l1a = smem_addr(&ctl->st.t.l1[0][0]); c.l2a = smem_addr(&ctl->st.t.l2[0][0]);
-  int ncopy = 8;
-  while (ncopy > 1 && (uint32_t)ncopy * hc_copy_bytes<C>() > (uint32_t)c.aux_bytes) ncopy >>= 1;
+  int ncopy = 32;
+  while (ncopy > 4 && hist_bytes<C>(ncopy) > (uint32_t)c.aux_bytes) ncopy >>= 1;
   c.par = 1;  // toggled to 0 by the first load
   c.dst = nullptr;
   if (tid == 0) {
     for (int k = 0; k < RES_MAXCHUNK; ++k) mbar_init(c.full0 + 8 * k, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
+    // shape-only work splits
+    const int wpr = (W * C) >> 2;
+    ctl->sharp_rows = res_sharp_split(wpr, H - 2);
+    const int vpitch = (4 + (W + 1) * C + 3) & ~3;
+    for (int k = 0; k < 2; ++k) {
+      const int vbytes = c.aux_bytes - (k ? (int)hist_bytes<C>(4) : 0);
+      int band = max(1, vbytes / vpitch - 2);
+      // whole bands of equal height: the last band is not a sliver
+      const int n_bands = (H + band - 1) / band;
+      band = (H + n_bands - 1) / n_bands;
+      ctl->gs_band[k] = band;
+      ctl->gs_rows[k] = res_sharp_split(wpr, min(band, max(H - 2, 1)));
+    }
+    ctl->n_prefetched = 0;
   }
   // Programmatic dependent launch: nothing the previous kernel of the stream wrote (the images, a
-  // replayed schedule, the work counter it left zeroed) is touched before it has completed.
+  // replayed schedule, the policy table, the work counter it left zeroed) is touched before it has completed.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tid == 0) ctl->next_img = (int)atomicAdd(p.counters, 1u);
+  // the policy table comes to shared memory once: the chain walk of every image reads it many times
+  DevOp* s_ops = reinterpret_cast<DevOp*>(smem_raw + pol_off);
+  uint8_t* s_optab = smem_raw + pol_off + (size_t)n_pol * sizeof(DevOp);
+  for (int i = tid; i < n_pol * (int)(sizeof(DevOp) / 16); i += RNT)
+    reinterpret_cast<uint4*>(s_ops)[i] = __ldg(reinterpret_cast<const uint4*>(p.ops) + i);
+  for (int i = tid; i < n_pol * 16; i += RNT)
+    reinterpret_cast<uint4*>(s_optab)[i] = __ldg(reinterpret_cast<const uint4*>(p.optab) + i);
+  if (tid == 0) {  // what decode_image / advance see
+    ctl->kp = p;
+    ctl->kp.ops = s_ops;
+    ctl->kp.optab = s_optab;
+  }
+  const KParams& pl = ctl->kp;
   __syncthreads();
   int img = ctl->next_img;
   uint8_t* scratch = p.scratch + (size_t)blockIdx.x * p.scratch_stride;
-  auto issue_load = [&](const uint8_t* src) {  // thread 0
-    for (int k = 0; k < n_chunks; ++k) {
-      const uint32_t bytes = (uint32_t)min(RES_CHUNK, img_bytes - k * RES_CHUNK);
-      mbar_arrive_expect_tx(c.full0 + 8 * k, bytes);
-      bulk_load(c.img + (uint32_t)k * RES_CHUNK, src + (size_t)k * RES_CHUNK, bytes, c.full0 + 8 * k);
+  // chunk k is issued by thread k (each arrives on its own barrier); chunks below `first` are already in flight
+  auto issue_load = [&](const uint8_t* src, int first) {
+    if (tid >= first && tid < n_chunks) {
+      const uint32_t bytes = (uint32_t)min(RES_CHUNK, img_bytes - tid * RES_CHUNK);
+      mbar_arrive_expect_tx(c.full0 + 8 * tid, bytes);
+      bulk_load(c.img + (uint32_t)tid * RES_CHUNK, src + (size_t)tid * RES_CHUNK, bytes, c.full0 + 8 * tid);
     }
   };
   while (img < p.B) {
     c.par ^= 1u;
+    issue_load(p.in + (size_t)img * img_bytes, ctl->n_prefetched);  // (a flat predecessor already issued some or all)
+    __syncthreads();
     if (tid == 0) {
-      issue_load(p.in + (size_t)img * img_bytes);
+      ctl->n_prefetched = 0;
       ctl->n_claimed = (int)atomicAdd(p.counters, 1u);  // the next image: the round trip hides behind this one
     }
     // schedule decode + chain walk up to the first pass (the loads are in flight)
     for (int i = tid; i < STATE_VECS; i += RNT) reinterpret_cast<uint4*>(&ctl->st)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    if (tid < 32) decode_image(p, &ctl->st, ctl->rnd, ctl->rndc, img, H, W, tid);
+    if (tid < 32) decode_image(pl, &ctl->st, ctl->rnd, ctl->rndc, img, H, W, tid);
     reset_view(&ctl->st, tid, RNT);
     __syncthreads();
-    advance(&ctl->st, &ctl->st, p, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
+    advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
     uint8_t* out_img = p.out + (size_t)img * img_bytes;
     for (;;) {
       const TileState& t = ctl->st.t;
@@ -714,38 +879,36 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
         ctl->fillc[0] = fa; ctl->fillc[1] = fb;
       }
       c.ncopy = ncopy;
-      c.hcopy = c.aux + (uint32_t)(c.lane & (ncopy - 1)) * hc_copy_bytes<C>();
+      c.hshift = 31u - (uint32_t)__clz(ncopy * 4);
+      c.hcopy = c.aux + (uint32_t)(c.lane & (ncopy - 1)) * 4u;
       __syncthreads();
       if (pass_kind == PASS_COUNT) {
         res_run_pass<C, true>(c, 0);
         if (tid == 0) ctl->st.hist_valid = 1;
         __syncthreads();
-        advance(&ctl->st, &ctl->st, p, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
-      } else if (pass_kind == PASS_WRITE_SCRATCH) {
-        bool any_geom = false;
-        for (int k = 0; k < t.n_sp; ++k) any_geom = any_geom || (t.sp[k].type == SP_GEOM);
-        // point-wise views (and CutOut rectangles, painted over them) materialise in the resident image itself
-        const bool in_place = (t.kmode == K_NONE || t.kmode == K_COLOR) && !any_geom;
-        if (in_place) {
-          res_run_pass<C, false>(c, 0);
-        } else {
-          c.dst = scratch;
-          res_run_pass<C, false>(c, 0);
-          // the scratch image (generic-proxy stores) comes back through the TMA
-          __threadfence();
-          fence_proxy_async_all();
-          __syncthreads();
-          c.par ^= 1u;
-          if (tid == 0) issue_load(scratch);
-        }
-        reset_view(&ctl->st, tid, RNT);
-        __syncthreads();
-        advance(&ctl->st, &ctl->st, p, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
-      } else {
-        c.dst = out_img;
-        res_run_pass<C, false>(c, 1);
-        break;
+        advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
+        continue;
       }
+      // WRITE_OUT, or WRITE_SCRATCH: point-wise views (and CutOut rectangles, painted over them)
+      // materialise in the resident image itself, the rare neighbourhood-of-neighbourhood chains go
+      // through this CTA's scratch image and come back through the TMA
+      const bool last = pass_kind == PASS_WRITE_OUT;
+      bool any_geom = false;
+      for (int k = 0; k < t.n_sp; ++k) any_geom = any_geom || (t.sp[k].type == SP_GEOM);
+      const bool in_place = !last && (t.kmode == K_NONE || t.kmode == K_COLOR) && !any_geom;
+      c.dst = last ? out_img : scratch;
+      res_run_pass<C, false>(c, last ? 1 : 0);
+      if (last) break;
+      if (!in_place) {
+        __threadfence();
+        fence_proxy_async_all();
+        __syncthreads();
+        c.par ^= 1u;
+        issue_load(scratch, 0);
+      }
+      reset_view(&ctl->st, tid, RNT);
+      __syncthreads();
+      advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
     }
     // every thread is done with the resident source; bulk stores out of it have read their bytes;
     // in-place writes (generic proxy) are ordered before the TMA refills the buffer

@@ -261,3 +261,75 @@ def test_resizing_min_max_shapes_match_the_reference_tests():
     assert np.array_equal(oracle.resize_bilinear(x, 7, 9), x.astype(np.float32))
     n = oracle.resize_nearest(x, 14, 18)
     assert n.dtype == np.uint8 and np.array_equal(n[:, ::2, ::2], x)
+
+
+def check_tf_vectors(path):
+    """Compares the oracle with vectors produced by the real reference on TensorFlow
+    (tests/golden/make_tf_vectors.py).  Returns (report lines, number of mismatching cases).  For the
+    behaviours behind oracle/switches.py it also tries the alternative setting and says which one
+    the vector confirms."""
+    from oracle import switches
+    z = np.load(path, allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    lines, bad = ["vectors from tensorflow %s / tensorflow-addons %s" % (meta["tensorflow"], meta["tensorflow_addons"])], 0
+    alternatives = {"Solarize": ("SOLARIZE_THRESHOLD_OVERFLOW", ("wrap", "saturate")),
+                    "Posterize": ("POSTERIZE_SHIFT8", ("clamp7", "zero")),
+                    "Sharpness": ("TFA_BLEND_ROUNDING", ("round_half_even", "truncate"))}
+    for case in meta["cases"]:
+        x = z["in_" + case["input"]]
+        want = z[case["tag"]]
+        centres = case["centres"] if case["centres"] is not None else [[0, 0]] * x.shape[0]
+        got = oracle.apply_op(x, case["name"], case["kwargs"], negate=bool(case["negate"]), centers=centres)
+        diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+        n_bad, worst = int((diff > 0).sum()), int(diff.max()) if diff.size else 0
+        verdict = "exact" if n_bad == 0 else "%d bytes differ (max %d LSB)" % (n_bad, worst)
+        if n_bad and case["name"] in alternatives:
+            sw, values = alternatives[case["name"]]
+            keep = getattr(switches, sw)
+            for v in values:
+                setattr(switches, sw, v)
+                alt = oracle.apply_op(x, case["name"], case["kwargs"], negate=bool(case["negate"]), centers=centres)
+                if np.array_equal(alt, want):
+                    verdict += "; switch %s=%r reproduces it (default is %r)" % (sw, v, keep)
+            setattr(switches, sw, keep)
+        bad += 1 if n_bad else 0
+        lines.append("%-12s %-60s on %-5s negate=%d: %s" % (case["name"], json.dumps(case["kwargs"])[:60], case["input"],
+                                                           case["negate"], verdict))
+    return lines, bad
+
+
+def test_oracle_against_tensorflow_vectors_when_present():
+    """Flips parity from "unpinned" to pinned the day tests/golden/tf_vectors.npz is generated (needs
+    TensorFlow 2.6 + tensorflow-addons: tests/golden/make_tf_vectors.py)."""
+    path = os.path.join(GOLDEN, "tf_vectors.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/tf_vectors.npz not generated yet (TensorFlow is not installable in this image)")
+    lines, bad = check_tf_vectors(path)
+    print("\n".join(lines))
+    assert bad == 0, "%d cases differ from TensorFlow:\n%s" % (bad, "\n".join(l for l in lines if "differ" in l))
+
+
+def test_tf_vector_file_format_roundtrip(tmp_path):
+    """The consumer above on a file in the generator's format (written here FROM THE ORACLE, in a temp
+    directory -- plumbing only, it pins nothing): every case must read back as exact, and a corrupted
+    Solarize(256) vector must be reported together with the switch value that would reproduce it."""
+    from oracle import switches
+    x = random_images(2, 16, 16, 3, seed=3)
+    cases, arrays = [], {"in_a": x}
+    specs = [("Invert", {}, 0, None), ("Rotate", {"degrees": 30.0, "interpolation": "nearest", "fill_mode": "constant", "fill_value": 128}, 1, None),
+             ("CutOut", {"mask_size": 8, "constant_values": 128}, 0, [[3, 4], [15, 0]]), ("Solarize", {"threshold": 256}, 0, None)]
+    for i, (name, kw, neg, cen) in enumerate(specs):
+        tag = "out_%03d_a_%d" % (i, neg)
+        arrays[tag] = oracle.apply_op(x, name, kw, negate=bool(neg), centers=cen if cen is not None else [[0, 0]] * 2)
+        cases.append({"tag": tag, "name": name, "kwargs": kw, "magnitude": None, "negate": neg, "input": "a", "centres": cen})
+    arrays["meta"] = np.array(json.dumps({"tensorflow": "fake", "tensorflow_addons": "fake", "cases": cases}))
+    path = str(tmp_path / "tf_vectors.npz")
+    np.savez_compressed(path, **arrays)
+    lines, bad = check_tf_vectors(path)
+    assert bad == 0 and sum("exact" in l for l in lines) == len(specs)
+    assert switches.SOLARIZE_THRESHOLD_OVERFLOW == "wrap"
+    arrays["out_003_a_0"] = x.copy()          # what "saturate" (nothing inverted at 256) would give
+    np.savez_compressed(path, **arrays)
+    lines, bad = check_tf_vectors(path)
+    assert bad == 1 and any("SOLARIZE_THRESHOLD_OVERFLOW='saturate' reproduces it" in l for l in lines)
+    assert switches.SOLARIZE_THRESHOLD_OVERFLOW == "wrap"   # restored
