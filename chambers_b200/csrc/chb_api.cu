@@ -43,6 +43,7 @@ static int g_pipe = 4;              // streams in use (CHB_E2E_STREAMS)
 static long long g_nf_first_images = 6;  // a batch is also "small" below this many images per CTA (CHB_NF_FIRST_IMAGES)
 static int g_self_clean = 1;         // CHB_SELF_CLEAN=0: zero the counters with a memset in front of every call instead
 static int g_chunk_kb = 2560;       // target chunk size of the host path in KiB (CHB_E2E_CHUNK_KB)
+static int g_lpt = 1;               // resident engine: cost-sorted claim order for small batches (CHB_LPT=0 disables)
 
 struct chb_ctx {
   int device = 0;
@@ -407,6 +408,7 @@ extern "C" int chb_init(int device, chb_ctx** out) {
   if (const char* e = getenv("CHB_SELF_CLEAN")) g_self_clean = (e[0] != '0') ? 1 : 0;
   if (const char* e = getenv("CHB_E2E_STREAMS")) { int v = atoi(e); if (v >= 1 && v <= kPipeMax) g_pipe = v; }
   if (const char* e = getenv("CHB_E2E_CHUNK_KB")) { int v = atoi(e); if (v >= 64) g_chunk_kb = v; }
+  if (const char* e = getenv("CHB_LPT")) g_lpt = (e[0] != '0') ? 1 : 0;
   const char* fg = getenv("CHB_FORCE_GENERIC");
   ctx->force_generic = (fg && fg[0] && fg[0] != '0') ? 1 : 0;
   *out = ctx;
@@ -456,6 +458,7 @@ extern "C" int chb_debug_timeline(chb_ctx* ctx, uint64_t* host_out, int max_word
   if (!ctx->timeline) {
     CHB_CUDA(ctx, cudaMalloc(&ctx->timeline, kTimelineWords * 8));
     CHB_CUDA(ctx, cudaMemset(ctx->timeline, 0, kTimelineWords * 8));
+    CHB_CUDA(ctx, cudaMemset(ctx->timeline + 1, 0xFF, 8));  // resident engine: earliest kernel entry (atomicMin)
   }
   if (!host_out) return 0;
   CHB_CUDA(ctx, cudaDeviceSynchronize());
@@ -463,6 +466,7 @@ extern "C" int chb_debug_timeline(chb_ctx* ctx, uint64_t* host_out, int max_word
   if (n > kTimelineWords) n = kTimelineWords;
   CHB_CUDA(ctx, cudaMemcpy(host_out, ctx->timeline, n * 8, cudaMemcpyDeviceToHost));
   CHB_CUDA(ctx, cudaMemset(ctx->timeline, 0, kTimelineWords * 8));
+  CHB_CUDA(ctx, cudaMemset(ctx->timeline + 1, 0xFF, 8));
   return (int)n;
 #else
   (void)host_out; (void)max_words;
@@ -668,6 +672,13 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     p.scratch = ws->scratch; p.scratch_stride = stride;
     p.counters = ws->counters;
     p.res_smem_bytes = ctx->res_smem;
+    p.res_lpt = g_lpt;
+    p.timeline = ctx->timeline;
+    {
+      const size_t fixed = chb::resident_ctl_bytes() + (pe->host.size() * (sizeof(DevOp) + 256) + 127) / 128 * 128 +
+                           (img_bytes + 127) / 128 * 128;
+      chb::resident_splits(p, C, (int)((size_t)ctx->res_smem - fixed));
+    }
     cudaError_t e = cudaSuccess;
     if (!ws->clean || !g_self_clean) {
       e = cudaMemsetAsync(ws->counters, 0, (32 + ws->cap_images * CHB_MAX_CHAIN + 2048) * sizeof(unsigned int), stream);

@@ -113,7 +113,10 @@ struct KParams {
   int n_flat_tiles;                   // flat runs per image (tiles of <= 256 units; == n_tiles unless the batch is 16-byte aligned)
   int flags;                          // 1: in is 16-byte aligned, 2: out is, 4: images are whole 16-byte units, 8: rows are
   unsigned long long* timeline;       // debug builds (-DCHB_TIMELINE): [1024 CTAs][2][16] words, else NULL
-  int res_smem_bytes;                 // resident engine: dynamic shared memory of a CTA (control + image + aux region)
+  int res_smem_bytes;                 // resident engine: dynamic shared memory of a CTA (control + policy + image + aux region)
+  int res_lpt;                        //   1: small batches are claimed most-expensive-chain-first (CHB_LPT=0 disables)
+  int res_sharp_rows;                 //   Sharpness: rows per sub-strip of the column walk
+  int res_gs_band[2], res_gs_rows[2]; //   gathered Sharpness (WRITE / COUNT): output rows per band, rows per sub-strip
 };
 
 // Opaque copy of a CUtensorMap (cuda.h), passed to the pass kernel as a __grid_constant__ parameter.
@@ -135,6 +138,7 @@ int pass_ctas_per_sm(int C);
 // Image-resident engine (chb_resident.cuh): one CTA per SM, the whole image in shared memory.
 cudaError_t launch_resident(const KParams& p, int C, int grid, cudaStream_t stream);
 cudaError_t configure_resident(int smem_bytes);
+void resident_splits(KParams& p, int C, int aux_bytes);
 // The layers either side of the policy path (chb_frontend.cu).
 cudaError_t launch_normalize(const void* in, int in_is_f32, float* out, unsigned long long n, int C, int mode, int num_sms,
                              cudaStream_t stream);

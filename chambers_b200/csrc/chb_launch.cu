@@ -11,7 +11,8 @@ CHB_DECL(1) CHB_DECL(2) CHB_DECL(3) CHB_DECL(4)
 #undef CHB_DECL
 #define CHB_DECL_RES(C)                                                        \
   cudaError_t launch_resident_c##C(const KParams&, int, cudaStream_t);         \
-  cudaError_t configure_resident_c##C(int);
+  cudaError_t configure_resident_c##C(int);                                    \
+  void resident_splits_c##C(KParams&, int);
 CHB_DECL_RES(1) CHB_DECL_RES(2) CHB_DECL_RES(3) CHB_DECL_RES(4)
 #undef CHB_DECL_RES
 
@@ -65,6 +66,15 @@ cudaError_t configure_resident(int smem_bytes) {
   if ((e = configure_resident_c2(smem_bytes)) != cudaSuccess) return e;
   if ((e = configure_resident_c3(smem_bytes)) != cudaSuccess) return e;
   return configure_resident_c4(smem_bytes);
+}
+
+void resident_splits(KParams& p, int C, int aux_bytes) {
+  switch (C) {
+    case 1: resident_splits_c1(p, aux_bytes); break;
+    case 2: resident_splits_c2(p, aux_bytes); break;
+    case 3: resident_splits_c3(p, aux_bytes); break;
+    default: resident_splits_c4(p, aux_bytes); break;
+  }
 }
 
 cudaError_t launch_resident(const KParams& p, int C, int grid, cudaStream_t stream) {

@@ -24,6 +24,7 @@
 // rows are whole 16-byte units, every geometric op is nearest / constant-fill (what the policies
 // use, augmentation_schemes.py:7-9).  Everything else stays on the tile engine (chb_kernels.cuh).
 #pragma once
+#define RES_CHUNK_BYTES 12288
 // the policy table is staged in shared memory: plain loads (see chb_kernels.cuh)
 #define CHB_LDP(ptr) (*(ptr))
 #include "chb_kernels.cuh"
@@ -31,14 +32,19 @@
 namespace chb {
 namespace {
 
-constexpr int RNT = 1024;              // threads of a resident CTA (32 warps, 64 registers each)
-constexpr int RES_CHUNK = 12288;       // bytes per load chunk: 256 units of 48 bytes / 768 of 16
+#ifndef CHB_RNT
+#define CHB_RNT 1024
+#endif
+constexpr int RNT = CHB_RNT;           // threads of a resident CTA (1024: 32 warps, 64 registers each)
+static_assert(RNT % 256 == 0 && (RNT * 48) % RES_CHUNK_BYTES == 0, "a flat step must be a whole number of load chunks");
+constexpr int RES_CHUNK = RES_CHUNK_BYTES;       // bytes per load chunk: 256 units of 48 bytes / 768 of 16
 constexpr int RES_MAXCHUNK = 16;       // -> images of up to 192 KB
 constexpr int RES_MIN_AUX = 16 * 1024;
+constexpr int LPT_MAX = 2048;          // batches up to this size are claimed longest-chain-first
 
 struct alignas(128) ResCtl {
   unsigned long long full[RES_MAXCHUNK];
-  int32_t next_img, n_claimed, n_prefetched, _p2;
+  int32_t next_img, n_claimed, _p1, _p2;
   // work splits that depend only on the shape (computed once per launch by thread 0)
   int32_t sharp_rows;                  // res_sharp: rows per sub-strip
   int32_t gs_band[2], gs_rows[2];      // res_gather_sharp, WRITE / COUNT: output rows per band, rows per sub-strip
@@ -49,6 +55,7 @@ struct alignas(128) ResCtl {
   uint32_t hmap[MAXC * 256];
   uint8_t etab[MAXC * 256];
   KParams kp;                          // the launch parameters with ops / optab pointing at the shared-memory copy
+  uint16_t order[LPT_MAX];             // small batches: claim position -> image, most expensive chains first
   ImgState st;
 };
 
@@ -122,10 +129,6 @@ __device__ __forceinline__ void wait_image(const RC<C>& c) {
 // transformed in place as their load chunks arrive, one unit per thread per step of RNT units; a
 // step leaves as one bulk store.  CutOut rectangles are painted over the step before it is stored.
 //   store   0: in place only (materialisation)  1: bulk-store every step to c.dst
-__device__ __forceinline__ void bulk_wait_read1() {  // all but this thread's most recent store have finished reading shared memory
-  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-}
-
 template <int C, bool COUNT>
 __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
   constexpr int UW = (C == 3) ? 12 : 4;
@@ -139,23 +142,6 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
   const float f = t.kfactor;
   const int n_paint = COUNT ? 0 : t.n_sp;  // this class holds masks only
   const bool touch = COUNT || use1 || kmode != K_NONE;  // else the staged bytes already are the result
-  // WRITE_OUT: the chunks of a step are free once the step's store has read them -- the next image's
-  // chunks go into them right away (thread 0 issues both, in order), so a flat image's store and the
-  // next image's load overlap the remaining steps instead of starting at the image boundary.
-  const uint8_t* next_src = nullptr;
-  int n_released = 0;  // thread 0: chunks of the next image already issued
-  if (!COUNT && store && c.tid == 0 && c.ctl->n_claimed < c.p->B)
-    next_src = c.p->in + (size_t)c.ctl->n_claimed * (size_t)c.img_bytes;
-  const int n_chunks = (c.img_bytes + RES_CHUNK - 1) / RES_CHUNK;
-  auto release_upto = [&](int bytes_done) {  // thread 0: every chunk that lies below bytes_done is free
-    while (n_released < n_chunks && min((n_released + 1) * RES_CHUNK, c.img_bytes) <= bytes_done) {
-      const uint32_t bytes = (uint32_t)min(RES_CHUNK, c.img_bytes - n_released * RES_CHUNK);
-      mbar_arrive_expect_tx(c.full0 + 8u * (uint32_t)n_released, bytes);
-      bulk_load(c.img + (uint32_t)n_released * RES_CHUNK, next_src + (size_t)n_released * RES_CHUNK, bytes,
-                c.full0 + 8u * (uint32_t)n_released);
-      ++n_released;
-    }
-  };
   if (COUNT) hist_zero(c);
   for (int base = 0; base < n_units; base += RNT) {
     const int wu = base + (c.tid & ~31);
@@ -232,18 +218,9 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
         if (c.tid == 0) {
           bulk_store(c.dst + (size_t)base * UB, c.img + (uint32_t)base * UB, (uint32_t)(u1 - base) * UB);
           bulk_commit();
-          if (next_src) {
-            bulk_wait_read1();        // the previous step's store has read its bytes
-            release_upto(base * UB);
-          }
         }
       }
     }
-  }
-  if (!COUNT && store && c.tid == 0 && next_src) {
-    bulk_wait_read0();
-    release_upto(c.img_bytes);
-    c.ctl->n_prefetched = n_released;
   }
   if (COUNT) hist_reduce(c);
   else __syncthreads();
@@ -276,12 +253,9 @@ __device__ __forceinline__ bool src_raw(float v, float nmh, uint32_t& raw) {
 
 // One or two spatial entries (all a RandAugment(N=2) chain can produce), K in {none, Color}: the
 // per-pixel arithmetic of the tile engine's gather_warp (exact float32 coordinates, src_index), the
-// source being the resident image.  A thread takes one unit (16 pixels for C = 3) at a time, four
-// pixels in flight, and stores the unit's 48 bytes from registers.
+// source being the resident image.
 template <int C, bool COUNT, bool TWO>
 __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
-  constexpr int UW = (C == 3) ? 12 : 4;
-  constexpr int PPU = UW * 4 / C;  // pixels per unit: 16, 8, 16, 4
   const TileState& t = *c.t;
   const int H = c.H, W = c.W;
   const int n_sp = t.n_sp;
@@ -303,122 +277,295 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
   // source byte of raw indices (rx, ry): img + (ry - K) * pitch + (rx - K) * C
   const uint32_t base_raw = c.img - SRC_K * (uint32_t)pitch - SRC_K * (uint32_t)C;
   uint32_t n_fill_a = 0, n_fill_b = 0;
-  for (UnitWalk q(c.tid, W / PPU); q.y < H; q.next()) {
-    const int y = q.y, x0 = q.ux * PPU;
+  // A thread takes G quads (4 adjacent pixels, C words each) at a time.  G = 1: the lanes of a warp read
+  // source pixels that are neighbours along the warp's direction, i.e. nearly consecutive shared-memory
+  // words (with G = 4 for C = 3 -- one 48-byte unit per lane -- the lanes are 16 source pixels apart and
+  // 61 % of the gather's wavefronts were bank conflicts, profiles/r02_v1_ncu_op_Rotate.txt).
+#ifndef CHB_GATHER_G
+#define CHB_GATHER_G 1
+#endif
+#ifndef CHB_GATHER_RAW
+#define CHB_GATHER_RAW 0
+#endif
+  constexpr int G = CHB_GATHER_G;
+  for (UnitWalk q(c.tid, W / (4 * G)); q.y < H; q.next()) {
+    const int y = q.y, xu = q.ux * (4 * G);
     const float fy = small_uint_to_float((uint32_t)y);
     const float t1y = __fmul_rn(t1, fy), t4y = __fmul_rn(t4, fy);
-    uint32_t o[UW];
 #pragma unroll
-    for (int g = 0; g < PPU / 4; ++g) {
-      uint32_t adr[4];
-      uint32_t hit = 0;  // bit i: pixel i shows entry a's colour, bit 4 + i: entry b's
+    for (int g = 0; g < G; ++g) {
+    const int x0 = xu + 4 * g;
+    uint32_t adr[4];
+    uint32_t hit = 0;  // bit i: pixel i shows entry a's colour, bit 4 + i: entry b's
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int ix = x0 + 4 * g + i, iy = y;
-        bool hit_a, hit_b = false;
-        uint32_t rx = (uint32_t)ix + SRC_K, ry = (uint32_t)iy + SRC_K;
-        if (a_geom) {
-          const float fx = small_uint_to_float((uint32_t)ix);
-          const bool inx = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(t0, fx), t1y), t2), wmh, rx);
-          const bool iny = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(t3, fx), t4y), t5), hmh, ry);
-          hit_a = !(inx && iny);
-        } else {
-          hit_a = (iy >= ea.y0) && (iy < ea.y1) && (ix >= ea.x0) && (ix < ea.x1);
-        }
-        if (TWO && !hit_a) {
-          ix = (int)(rx - SRC_K); iy = (int)(ry - SRC_K);
-          if (b_geom) {
-            const float gx = small_uint_to_float((uint32_t)ix), gy = small_uint_to_float((uint32_t)iy);
-            const bool inx = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[0], gx), __fmul_rn(eb.t[1], gy)), eb.t[2]), wmh, rx);
-            const bool iny = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[3], gx), __fmul_rn(eb.t[4], gy)), eb.t[5]), hmh, ry);
-            hit_b = !(inx && iny);
-          } else {
-            hit_b = (iy >= eb.y0) && (iy < eb.y1) && (ix >= eb.x0) && (ix < eb.x1);
-          }
-        }
-        adr[i] = !(hit_a || hit_b) ? base_raw + ry * (uint32_t)pitch + rx * (uint32_t)C : (hit_a ? fa_addr : fb_addr);
-        hit |= (hit_a ? 1u : 0u) << i | (hit_b ? 16u : 0u) << i;
+    for (int i = 0; i < 4; ++i) {
+      int ix = x0 + i, iy = y;
+      bool hit_a, hit_b = false;
+#if CHB_GATHER_RAW
+      uint32_t rx = (uint32_t)ix + SRC_K, ry = (uint32_t)iy + SRC_K;
+      if (a_geom) {
+        const float fx = small_uint_to_float((uint32_t)ix);
+        const bool inx = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(t0, fx), t1y), t2), wmh, rx);
+        const bool iny = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(t3, fx), t4y), t5), hmh, ry);
+        hit_a = !(inx && iny);
+      } else {
+        hit_a = (iy >= ea.y0) && (iy < ea.y1) && (ix >= ea.x0) && (ix < ea.x1);
       }
-      uint32_t v[4][C];
+      if (TWO && !hit_a) {
+        ix = (int)(rx - SRC_K); iy = (int)(ry - SRC_K);
+        if (b_geom) {
+          const float gx = small_uint_to_float((uint32_t)ix), gy = small_uint_to_float((uint32_t)iy);
+          const bool inx = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[0], gx), __fmul_rn(eb.t[1], gy)), eb.t[2]), wmh, rx);
+          const bool iny = src_raw(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[3], gx), __fmul_rn(eb.t[4], gy)), eb.t[5]), hmh, ry);
+          hit_b = !(inx && iny);
+        } else {
+          hit_b = (iy >= eb.y0) && (iy < eb.y1) && (ix >= eb.x0) && (ix < eb.x1);
+        }
+      }
+      adr[i] = !(hit_a || hit_b) ? base_raw + ry * (uint32_t)pitch + rx * (uint32_t)C : (hit_a ? fa_addr : fb_addr);
+#else
+      if (a_geom) {
+        const float fx = small_uint_to_float((uint32_t)ix);
+        int jx, jy;
+        const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(t0, fx), t1y), t2), W, jx);
+        const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(t3, fx), t4y), t5), H, jy);
+        hit_a = !(inx && iny);
+        ix = jx; iy = jy;
+      } else {
+        hit_a = (iy >= ea.y0) && (iy < ea.y1) && (ix >= ea.x0) && (ix < ea.x1);
+      }
+      if (TWO && !hit_a) {
+        if (b_geom) {
+          const float gx = small_uint_to_float((uint32_t)ix), gy = small_uint_to_float((uint32_t)iy);
+          int jx, jy;
+          const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[0], gx), __fmul_rn(eb.t[1], gy)), eb.t[2]), W, jx);
+          const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[3], gx), __fmul_rn(eb.t[4], gy)), eb.t[5]), H, jy);
+          hit_b = !(inx && iny);
+          ix = jx; iy = jy;
+        } else {
+          hit_b = (iy >= eb.y0) && (iy < eb.y1) && (ix >= eb.x0) && (ix < eb.x1);
+        }
+      }
+      adr[i] = !(hit_a || hit_b) ? c.img + (uint32_t)(iy * pitch + ix * C) : (hit_a ? fa_addr : fb_addr);
+#endif
+      hit |= (hit_a ? 1u : 0u) << i | (hit_b ? 16u : 0u) << i;
+    }
+    uint32_t v[4][C];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(adr[i] + ch);
-      if (!plain) {
-        if (kmode == K_NONE) {
-          if (aff1) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int ch = 0; ch < C; ++ch) v[i][ch] = (v[i][ch] & am1) ^ ac1;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(c.l1a + ch * 256 + v[i][ch]);
-          }
-        } else if (C == 3) {
-          if (use1) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(c.l1a + ch * 256 + v[i][ch]);
-          }
+      for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(adr[i] + ch);
+    if (!plain) {
+      if (kmode == K_NONE) {
+        if (aff1) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            color_pixel_f(small_uint_to_float(v[i][0]), small_uint_to_float(v[i][1 % C]), small_uint_to_float(v[i][2 % C]), f,
-                          v[i][0], v[i][1 % C], v[i][2 % C]);
-          if (!COUNT && use2) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int ch = 0; ch < C; ++ch) v[i][ch] = (v[i][ch] & am1) ^ ac1;
+        } else {
 #pragma unroll
-              for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(c.l2a + ch * 256 + v[i][ch]);
-          }
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(c.l1a + ch * 256 + v[i][ch]);
         }
-        if (!COUNT) {  // the spatial colours already are final colours
+      } else if (C == 3) {
+        if (use1) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const bool ha = (hit >> i) & 1u, hb = (hit >> (4 + i)) & 1u;
-            const uint32_t fillv = ha ? fill_a : fill_b;
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) v[i][ch] = (ha || hb) ? byte_of(fillv, ch) : v[i][ch];
-          }
+            for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(c.l1a + ch * 256 + v[i][ch]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          color_pixel_f(small_uint_to_float(v[i][0]), small_uint_to_float(v[i][1 % C]), small_uint_to_float(v[i][2 % C]), f,
+                        v[i][0], v[i][1 % C], v[i][2 % C]);
+        if (!COUNT && use2) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) v[i][ch] = lds_u8(c.l2a + ch * 256 + v[i][ch]);
         }
       }
-      if (COUNT) {
+      if (!COUNT) {  // the spatial colours already are final colours
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const bool ha = (hit >> i) & 1u, hb = (hit >> (4 + i)) & 1u;
-          if (!(ha || hb)) {
+          const uint32_t fillv = ha ? fill_a : fill_b;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) hist_add(c, ch, v[i][ch]);
-          } else if (ha) {
-            ++n_fill_a;
-          } else {
-            ++n_fill_b;
-          }
+          for (int ch = 0; ch < C; ++ch) v[i][ch] = (ha || hb) ? byte_of(fillv, ch) : v[i][ch];
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int ch = 0; ch < C; ++ch) {
-            const int bi = i * C + ch;
-            const int wi = g * C + (bi >> 2);
-            o[wi] = ((bi & 3) == 0) ? v[i][ch] : put_byte(o[wi], v[i][ch], bi & 3);  // (every v is a zero-extended byte)
-          }
       }
     }
-    if (!COUNT) {
-      uint4* gp = reinterpret_cast<uint4*>(c.dst + ((size_t)y * W + x0) * C);
+    if (COUNT) {
 #pragma unroll
-      for (int qv = 0; qv < UW / 4; ++qv) __stcg(gp + qv, make_uint4(o[4 * qv], o[4 * qv + 1], o[4 * qv + 2], o[4 * qv + 3]));
+      for (int i = 0; i < 4; ++i) {
+        const bool ha = (hit >> i) & 1u, hb = (hit >> (4 + i)) & 1u;
+        if (!(ha || hb)) {
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) hist_add(c, ch, v[i][ch]);
+        } else if (ha) {
+          ++n_fill_a;
+        } else {
+          ++n_fill_b;
+        }
+      }
+    } else {
+      uint32_t o[C];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+          const int bi = i * C + ch;
+          o[bi >> 2] = ((bi & 3) == 0) ? v[i][ch] : put_byte(o[bi >> 2], v[i][ch], bi & 3);  // (every v is a zero-extended byte)
+        }
+      uint32_t* gp = reinterpret_cast<uint32_t*>(c.dst + ((size_t)y * W + x0) * C);
+      if (C == 4) {
+        __stcg(reinterpret_cast<uint4*>(gp), make_uint4(o[0], o[1 % C], o[2 % C], o[3 % C]));
+      } else if (C == 2) {
+        __stcg(reinterpret_cast<uint2*>(gp), make_uint2(o[0], o[1 % C]));
+      } else {
+#pragma unroll
+        for (int w = 0; w < C; ++w) __stcg(gp + w, o[w]);
+      }
+    }
     }
   }
   if (COUNT) {
     if (n_fill_a) atomicAdd(&c.ctl->st.color_cnt[n_sp - 1], n_fill_a);
     if (TWO && n_fill_b) atomicAdd(&c.ctl->st.color_cnt[n_sp - 2], n_fill_b);
   }
+}
+
+// One warp whose source row is the output row shifted by a whole number of rows and whose source column
+// is x + s for a per-row constant s -- ShearX (s = level * y), TranslateX (s = pixels), TranslateY
+// (s = 0) -- K == none.  The exact coordinate of the reference is sx = fl(x + s) (one float32 rounding:
+// the entry has t0 == 1, t3 == 0, t4 == 1 and t1 == 0 or t2 == 0), then round-half-away.  For integer
+// x the value fl(x + s) - x depends only on the binade (and sign) of x + s: the rounding grid 2^(e-23)
+// divides 1, so fl(x + s) = x + rnd_e(s): shifts only change at binade boundaries.  Every pixel still
+// gets its exact index (one add + the index step: 6 instructions instead of the general warp's 16), and
+// a quad whose four indices are consecutive -- all but the quads on a binade boundary or the image
+// border -- is copied as C + 1 aligned words and a funnel shift instead of 4 * C byte loads.
+template <int C, bool COUNT>
+__device__ __forceinline__ void res_gather_rowshift(const RC<C>& c) {
+  const TileState& t = *c.t;
+  const int H = c.H, W = c.W;
+  const Spatial& ea = t.sp[0];
+  const float t1 = ea.t[1], t2 = ea.t[2];
+  const int dy = (int)ea.t[5];
+  const bool use1 = !COUNT && !t.l1_id;
+  const bool aff1 = (t.l1_aff & 0x10000) != 0;
+  const uint32_t am1 = (uint32_t)((t.l1_aff >> 8) & 0xFF) * 0x01010101u, ac1 = (uint32_t)(t.l1_aff & 0xFF) * 0x01010101u;
+  const uint32_t fill_a = c.ctl->fillc[0];  // the entry's final colour bytes
+  const int pitch = c.row;
+  uint32_t n_fill = 0;
+  // the fill quad: colour bytes repeated (C words)
+  uint32_t fq[C];
+#pragma unroll
+  for (int w = 0; w < C; ++w) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) x |= byte_of(fill_a, (4 * w + b) % C) << (8 * b);
+    fq[w] = x;
+  }
+  for (UnitWalk q(c.tid, W >> 2); q.y < H; q.next()) {
+    const int y = q.y, x0 = q.ux << 2;
+    const int iy = y + dy;
+    uint32_t o[C];
+    if ((unsigned)iy >= (unsigned)H) {  // the whole row shows the fill colour
+      if (COUNT) { n_fill += 4; continue; }
+#pragma unroll
+      for (int w = 0; w < C; ++w) o[w] = fq[w];
+    } else {
+      const float fy = small_uint_to_float((uint32_t)y);
+      const float s = (t1 == 0.0f) ? t2 : __fmul_rn(t1, fy);  // (the other term adds +-0)
+      // the exact source column of every pixel: one add and the index step each
+      int j[4];
+      bool in[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) in[i] = src_index(__fadd_rn(small_uint_to_float((uint32_t)(x0 + i)), s), W, j[i]);
+      const bool all_in = in[0] && in[1] && in[2] && in[3];
+      const bool none_in = !(in[0] || in[1] || in[2] || in[3]);
+      if (all_in && j[1] - j[0] == 1 && j[2] - j[0] == 2 && j[3] - j[0] == 3) {
+        // four consecutive source pixels: C + 1 aligned words and a funnel shift
+        const uint32_t a = c.img + (uint32_t)(iy * pitch + j[0] * C);
+        const uint32_t aw = a & ~3u, sh = (a & 3u) * 8u;
+        uint32_t w[C + 1];
+#pragma unroll
+        for (int k = 0; k <= C; ++k) w[k] = lds_u32(aw + 4 * k);  // (the word after the quad may belong to the next row / the pad: its bytes are shifted out)
+#pragma unroll
+        for (int k = 0; k < C; ++k) o[k] = __funnelshift_r(w[k], w[k + 1], sh);
+        if (COUNT) {
+#pragma unroll
+          for (int k = 0; k < C; ++k)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) hist_add(c, (4 * k + b) % C, byte_of(o[k], b));
+          continue;
+        }
+        if (use1) {
+          if (aff1) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) o[k] = (o[k] & am1) ^ ac1;
+          } else {
+#pragma unroll
+            for (int k = 0; k < C; ++k)
+              o[k] = map_word(o[k], c.l1a + ((4 * k + 0) % C) * 256, c.l1a + ((4 * k + 1) % C) * 256, c.l1a + ((4 * k + 2) % C) * 256,
+                              c.l1a + ((4 * k + 3) % C) * 256);
+          }
+        }
+      } else if (none_in) {
+        if (COUNT) { n_fill += 4; continue; }
+#pragma unroll
+        for (int w = 0; w < C; ++w) o[w] = fq[w];
+      } else {
+        // the quad straddles the image border or a float32 binade boundary of x + s: byte gathers
+#pragma unroll
+        for (int k = 0; k < C; ++k) o[k] = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t v[C];
+          if (in[i]) {
+            const uint32_t a = c.img + (uint32_t)(iy * pitch + j[i] * C);
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(a + ch);
+            if (COUNT) {
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) hist_add(c, ch, v[ch]);
+            } else if (use1) {
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(c.l1a + ch * 256 + v[ch]);
+            }
+          } else {
+            if (COUNT) ++n_fill;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) v[ch] = byte_of(fill_a, ch);
+          }
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) {
+            const int bi = i * C + ch;
+            o[bi >> 2] = ((bi & 3) == 0) ? v[ch] : put_byte(o[bi >> 2], v[ch], bi & 3);
+          }
+        }
+        if (COUNT) continue;
+      }
+    }
+    uint32_t* gp = reinterpret_cast<uint32_t*>(c.dst + ((size_t)y * W + x0) * C);
+    if (C == 4) {
+      __stcg(reinterpret_cast<uint4*>(gp), make_uint4(o[0], o[1 % C], o[2 % C], o[3 % C]));
+    } else if (C == 2) {
+      __stcg(reinterpret_cast<uint2*>(gp), make_uint2(o[0], o[1 % C]));
+    } else {
+#pragma unroll
+      for (int w = 0; w < C; ++w) __stcg(gp + w, o[w]);
+    }
+  }
+  if (COUNT && n_fill) atomicAdd(&c.ctl->st.color_cnt[0], n_fill);
+}
+
+// Does the single spatial entry qualify for res_gather_rowshift?
+__device__ __forceinline__ bool is_rowshift(const Spatial& e) {
+  const float t5 = e.t[5];
+  return e.type == SP_GEOM && e.t[0] == 1.0f && e.t[3] == 0.0f && e.t[4] == 1.0f && (e.t[1] == 0.0f || e.t[2] == 0.0f) &&
+         fabsf(t5) < 4194304.0f && t5 == truncf(t5);
 }
 
 // General form: any list of constant-fill warps and masks, K in {none, Color}; one pixel per thread
@@ -482,7 +629,11 @@ __device__ __forceinline__ void res_gather(const RC<C>& c) {
   const TileState& t = *c.t;
   wait_image(c);
   if (COUNT) hist_zero(c);
-  if (t.n_sp == 1 && t.sp[0].type == SP_GEOM) res_gather_fast<C, COUNT, false>(c);
+#ifndef CHB_ROWSHIFT
+#define CHB_ROWSHIFT 1
+#endif
+  if (CHB_ROWSHIFT && t.n_sp == 1 && t.kmode == K_NONE && is_rowshift(t.sp[0])) res_gather_rowshift<C, COUNT>(c);
+  else if (t.n_sp == 1 && t.sp[0].type == SP_GEOM) res_gather_fast<C, COUNT, false>(c);
   else if (t.n_sp == 2) res_gather_fast<C, COUNT, true>(c);
   else res_gather_list<C, COUNT>(c);
   if (COUNT) hist_reduce(c);
@@ -509,8 +660,7 @@ __device__ __forceinline__ void res_bake_l1(const RC<C>& c) {
 }
 
 // Rows per sub-strip so that (word columns x sub-strips) fills the CTA: minimise rounds * (rows + 2).
-// Runs on one thread once per launch (the results live in ResCtl).
-__device__ __forceinline__ int res_sharp_split(int columns, int inner) {
+inline int res_sharp_split(int columns, int inner) {
   if (inner <= 0) return 1;
   int best_s = 1, best_cost = 0x7FFFFFFF;
   for (int S = 1; S <= 64 && S <= inner; ++S) {
@@ -519,6 +669,26 @@ __device__ __forceinline__ int res_sharp_split(int columns, int inner) {
     if (cost < best_cost) { best_cost = cost; best_s = S; }
   }
   return (inner + best_s - 1) / best_s;
+}
+
+// Work splits of the Sharpness executors: they depend only on the shape and the size of the aux
+// region, so the host computes them once per call (KParams::res_*).
+template <int C>
+void resident_splits_c(KParams& p, int aux_bytes) {
+  const int H = p.H, W = p.W;
+  const int wpr = (W * C) >> 2;
+  p.res_sharp_rows = res_sharp_split(wpr, H - 2);
+  const int vpitch = (4 + (W + 1) * C + 3) & ~3;
+  for (int k = 0; k < 2; ++k) {
+    const int vbytes = aux_bytes - (k ? (int)hist_bytes<C>(4) : 0);
+    int band = vbytes / vpitch - 2;
+    if (band < 1) band = 1;
+    const int n_bands = (H + band - 1) / band;  // bands of equal height: the last one is not a sliver
+    band = (H + n_bands - 1) / n_bands;
+    p.res_gs_band[k] = band;
+    const int inner = band < (H - 2 > 1 ? H - 2 : 1) ? band : (H - 2 > 1 ? H - 2 : 1);
+    p.res_gs_rows[k] = res_sharp_split(wpr, inner);
+  }
 }
 
 // tfa.image.sharpness (oracle/ops.py sharpness) down one word column (4 output bytes), streaming: the
@@ -538,10 +708,12 @@ __device__ __forceinline__ void sharp_stream(uint32_t col, int pitch, int n, boo
   const float k1 = __int_as_float(0x3d9d89d9);  // float32(1)/float32(13)
   const float k5 = __int_as_float(0x3ec4ec4f);  // float32(5)/float32(13)
   const float nk1 = -8388608.0f * k1, nk5 = -8388608.0f * k5;  // exact (powers of two)
-  float T[4], A[4], xm_mid[4];
+  float T[4], A[4];
+  uint32_t w_mid = 0;  // centre word of the row whose outputs are being accumulated in A
   float p[NB], xm[4];
+  uint32_t w1 = 0;
   auto load_row = [&](uint32_t ra) {
-    const uint32_t w1 = lds_u32(ra);
+    w1 = lds_u32(ra);
     const uint32_t w0 = has_prev ? lds_u32(ra - 4) : 0u;
     const uint32_t w2 = has_next ? lds_u32(ra + 4) : 0u;
 #pragma unroll
@@ -567,7 +739,7 @@ __device__ __forceinline__ void sharp_stream(uint32_t col, int pitch, int n, boo
         float acc = __fadd_rn(A[b], p[b]);
         acc = __fadd_rn(acc, p[b + C]);
         acc = __fadd_rn(acc, p[b + 2 * C]);
-        const float orig = __fadd_rn(xm_mid[b], -8388608.0f);
+        const float orig = byte_to_float(w_mid, b);
         float deg = __fadd_rn(__fadd_rz(acc, 8388608.0f), -8388608.0f);  // float(trunc(acc))
         deg = ((bmask >> b) & 1u) ? orig : deg;                           // border pixels keep the original
         const uint32_t res = sharp_blend(deg, orig, f);
@@ -582,10 +754,10 @@ __device__ __forceinline__ void sharp_stream(uint32_t col, int pitch, int n, boo
         float acc = __fadd_rn(T[b], p[b]);
         acc = __fadd_rn(acc, __fmaf_rn(xm[b], k5, nk5));
         A[b] = __fadd_rn(acc, p[b + 2 * C]);
-        xm_mid[b] = xm[b];
         // and it is the row above output row r + 1
         T[b] = __fadd_rn(__fadd_rn(p[b], p[b + C]), p[b + 2 * C]);
       }
+      w_mid = w1;
     }
   }
 }
@@ -684,7 +856,66 @@ __device__ __forceinline__ void res_gather_sharp(RC<C> c) {
   };
   for (int ya = 0; ya < H; ya += band) {
     const int yb = min(H, ya + band);
-    // phase 1: virtual pre-image on [-1, W] x [ya-1, yb]
+    // phase 1: virtual pre-image (spatial list -> l1) of rows [ya-1, yb] in the band buffer.  One
+    // spatial entry (all a two-op chain can put in front of Sharpness): four pixels per thread, three
+    // aligned word stores (pixel x sits at byte 4 + C * x of a band row).  The halo columns and the
+    // rows outside the image are never tapped by a pixel whose result is kept (border pixels keep the
+    // original), so they are left as they are.
+    if (one) {
+      const int r0 = max(ya - 1, 0), r1 = min(yb, H - 1);  // rows to fill, inclusive
+      const int qpr = W >> 2;
+      const int nq = (r1 - r0 + 1) * qpr;
+      const uint32_t inv_qpr = (uint32_t)((0x100000000ull + (unsigned)qpr - 1ull) / (unsigned)qpr);
+      for (int i = c.tid; i < nq; i += RNT) {
+        const int ry = (int)__umulhi((uint32_t)i, inv_qpr), qx = i - ry * qpr;
+        const int y = r0 + ry, x0 = qx << 2;
+        const float fy = small_uint_to_float((uint32_t)y);
+        const float t1y = __fmul_rn(e0.t[1], fy), t4y = __fmul_rn(e0.t[4], fy);
+        uint32_t adr[4];
+        uint32_t hitm = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int x = x0 + k;
+          int sx = x, sy = y;
+          bool hit;
+          if (e_geom) {
+            const float fx = small_uint_to_float((uint32_t)x);
+            const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(e0.t[0], fx), t1y), e0.t[2]), W, sx);
+            const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(e0.t[3], fx), t4y), e0.t[5]), H, sy);
+            hit = !(inx && iny);
+          } else {
+            hit = (y >= e0.y0) && (y < e0.y1) && (x >= e0.x0) && (x < e0.x1);
+          }
+          adr[k] = hit ? fill_addr : c.img + (uint32_t)(sy * row + sx * C);
+          hitm |= (hit ? 1u : 0u) << k;
+        }
+        uint32_t v[4][C];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) v[k][ch] = lds_u8(adr[k] + ch);
+        if (use1) {  // (the entry's colour already is a post-l1 value)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+              const uint32_t m = lds_u8(c.l1a + ch * 256 + v[k][ch]);
+              v[k][ch] = ((hitm >> k) & 1u) ? v[k][ch] : m;
+            }
+        }
+        uint32_t o[C];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) {
+            const int bi = k * C + ch;
+            o[bi >> 2] = ((bi & 3) == 0) ? v[k][ch] : put_byte(o[bi >> 2], v[k][ch], bi & 3);
+          }
+        const uint32_t va = vbuf + (uint32_t)((y - (ya - 1)) * vpitch + 4 + x0 * C);
+#pragma unroll
+        for (int w = 0; w < C; ++w) sts_u32(va + 4 * w, o[w]);
+      }
+    } else {
     const int nv = (yb - ya + 2) * vw;
     for (int i = c.tid; i < nv; i += RNT) {
       const int vy = (int)__umulhi((uint32_t)i, inv_vw), vx = i - vy * vw;  // i / vw, exact for i < 2^16 ... 2^22
@@ -693,25 +924,7 @@ __device__ __forceinline__ void res_gather_sharp(RC<C> c) {
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) v[ch] = 0;
       if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) {
-        if (one) {
-          int sx = x, sy = y;
-          bool hit;
-          if (e_geom) {
-            const float fx = small_uint_to_float((uint32_t)x), fy = small_uint_to_float((uint32_t)y);
-            const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(e0.t[0], fx), __fmul_rn(e0.t[1], fy)), e0.t[2]), W, sx);
-            const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(e0.t[3], fx), __fmul_rn(e0.t[4], fy)), e0.t[5]), H, sy);
-            hit = !(inx && iny);
-          } else {
-            hit = (y >= e0.y0) && (y < e0.y1) && (x >= e0.x0) && (x < e0.x1);
-          }
-          const uint32_t a = hit ? fill_addr : c.img + (uint32_t)(sy * row + sx * C);
-#pragma unroll
-          for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(a + ch);
-          if (use1 && !hit) {
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(c.l1a + ch * 256 + v[ch]);
-          }
-        } else {
+        {
           int sx = x, sy = y;
           const int k = resolve(t.sp, n_sp, H, W, sx, sy);
           if (k < 0) {
@@ -731,6 +944,7 @@ __device__ __forceinline__ void res_gather_sharp(RC<C> c) {
       const uint32_t va = vbuf + (uint32_t)(vy * vpitch + 4 - C + vx * C);
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) asm volatile("st.shared.u8 [%0], %1;" ::"r"(va + ch), "r"(v[ch]) : "memory");
+    }
     }
     __syncthreads();
     // phase 2: sharpen W x (yb - ya) pixels out of the halo band
@@ -760,6 +974,130 @@ __device__ __forceinline__ void res_gather_sharp(RC<C> c) {
     __syncthreads();  // the next band overwrites the buffer
   }
   if (COUNT) hist_reduce(c);
+}
+
+// ================================================================ claim order of small batches
+// A CTA works on one image at a time, so a 256-image call is 1.7 images per SM and its duration is the
+// most loaded SM's: which images an SM gets matters more than anything else.  Every CTA therefore
+// decodes the op chain of EVERY image of a small batch (Philox again, or the replayed schedule), turns
+// it into a cost estimate and sorts the images by decreasing cost -- the same order in every CTA, no
+// communication -- and the claim counter indexes that order: the expensive chains (a gathered
+// Sharpness is 10x an Invert) start first, one per SM, and the cheap ones fill the gaps (LPT).
+// Only the ORDER depends on the estimate; the pixels do not.
+__device__ __forceinline__ int chain_cost(const KParams& p, const DevOp* ops, int img) {
+  const unsigned long long own = p.image_index_base + (unsigned long long)img;
+  const unsigned long long stream_img = p.elementwise ? own : ~0ull;
+  const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+  int cost = 0, n_geo = 0, n_mask = 0, k = 0, lut = 0;  // k: 0 none, 1 Color, 2 Sharpness (spatial list frozen)
+  for (int i = 0; i < p.n_draws; ++i) {
+    const int slot0 = i * (p.K + 1);
+    const size_t rbase = ((size_t)img * p.n_draws + i) * p.K * CHB_SCHED_FIELDS;
+    int choice;
+    if (p.replay) {
+      choice = p.replay[rbase];
+      if (choice < 0 || choice >= p.T) choice = 0;
+    } else {
+      choice = (int)__umulhi(philox4x32_10(make_uint4((uint32_t)stream_img, (uint32_t)(stream_img >> 32), p.call_counter, (uint32_t)slot0), key).x,
+                             (uint32_t)p.T);
+    }
+    for (int j = 0; j < p.K; ++j) {
+      const DevOp& op = ops[choice * p.K + j];
+      const int kind = op.kind;
+      bool applied;
+      if (p.replay) {
+        applied = p.replay[rbase + (size_t)j * CHB_SCHED_FIELDS + 1] != 0 && kind >= 0;
+      } else {
+        const uint32_t r = philox4x32_10(make_uint4((uint32_t)stream_img, (uint32_t)(stream_img >> 32), p.call_counter,
+                                                    (uint32_t)(slot0 + 1 + j)), key).x;
+        applied = kind >= 0 && (int)(r >> 8) < op.thr24;
+      }
+      if (!applied) continue;
+      const bool spatial = n_geo + n_mask > 0;
+      switch (kind) {
+        case CHB_OP_AUTOCONTRAST: case CHB_OP_EQUALIZE:
+          cost += (kind == CHB_OP_EQUALIZE ? 14 : 12) + (k == 2 ? (spatial ? 40 : 22) : 0) + 7 * n_geo + (k == 1 ? 8 : 0);
+          break;
+        case CHB_OP_COLOR:
+          if (op.blend_mode == BLEND_IMAGE2) break;
+          if (k != 0) { cost += 6; n_geo = n_mask = 0; }
+          k = 1; cost += 8;
+          break;
+        case CHB_OP_SHARPNESS:
+          if (op.blend_mode == BLEND_IMAGE2) break;
+          if (k != 0) { cost += 6; n_geo = n_mask = 0; }
+          k = 2; cost += (n_geo + n_mask > 0) ? 36 : 22;
+          break;
+        case CHB_OP_CUTOUT:
+          if (k == 2) { cost += 8; k = 0; n_geo = 0; n_mask = 0; }
+          ++n_mask; cost += (n_geo > 0) ? 8 : 3;
+          break;
+        case CHB_OP_SHEAR_X: case CHB_OP_SHEAR_Y: case CHB_OP_TRANSLATE_X: case CHB_OP_TRANSLATE_Y: case CHB_OP_ROTATE:
+          if (k == 2) { cost += 8; k = 0; n_geo = 0; n_mask = 0; }
+          ++n_geo; cost += (n_geo + n_mask > 1) ? 12 : 6;
+          break;
+        case CHB_OP_INVERT: case CHB_OP_POSTERIZE: case CHB_OP_SOLARIZE:
+          break;
+        default:  // Brightness, Contrast, SolarizeAdd: table lookups
+          if (!lut) { lut = 1; cost += 5; }
+          break;
+      }
+    }
+  }
+  return cost;
+}
+
+// Fills ctl->order for a batch of B <= LPT_MAX images.  `scratch`: 64 x 64 uint16 + 64 int of shared memory.
+__device__ void plan_order(const KParams& p, const DevOp* ops, ResCtl* ctl, uint16_t* scratch, int tid) {
+  constexpr int NBK = 64;                       // cost buckets (bucket 0 = most expensive)
+  const int B = p.B;
+  const int lane = tid & 31;
+  for (int i = tid; i < NBK * NBK; i += RNT) scratch[i] = 0;
+  __syncthreads();
+  // pass 1: bucket of every image; count per (32-image chunk, bucket)
+  int bk[LPT_MAX / RNT];
+#pragma unroll
+  for (int r = 0; r < LPT_MAX / RNT; ++r) {
+    const int i = r * RNT + tid;
+    bk[r] = 0;
+    if (i < B) {
+      int cst = chain_cost(p, ops, i);
+      bk[r] = NBK - 1 - min(cst >> 1, NBK - 1);
+      atomicAdd(reinterpret_cast<unsigned int*>(scratch) + (((i >> 5) * NBK + bk[r]) >> 1), (((i >> 5) * NBK + bk[r]) & 1) ? 0x10000u : 1u);
+    }
+  }
+  __syncthreads();
+  // exclusive prefix over (bucket major, chunk minor): thread b scans bucket b's chunks, then the bucket totals are scanned
+  const int n_chunks = (B + 31) >> 5;
+  int* bucket_total = reinterpret_cast<int*>(scratch + NBK * NBK);  // (no static shared memory: the kernel takes the SM's whole carve-out dynamically)
+  if (tid < NBK) {
+    int run = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int v = scratch[ch * NBK + tid];
+      scratch[ch * NBK + tid] = (uint16_t)run;
+      run += v;
+    }
+    bucket_total[tid] = run;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int b = 0; b < NBK; ++b) { const int v = bucket_total[b]; bucket_total[b] = run; run += v; }
+  }
+  __syncthreads();
+  // pass 2: position = bucket start + images of the bucket in earlier chunks + rank among the chunk's lanes
+#pragma unroll
+  for (int r = 0; r < LPT_MAX / RNT; ++r) {
+    const int i = r * RNT + tid;
+    const bool valid = i < B;
+    const unsigned act = __ballot_sync(0xFFFFFFFFu, valid);
+    if (valid) {
+      const unsigned same = __match_any_sync(act, bk[r]);
+      const int rank = __popc(same & ((1u << lane) - 1u));
+      const int pos = bucket_total[bk[r]] + scratch[(i >> 5) * NBK + bk[r]] + rank;
+      ctl->order[pos] = (uint16_t)i;
+    }
+  }
+  __syncthreads();
 }
 
 // ================================================================================= the kernel
@@ -808,25 +1146,14 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
     for (int k = 0; k < RES_MAXCHUNK; ++k) mbar_init(c.full0 + 8 * k, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
-    // shape-only work splits
-    const int wpr = (W * C) >> 2;
-    ctl->sharp_rows = res_sharp_split(wpr, H - 2);
-    const int vpitch = (4 + (W + 1) * C + 3) & ~3;
-    for (int k = 0; k < 2; ++k) {
-      const int vbytes = c.aux_bytes - (k ? (int)hist_bytes<C>(4) : 0);
-      int band = max(1, vbytes / vpitch - 2);
-      // whole bands of equal height: the last band is not a sliver
-      const int n_bands = (H + band - 1) / band;
-      band = (H + n_bands - 1) / n_bands;
-      ctl->gs_band[k] = band;
-      ctl->gs_rows[k] = res_sharp_split(wpr, min(band, max(H - 2, 1)));
-    }
-    ctl->n_prefetched = 0;
+    // shape-only work splits (computed on the host, resident_splits)
+    ctl->sharp_rows = p.res_sharp_rows;
+    for (int k = 0; k < 2; ++k) { ctl->gs_band[k] = p.res_gs_band[k]; ctl->gs_rows[k] = p.res_gs_rows[k]; }
   }
   // Programmatic dependent launch: nothing the previous kernel of the stream wrote (the images, a
   // replayed schedule, the policy table, the work counter it left zeroed) is touched before it has completed.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (tid == 0) ctl->next_img = (int)atomicAdd(p.counters, 1u);
+  if (tid == 0) ctl->next_img = (int)atomicAdd(p.counters, 1u);  // a claim POSITION (see plan_order)
   // the policy table comes to shared memory once: the chain walk of every image reads it many times
   DevOp* s_ops = reinterpret_cast<DevOp*>(smem_raw + pol_off);
   uint8_t* s_optab = smem_raw + pol_off + (size_t)n_pol * sizeof(DevOp);
@@ -841,24 +1168,39 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   }
   const KParams& pl = ctl->kp;
   __syncthreads();
-  int img = ctl->next_img;
+  // small batches: positions map to images through the cost-sorted order (all images share one chain in
+  // batch mode: nothing to sort)
+  const bool lpt = p.B <= LPT_MAX && p.B > (int)gridDim.x && p.elementwise && p.res_lpt;
+  if (lpt) plan_order(pl, s_ops, ctl, reinterpret_cast<uint16_t*>(smem_raw + aux_off), tid);
+  auto image_of = [&](int pos) { return (lpt && pos < p.B) ? (int)ctl->order[pos] : pos; };
+  int img = image_of(ctl->next_img);
   uint8_t* scratch = p.scratch + (size_t)blockIdx.x * p.scratch_stride;
-  // chunk k is issued by thread k (each arrives on its own barrier); chunks below `first` are already in flight
-  auto issue_load = [&](const uint8_t* src, int first) {
-    if (tid >= first && tid < n_chunks) {
-      const uint32_t bytes = (uint32_t)min(RES_CHUNK, img_bytes - tid * RES_CHUNK);
-      mbar_arrive_expect_tx(c.full0 + 8 * tid, bytes);
-      bulk_load(c.img + (uint32_t)tid * RES_CHUNK, src + (size_t)tid * RES_CHUNK, bytes, c.full0 + 8 * tid);
+  // Thread 0 issues the chunks IN ORDER: the executors consume them front to back, and chunks issued
+  // by different lanes of a warp were served in an order that made every step of a flat image wait for
+  // the tail of the load (profiles/r02_v2_ab_notes.txt: identity 102 % -> 79 % of the copy peak).
+  auto issue_load = [&](const uint8_t* src) {
+    if (tid == 0) {
+      for (int k = 0; k < n_chunks; ++k) {
+        const uint32_t bytes = (uint32_t)min(RES_CHUNK, img_bytes - k * RES_CHUNK);
+        mbar_arrive_expect_tx(c.full0 + 8 * k, bytes);
+        bulk_load(c.img + (uint32_t)k * RES_CHUNK, src + (size_t)k * RES_CHUNK, bytes, c.full0 + 8 * k);
+      }
     }
   };
+#ifdef CHB_TIMELINE
+  // debug builds: one record of 4 words per processed image -- (cta << 32 | image), start, first pass start, end
+  // (ns, %globaltimer) -- appended to KParams::timeline; word 0 counts the records, words 1-3: kernel entry of
+  // the first CTA to get there, unused, unused.
+  unsigned long long tl_t0 = 0, tl_t1 = 0;
+  if (p.timeline && tid == 0) atomicMin(p.timeline + 1, tl_now());
+#endif
   while (img < p.B) {
+#ifdef CHB_TIMELINE
+    if (tid == 0) tl_t0 = tl_now();
+#endif
     c.par ^= 1u;
-    issue_load(p.in + (size_t)img * img_bytes, ctl->n_prefetched);  // (a flat predecessor already issued some or all)
-    __syncthreads();
-    if (tid == 0) {
-      ctl->n_prefetched = 0;
-      ctl->n_claimed = (int)atomicAdd(p.counters, 1u);  // the next image: the round trip hides behind this one
-    }
+    issue_load(p.in + (size_t)img * img_bytes);
+    if (tid == 0) ctl->n_claimed = (int)atomicAdd(p.counters, 1u);  // the next image: the round trip hides behind this one
     // schedule decode + chain walk up to the first pass (the loads are in flight)
     for (int i = tid; i < STATE_VECS; i += RNT) reinterpret_cast<uint4*>(&ctl->st)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
@@ -867,6 +1209,9 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
     __syncthreads();
     advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
     uint8_t* out_img = p.out + (size_t)img * img_bytes;
+#ifdef CHB_TIMELINE
+    if (tid == 0) tl_t1 = tl_now();
+#endif
     for (;;) {
       const TileState& t = ctl->st.t;
       const int pass_kind = t.pass_kind;
@@ -904,7 +1249,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
         fence_proxy_async_all();
         __syncthreads();
         c.par ^= 1u;
-        issue_load(scratch, 0);
+        issue_load(scratch);
       }
       reset_view(&ctl->st, tid, RNT);
       __syncthreads();
@@ -915,7 +1260,16 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
     fence_proxy_async();
     if (tid == 0) bulk_wait_read0();
     __syncthreads();
-    img = ctl->n_claimed;
+#ifdef CHB_TIMELINE
+    if (p.timeline && tid == 0) {
+      const unsigned long long slot = atomicAdd(p.timeline, 1ull);
+      if (slot < 8000ull) {
+        unsigned long long* r = p.timeline + 4 + slot * 4;
+        r[0] = ((unsigned long long)blockIdx.x << 32) | (unsigned)img; r[1] = tl_t0; r[2] = tl_t1; r[3] = tl_now();
+      }
+    }
+#endif
+    img = image_of(ctl->n_claimed);
     __syncthreads();
   }
   if (tid == 0) {

@@ -206,3 +206,65 @@ def test_concurrent_streams_and_repeatability(A):
             torch.cuda.synchronize()
             for c in range(4):
                 assert torch.equal(ys[c], ref[c])
+
+
+def test_row_shift_warps(A):
+    """ShearX / TranslateX / TranslateY run as shifted copies (res_gather_rowshift) wherever four pixels
+    share one exact shift: integral and half-integral shifts, shifts beyond the image, levels whose
+    per-row offsets cross float32 binade boundaries, a LUT in front, a histogram op behind (the COUNT
+    form), three image widths.  Oracle on identical schedules, and the tile engine."""
+    kw = dict(interpolation="nearest", fill_mode="constant", fill_value=128.0)
+    singles = ([A.ShearX(l, **kw) for l in (0.3, 0.44999999999999996, 0.07, 1.3, 3.0, 0.0)] +
+               [A.TranslateX(p, **kw) for p in (100.0, 12.5, 0.5, 1.0, 223.0, 224.0, 300.0, 7.25)] +
+               [A.TranslateY(p, **kw) for p in (17.0, 12.5, 250.0, 0.0, 1.0)])
+    chains = [A.Sequential([A.Brightness(1.9), A.ShearX(0.3, **kw)]), A.Sequential([A.TranslateX(33.0, **kw), A.Equalize()]),
+              A.Sequential([A.ShearX(0.21, **kw), A.AutoContrast(), A.Invert()]), A.Sequential([A.Solarize(77), A.TranslateY(9.0, **kw), A.Posterize(3)]),
+              A.Sequential([A.TranslateX(40.0, **kw), A.CutOut(20, 7)]), A.Sequential([A.ShearX(0.3, **kw), A.Sharpness(1.9)]),
+              A.Sequential([A.TranslateY(5.0, **kw), A.Color(1.9)])]
+    transforms = singles + chains
+    for shape in ((16, 16), (224, 224), (100, 256)):
+        B = 2 * len(transforms)
+        x = random_images(B, shape[0], shape[1], 3, seed=shape[1], kind="uniform")
+        s = np.zeros((B, 1, 4, 5), np.int32)
+        s[:, 0, :, 0] = np.repeat(np.arange(len(transforms)), 2)[:, None]
+        s[..., 1] = 1
+        s[1::2, :, :, 2] = 1                       # second copy of every transform: negated sign
+        s[..., 3] = 3; s[..., 4] = 5
+        layer = A.RandomChoice([t if isinstance(t, A.Sequential) else A.Sequential([t]) for t in transforms], 1, elementwise=True)
+        # pad every transform to K = 4 sub-op slots: the schedule rows of the missing ops are ignored
+        r, t = both_engines(layer, to_gpu(x), replay=_fit(s, layer))
+        same = (r == t).flatten(1).all(dim=1).cpu().numpy()
+        assert same.all(), "resident != tiles for transforms %r" % (np.nonzero(~same)[0] // 2,)
+        sched = _fit(s, layer)
+        want = oracle.apply_schedule(x, policy_of(layer), sched, elementwise=True)
+        got = r.cpu().numpy()
+        for b in range(B):
+            assert_same(got[b], want[b], "transform %d (%s) negate=%d shape %r" % (b // 2, type(transforms[b // 2]).__name__, b % 2, shape))
+
+
+def _fit(s, layer):
+    """Schedule with as many sub-op slots as the layer's widest transform."""
+    from chambers_b200.augmentations.image_augmentations import _flatten_transform
+    K = max(len(_flatten_transform(t)) for t in layer.transforms)
+    return np.ascontiguousarray(s[:, :, :K])
+
+
+def test_small_batch_claim_order(A):
+    """Batches of up to 2048 images are claimed most-expensive-chain-first (plan_order): the order is an
+    internal schedule, so results must not depend on it -- device coins and replay, batch sizes around
+    the CTA count and the 1024 / 2048 thresholds, against the tile engine and the oracle."""
+    layer = A.RandAugment(2, 10, elementwise=True)
+    for B in (149, 256, 300, 1023, 1025, 2048, 2049):
+        x = random_images(B, 32, 48, 3, seed=B)
+        xg = to_gpu(x)
+        with engine("resident"):
+            y = layer(xg, training=True, seed=B, call_counter=1, record=True)
+            sched = layer.last_schedule
+            y2 = layer(xg, training=True, replay=sched)
+        assert torch.equal(y, y2), "replay differs from device coins at B=%d" % B
+        with engine("tiles"):
+            t = layer(xg, training=True, replay=sched)
+        assert torch.equal(y, t), "resident != tiles at B=%d" % B
+        idx = list(range(0, B, max(1, B // 40)))
+        want = oracle.apply_schedule(x[idx], policy_of(layer), sched[idx], elementwise=True)
+        assert_same(y[idx].cpu().numpy(), want, "B=%d" % B)
