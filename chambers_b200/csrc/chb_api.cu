@@ -673,6 +673,7 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     p.counters = ws->counters;
     p.res_smem_bytes = ctx->res_smem;
     p.res_lpt = g_lpt;
+    p.res_rules = 1;
     p.timeline = ctx->timeline;
     {
       const size_t fixed = chb::resident_ctl_bytes() + (pe->host.size() * (sizeof(DevOp) + 256) + 127) / 128 * 128 +

@@ -115,6 +115,7 @@ struct KParams {
   unsigned long long* timeline;       // debug builds (-DCHB_TIMELINE): [1024 CTAs][2][16] words, else NULL
   int res_smem_bytes;                 // resident engine: dynamic shared memory of a CTA (control + policy + image + aux region)
   int res_lpt;                        //   1: small batches are claimed most-expensive-chain-first (CHB_LPT=0 disables)
+  int res_rules;                      //   1: advance() materialises non-flat views in front of Sharpness / a histogram op
   int res_sharp_rows;                 //   Sharpness: rows per sub-strip of the column walk
   int res_gs_band[2], res_gs_rows[2]; //   gathered Sharpness (WRITE / COUNT): output rows per band, rows per sub-strip
 };

@@ -332,13 +332,19 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
         s->next_op = pi + 1;
       }
     } else if (kind == CHB_OP_EQUALIZE || kind == CHB_OP_AUTOCONTRAST) {
-      if (!hist_valid) {
+      if (!hist_valid && p.res_rules && (kmode != K_NONE || n_sp > 0)) {
+        // resident engine: the histogram of a view that holds a warp, a mask, Color or Sharpness is taken
+        // while that view is MATERIALISED (one evaluation of the expensive part, tallied on the fly or by a
+        // flat COUNT pass afterwards) instead of evaluating it once to count and once more to write
+        boundary = true;
+      } else if (!hist_valid) {
         // the histogram of the virtual image is needed: run a COUNT pass, then come back here.
         for (int t = tid; t < MAXC * 256; t += nt) (&g->hist[0][0])[t] = 0u;
         if (tid < CHB_MAX_CHAIN) s->color_cnt[tid] = 0u;
         if (tid == 0) { s->t.pass_kind = PASS_COUNT; s->tiles_done = 0u; }
         break;
       }
+      if (!boundary) {
       // s->hist counts the values entering the last LUT; map them through it, add the spatial colours.
       for (int t = tid; t < MAXC * 256; t += nt) hmap[t] = 0u;
       sync();
@@ -365,6 +371,7 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
         if (kmode == K_NONE) s->t.l1_id = 0; else s->t.l2_id = 0;
         s->next_op = pi + 1;
       }
+      }
     } else if (kind == CHB_OP_COLOR) {
       const int mode = CHB_LDP(&op->blend_mode);
       if (mode == BLEND_IMAGE2 || C != 3) {  // factor 1: blend returns the image itself (:30-31)
@@ -385,6 +392,11 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
       const int mode = CHB_LDP(&op->blend_mode);
       if (mode == BLEND_IMAGE2) {
         if (tid == 0) s->next_op = pi + 1;
+      } else if (kmode == K_NONE && p.res_rules && n_sp > 0) {
+        // resident engine: Sharpness of a warped / masked view runs on the materialised view (a gather
+        // into the scratch image or a paint in place, then the plain row walk) -- cheaper than gathering
+        // a halo band per strip
+        boundary = true;
       } else if (kmode == K_NONE) {
         if (tid == 0) {
           s->t.kmode = K_SHARP;

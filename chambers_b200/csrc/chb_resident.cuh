@@ -24,7 +24,7 @@
 // rows are whole 16-byte units, every geometric op is nearest / constant-fill (what the policies
 // use, augmentation_schemes.py:7-9).  Everything else stays on the tile engine (chb_kernels.cuh).
 #pragma once
-#define RES_CHUNK_BYTES 12288
+#define RES_CHUNK_BYTES 49152
 // the policy table is staged in shared memory: plain loads (see chb_kernels.cuh)
 #define CHB_LDP(ptr) (*(ptr))
 #include "chb_kernels.cuh"
@@ -36,9 +36,10 @@ namespace {
 #define CHB_RNT 1024
 #endif
 constexpr int RNT = CHB_RNT;           // threads of a resident CTA (1024: 32 warps, 64 registers each)
-static_assert(RNT % 256 == 0 && (RNT * 48) % RES_CHUNK_BYTES == 0, "a flat step must be a whole number of load chunks");
-constexpr int RES_CHUNK = RES_CHUNK_BYTES;       // bytes per load chunk: 256 units of 48 bytes / 768 of 16
-constexpr int RES_MAXCHUNK = 16;       // -> images of up to 192 KB
+static_assert(RNT % 256 == 0, "whole warps, and flat steps of whole 16-byte units");
+constexpr int RES_CHUNK = RES_CHUNK_BYTES;       // bytes per load chunk: one flat step of 1024 48-byte units (issuing a bulk copy costs
+                                                 // the issuing thread ~150 ns: 13 chunks of 12 KB were 2 us of every image's start-up)
+constexpr int RES_MAXCHUNK = 4;        // -> images of up to 192 KB
 constexpr int RES_MIN_AUX = 16 * 1024;
 constexpr int LPT_MAX = 2048;          // batches up to this size are claimed longest-chain-first
 
@@ -75,6 +76,7 @@ struct RC {
   uint32_t hcopy;      // shared address of this lane's histogram copy (word 0)
   int ncopy;           // histogram copies: 32, 16, 8 or 4
   uint32_t hshift;     // log2(ncopy * 4): byte shift of a counter-pair row
+  int tally;           // WRITE pass: also count the bytes written (the materialised view feeds a histogram op next)
 };
 
 // Histogram of a COUNT pass: `ncopy` copies of packed 16-bit counters in the aux region, copy =
@@ -410,6 +412,12 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
         }
       }
     } else {
+      if (c.tally) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) hist_add(c, ch, v[i][ch]);
+      }
       uint32_t o[C];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -548,6 +556,12 @@ __device__ __forceinline__ void res_gather_rowshift(const RC<C>& c) {
         if (COUNT) continue;
       }
     }
+    if (!COUNT && c.tally) {
+#pragma unroll
+      for (int k = 0; k < C; ++k)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) hist_add(c, (4 * k + b) % C, byte_of(o[k], b));
+    }
     uint32_t* gp = reinterpret_cast<uint32_t*>(c.dst + ((size_t)y * W + x0) * C);
     if (C == 4) {
       __stcg(reinterpret_cast<uint4*>(gp), make_uint4(o[0], o[1 % C], o[2 % C], o[3 % C]));
@@ -617,6 +631,10 @@ __device__ __forceinline__ void res_gather_list(const RC<C>& c) {
       }
     }
     if (!COUNT) {
+      if (c.tally) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) hist_add(c, ch, v[ch] & 255u);
+      }
       uint8_t* d = c.dst + (size_t)i * C;
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) d[ch] = (uint8_t)v[ch];
@@ -783,6 +801,10 @@ __device__ __forceinline__ void res_sharp(const RC<C>& c) {
       if (use2)
         o = map_word(o, c.l2a + (uint32_t)((ph + 0) % C) * 256u, c.l2a + (uint32_t)((ph + 1) % C) * 256u,
                      c.l2a + (uint32_t)((ph + 2) % C) * 256u, c.l2a + (uint32_t)((ph + 3) % C) * 256u);
+      if (c.tally) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) hist_add(c, (ph + b) % C, byte_of(o, b));
+      }
       __stcg(reinterpret_cast<uint32_t*>(c.dst + (size_t)y * row) + xw, o);
     }
   };
@@ -813,169 +835,6 @@ __device__ __forceinline__ void res_sharp(const RC<C>& c) {
   if (COUNT) hist_reduce(c);
 }
 
-// K == Sharpness with a spatial list pending (e.g. Rotate -> Sharpness): the virtual pre-image
-// (spatial list -> l1) of a band of rows plus one halo row each side is gathered from the resident
-// source into the aux region, then sharpened from there with the column walk.  A halo row is laid
-// out so that the row's first pixel starts on a word: 4 - C pad bytes, the left halo pixel, the
-// row, the right halo pixel.
-template <int C, bool COUNT>
-__device__ __forceinline__ void res_gather_sharp(RC<C> c) {
-  wait_image(c);
-  const TileState& t = *c.t;
-  const int H = c.H, W = c.W, row = c.row;
-  const int n_sp = t.n_sp;
-  const bool use1 = !t.l1_id, use2 = !t.l2_id;
-  const float f = t.kfactor;
-  const int vw = W + 2;
-  const int vpitch = (4 + (W + 1) * C + 3) & ~3;
-  uint32_t vbuf = c.aux;
-  if (COUNT) {  // four histogram copies in front of the band buffer
-    c.ncopy = 4; c.hshift = 4u; c.hcopy = c.aux + (uint32_t)(c.lane & 3) * 4u;
-    hist_zero(c);
-    vbuf += hist_bytes<C>(4);
-  }
-  const int band = c.ctl->gs_band[COUNT ? 1 : 0];  // output rows per band (aux capacity)
-  const int band_rows = c.ctl->gs_rows[COUNT ? 1 : 0];
-  const int wpr = row >> 2;
-  const Spatial& e0 = t.sp[0];
-  const bool one = (n_sp == 1);
-  const bool e_geom = e0.type == SP_GEOM;
-  const uint32_t fill_addr = smem_addr(&c.ctl->fillc[0]);
-  const uint32_t inv_vw = (uint32_t)((0x100000000ull + (unsigned)vw - 1ull) / (unsigned)vw);
-  auto emit = [&](int y, int xw, uint32_t o) {
-    const int ph = (C == 3) ? (xw % 3) : 0;
-    if (COUNT) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b) hist_add(c, (ph + b) % C, byte_of(o, b));
-    } else {
-      if (use2)
-        o = map_word(o, c.l2a + (uint32_t)((ph + 0) % C) * 256u, c.l2a + (uint32_t)((ph + 1) % C) * 256u,
-                     c.l2a + (uint32_t)((ph + 2) % C) * 256u, c.l2a + (uint32_t)((ph + 3) % C) * 256u);
-      __stcg(reinterpret_cast<uint32_t*>(c.dst + (size_t)y * row) + xw, o);
-    }
-  };
-  for (int ya = 0; ya < H; ya += band) {
-    const int yb = min(H, ya + band);
-    // phase 1: virtual pre-image (spatial list -> l1) of rows [ya-1, yb] in the band buffer.  One
-    // spatial entry (all a two-op chain can put in front of Sharpness): four pixels per thread, three
-    // aligned word stores (pixel x sits at byte 4 + C * x of a band row).  The halo columns and the
-    // rows outside the image are never tapped by a pixel whose result is kept (border pixels keep the
-    // original), so they are left as they are.
-    if (one) {
-      const int r0 = max(ya - 1, 0), r1 = min(yb, H - 1);  // rows to fill, inclusive
-      const int qpr = W >> 2;
-      const int nq = (r1 - r0 + 1) * qpr;
-      const uint32_t inv_qpr = (uint32_t)((0x100000000ull + (unsigned)qpr - 1ull) / (unsigned)qpr);
-      for (int i = c.tid; i < nq; i += RNT) {
-        const int ry = (int)__umulhi((uint32_t)i, inv_qpr), qx = i - ry * qpr;
-        const int y = r0 + ry, x0 = qx << 2;
-        const float fy = small_uint_to_float((uint32_t)y);
-        const float t1y = __fmul_rn(e0.t[1], fy), t4y = __fmul_rn(e0.t[4], fy);
-        uint32_t adr[4];
-        uint32_t hitm = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int x = x0 + k;
-          int sx = x, sy = y;
-          bool hit;
-          if (e_geom) {
-            const float fx = small_uint_to_float((uint32_t)x);
-            const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(e0.t[0], fx), t1y), e0.t[2]), W, sx);
-            const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(e0.t[3], fx), t4y), e0.t[5]), H, sy);
-            hit = !(inx && iny);
-          } else {
-            hit = (y >= e0.y0) && (y < e0.y1) && (x >= e0.x0) && (x < e0.x1);
-          }
-          adr[k] = hit ? fill_addr : c.img + (uint32_t)(sy * row + sx * C);
-          hitm |= (hit ? 1u : 0u) << k;
-        }
-        uint32_t v[4][C];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int ch = 0; ch < C; ++ch) v[k][ch] = lds_u8(adr[k] + ch);
-        if (use1) {  // (the entry's colour already is a post-l1 value)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-              const uint32_t m = lds_u8(c.l1a + ch * 256 + v[k][ch]);
-              v[k][ch] = ((hitm >> k) & 1u) ? v[k][ch] : m;
-            }
-        }
-        uint32_t o[C];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int ch = 0; ch < C; ++ch) {
-            const int bi = k * C + ch;
-            o[bi >> 2] = ((bi & 3) == 0) ? v[k][ch] : put_byte(o[bi >> 2], v[k][ch], bi & 3);
-          }
-        const uint32_t va = vbuf + (uint32_t)((y - (ya - 1)) * vpitch + 4 + x0 * C);
-#pragma unroll
-        for (int w = 0; w < C; ++w) sts_u32(va + 4 * w, o[w]);
-      }
-    } else {
-    const int nv = (yb - ya + 2) * vw;
-    for (int i = c.tid; i < nv; i += RNT) {
-      const int vy = (int)__umulhi((uint32_t)i, inv_vw), vx = i - vy * vw;  // i / vw, exact for i < 2^16 ... 2^22
-      const int y = ya - 1 + vy, x = vx - 1;
-      uint32_t v[C];
-#pragma unroll
-      for (int ch = 0; ch < C; ++ch) v[ch] = 0;
-      if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) {
-        {
-          int sx = x, sy = y;
-          const int k = resolve(t.sp, n_sp, H, W, sx, sy);
-          if (k < 0) {
-            const uint32_t a = c.img + (uint32_t)(sy * row + sx * C);
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(a + ch);
-            if (use1) {
-#pragma unroll
-              for (int ch = 0; ch < C; ++ch) v[ch] = lds_u8(c.l1a + ch * 256 + v[ch]);
-            }
-          } else {
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) v[ch] = (uint32_t)t.sp[k].color[ch];
-          }
-        }
-      }
-      const uint32_t va = vbuf + (uint32_t)(vy * vpitch + 4 - C + vx * C);
-#pragma unroll
-      for (int ch = 0; ch < C; ++ch) asm volatile("st.shared.u8 [%0], %1;" ::"r"(va + ch), "r"(v[ch]) : "memory");
-    }
-    }
-    __syncthreads();
-    // phase 2: sharpen W x (yb - ya) pixels out of the halo band
-    for (int y = ya; y < yb; ++y)
-      if (y == 0 || y == H - 1)
-        for (int xw = c.tid; xw < wpr; xw += RNT) emit(y, xw, lds_u32(vbuf + (uint32_t)((y - ya + 1) * vpitch + 4 + (xw << 2))));
-    const int in0 = max(ya, 1), in1 = min(yb, H - 1);
-    const int inner = in1 - in0;
-    if (inner > 0) {
-      const int R = band_rows;
-      const int n_strips = (inner + R - 1) / R;
-      const int n_items = wpr * n_strips;
-      for (int item = c.tid; item < n_items; item += RNT) {
-        const int strip = item / wpr, xw = item - strip * wpr;
-        const int y_begin = in0 + strip * R, y_end = min(in1, y_begin + R);
-        uint32_t bmask = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int xb = (xw << 2) + b;
-          if (xb < C || xb >= row - C) bmask |= 1u << b;
-        }
-        const uint32_t col = vbuf + (uint32_t)((y_begin - 1 - (ya - 1)) * vpitch + 4 + (xw << 2));
-        sharp_stream<C>(col, vpitch, y_end - y_begin, true, true, bmask, f,
-                        [&](int r, uint32_t o) { emit(y_begin + r, xw, o); });
-      }
-    }
-    __syncthreads();  // the next band overwrites the buffer
-  }
-  if (COUNT) hist_reduce(c);
-}
-
 // ================================================================ claim order of small batches
 // A CTA works on one image at a time, so a 256-image call is 1.7 images per SM and its duration is the
 // most loaded SM's: which images an SM gets matters more than anything else.  Every CTA therefore
@@ -988,7 +847,7 @@ __device__ __forceinline__ int chain_cost(const KParams& p, const DevOp* ops, in
   const unsigned long long own = p.image_index_base + (unsigned long long)img;
   const unsigned long long stream_img = p.elementwise ? own : ~0ull;
   const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-  int cost = 0, n_geo = 0, n_mask = 0, k = 0, lut = 0;  // k: 0 none, 1 Color, 2 Sharpness (spatial list frozen)
+  int cost = 8, n_geo = 0, n_mask = 0, k = 0, lut = 0;  // k: 0 none, 1 Color, 2 Sharpness (spatial list frozen)
   for (int i = 0; i < p.n_draws; ++i) {
     const int slot0 = i * (p.K + 1);
     const size_t rbase = ((size_t)img * p.n_draws + i) * p.K * CHB_SCHED_FIELDS;
@@ -1012,28 +871,32 @@ __device__ __forceinline__ int chain_cost(const KParams& p, const DevOp* ops, in
         applied = kind >= 0 && (int)(r >> 8) < op.thr24;
       }
       if (!applied) continue;
-      const bool spatial = n_geo + n_mask > 0;
+      // rough per-image microseconds at 224 x 224 x 3 (profiles/r02_v3_timeline_256.txt), following the rules
+      // of the chain walk: what forces a materialisation, what is evaluated once in the last pass
       switch (kind) {
         case CHB_OP_AUTOCONTRAST: case CHB_OP_EQUALIZE:
-          cost += (kind == CHB_OP_EQUALIZE ? 14 : 12) + (k == 2 ? (spatial ? 40 : 22) : 0) + 7 * n_geo + (k == 1 ? 8 : 0);
+          if (n_geo > 0 || k == 2) cost += 12;            // tallied while materialised, reload, flat apply
+          else if (n_mask > 0 || k == 1) cost += 20;      // in place, flat COUNT, flat apply
+          else cost += 17;                                // flat COUNT, flat apply
+          n_geo = n_mask = 0; k = 0;
           break;
         case CHB_OP_COLOR:
           if (op.blend_mode == BLEND_IMAGE2) break;
-          if (k != 0) { cost += 6; n_geo = n_mask = 0; }
-          k = 1; cost += 8;
+          if (k != 0) { cost += 3; n_geo = n_mask = 0; }
+          k = 1; cost += 13;
           break;
         case CHB_OP_SHARPNESS:
           if (op.blend_mode == BLEND_IMAGE2) break;
-          if (k != 0) { cost += 6; n_geo = n_mask = 0; }
-          k = 2; cost += (n_geo + n_mask > 0) ? 36 : 22;
+          if (k != 0 || n_geo + n_mask > 0) { cost += 3; n_geo = n_mask = 0; }
+          k = 2; cost += lut ? 36 : 30;
           break;
         case CHB_OP_CUTOUT:
-          if (k == 2) { cost += 8; k = 0; n_geo = 0; n_mask = 0; }
-          ++n_mask; cost += (n_geo > 0) ? 8 : 3;
+          if (k == 2) { cost += 3; k = 0; n_geo = 0; n_mask = 0; }
+          ++n_mask; cost += (n_geo > 0) ? 9 : 3;
           break;
         case CHB_OP_SHEAR_X: case CHB_OP_SHEAR_Y: case CHB_OP_TRANSLATE_X: case CHB_OP_TRANSLATE_Y: case CHB_OP_ROTATE:
-          if (k == 2) { cost += 8; k = 0; n_geo = 0; n_mask = 0; }
-          ++n_geo; cost += (n_geo + n_mask > 1) ? 12 : 6;
+          if (k == 2) { cost += 3; k = 0; n_geo = 0; n_mask = 0; }
+          ++n_geo; cost += (n_geo + n_mask > 1) ? 14 : 8;
           break;
         case CHB_OP_INVERT: case CHB_OP_POSTERIZE: case CHB_OP_SOLARIZE:
           break;
@@ -1101,18 +964,29 @@ __device__ void plan_order(const KParams& p, const DevOp* ops, ResCtl* ctl, uint
 }
 
 // ================================================================================= the kernel
-template <int C, bool COUNT>
-__device__ __forceinline__ void res_run_pass(RC<C>& c, int store) {
+// With KParams::res_rules the chain walk materialises a view before Sharpness or a histogram op sees a
+// spatial list or an occupied K slot, so COUNT passes only ever meet the flat point-wise view and
+// Sharpness never has a warp pending; the general list gather stays as the safety net of the former.
+template <int C>
+__device__ __forceinline__ void res_count_pass(RC<C>& c) {
+  const TileState& t = *c.t;
+  if (t.kmode == K_NONE && t.n_sp == 0) res_flat<C, true>(c, 0);
+  else if (t.kmode != K_SHARP) { wait_image(c); hist_zero(c); res_gather_list<C, true>(c); hist_reduce(c); }
+  else __trap();
+}
+
+template <int C>
+__device__ __forceinline__ void res_write_pass(RC<C>& c, int store) {
   const TileState& t = *c.t;
   bool any_geom = false;
   for (int k = 0; k < t.n_sp; ++k) any_geom = any_geom || (t.sp[k].type == SP_GEOM);
   if (t.kmode == K_SHARP) {
-    if (t.n_sp > 0) res_gather_sharp<C, COUNT>(c);
-    else res_sharp<C, COUNT>(c);
-  } else if (t.n_sp == 0 || (!any_geom && !COUNT)) {
-    res_flat<C, COUNT>(c, store);
+    if (t.n_sp > 0) __trap();
+    res_sharp<C, false>(c);
+  } else if (!any_geom) {
+    res_flat<C, false>(c, store);
   } else {
-    res_gather<C, COUNT>(c);
+    res_gather<C, false>(c);
   }
 }
 
@@ -1179,7 +1053,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   // by different lanes of a warp were served in an order that made every step of a flat image wait for
   // the tail of the load (profiles/r02_v2_ab_notes.txt: identity 102 % -> 79 % of the copy peak).
   auto issue_load = [&](const uint8_t* src) {
-    if (tid == 0) {
+    if (tid == 32) {  // (not thread 0: that one drives the claims and the bulk stores)
       for (int k = 0; k < n_chunks; ++k) {
         const uint32_t bytes = (uint32_t)min(RES_CHUNK, img_bytes - k * RES_CHUNK);
         mbar_arrive_expect_tx(c.full0 + 8 * k, bytes);
@@ -1200,7 +1074,6 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
 #endif
     c.par ^= 1u;
     issue_load(p.in + (size_t)img * img_bytes);
-    if (tid == 0) ctl->n_claimed = (int)atomicAdd(p.counters, 1u);  // the next image: the round trip hides behind this one
     // schedule decode + chain walk up to the first pass (the loads are in flight)
     for (int i = tid; i < STATE_VECS; i += RNT) reinterpret_cast<uint4*>(&ctl->st)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
@@ -1227,8 +1100,9 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
       c.hshift = 31u - (uint32_t)__clz(ncopy * 4);
       c.hcopy = c.aux + (uint32_t)(c.lane & (ncopy - 1)) * 4u;
       __syncthreads();
+      c.tally = 0;
       if (pass_kind == PASS_COUNT) {
-        res_run_pass<C, true>(c, 0);
+        res_count_pass<C>(c);
         if (tid == 0) ctl->st.hist_valid = 1;
         __syncthreads();
         advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
@@ -1238,12 +1112,32 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
       // materialise in the resident image itself, the rare neighbourhood-of-neighbourhood chains go
       // through this CTA's scratch image and come back through the TMA
       const bool last = pass_kind == PASS_WRITE_OUT;
+      // The next image is claimed when this one's last pass starts: the round trip hides behind the pass, and
+      // -- unlike a claim at the image's start -- a CTA with a long chain does not sit on a second image that
+      // an idle CTA could have taken (profiles/r02_v3_timeline_256.txt: the tail of a 256-image call was the
+      // pre-claimed image behind the longest chain).
+      if (last && tid == 0) ctl->n_claimed = (int)atomicAdd(p.counters, 1u);
       bool any_geom = false;
       for (int k = 0; k < t.n_sp; ++k) any_geom = any_geom || (t.sp[k].type == SP_GEOM);
       const bool in_place = !last && (t.kmode == K_NONE || t.kmode == K_COLOR) && !any_geom;
       c.dst = last ? out_img : scratch;
-      res_run_pass<C, false>(c, last ? 1 : 0);
+      // a view materialised for a histogram op is counted while it is written (gathers and Sharpness:
+      // their bytes pass through registers anyway); in-place materialisations are counted by a flat
+      // COUNT pass afterwards
+      bool tally = false;
+      if (!last && !in_place && ctl->st.next_op < ctl->st.n_prog) {
+        const int kind = s_ops[ctl->st.prog[ctl->st.next_op].table_index].kind;
+        tally = (kind == CHB_OP_EQUALIZE || kind == CHB_OP_AUTOCONTRAST);
+      }
+      if (tally) {
+        c.tally = 1;
+        wait_image(c);
+        hist_zero(c);
+        for (int i = tid; i < MAXC * 256; i += RNT) (&ctl->st.hist[0][0])[i] = 0u;
+      }
+      res_write_pass<C>(c, last ? 1 : 0);
       if (last) break;
+      if (tally) hist_reduce(c);
       if (!in_place) {
         __threadfence();
         fence_proxy_async_all();
@@ -1253,6 +1147,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
       }
       reset_view(&ctl->st, tid, RNT);
       __syncthreads();
+      if (tally && tid == 0) ctl->st.hist_valid = 1;  // reset_view cleared it: the tallied bytes ARE the new source
       advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
     }
     // every thread is done with the resident source; bulk stores out of it have read their bytes;

@@ -38,9 +38,23 @@ def main():
     bufs = [(x[0], torch.empty_like(x[0])) for x in bufs]
     pol = A.RandAugment(2, 10, elementwise=True) if args.policy == "randaugment" else A.AutoAugment(elementwise=True)
     layer = pol._transform
-    for i in range(6):
+    for i in range(400):  # long warm-up: the SM clock has to be up before a single call is looked at
         layer(bufs[i % n][0], seed=0, call_counter=i, out=bufs[i % n][1])
     torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(100):
+        layer(bufs[i % n][0], seed=0, call_counter=i, out=bufs[i % n][1])
+    ev1.record()
+    torch.cuda.synchronize()
+    print("steady state: %.1f us per call over 100 back-to-back calls" % (ev0.elapsed_time(ev1) * 10))
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(0)
+        print("SM clock now %d MHz" % pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+    except Exception as e:
+        print("no nvml", e)
     lib = _lib.load()
     ctx = _lib.context(0)
     _lib.check(ctx, lib.chb_debug_timeline(ctx, None, 0))
@@ -48,6 +62,9 @@ def main():
     words = 1024 * 2 * 16
     host = np.zeros(words, dtype=np.uint64)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(50):
+        layer(bufs[i % n][0], seed=0, call_counter=i, out=bufs[i % n][1])
+    lib.chb_debug_timeline(ctx, host.ctypes.data, words)  # drop what the warm-up recorded (returns the word count)
     e0.record()
     layer(bufs[6 % n][0], seed=0, call_counter=6, out=bufs[6 % n][1], record=True)
     e1.record()
