@@ -44,6 +44,8 @@ static long long g_nf_first_images = 6;  // a batch is also "small" below this m
 static int g_self_clean = 1;         // CHB_SELF_CLEAN=0: zero the counters with a memset in front of every call instead
 static int g_chunk_kb = 2560;       // target chunk size of the host path in KiB (CHB_E2E_CHUNK_KB)
 static int g_lpt = 1;               // resident engine: cost-sorted claim order for small batches (CHB_LPT=0 disables)
+static int g_split_pct = 90;        // resident engine: split an item that would outlast this % of the average SM's load (CHB_SPLIT_PCT)
+static int g_split = 1;             // resident engine: small batches cut expensive last passes into row ranges (CHB_SPLIT=0 disables)
 
 struct chb_ctx {
   int device = 0;
@@ -409,6 +411,8 @@ extern "C" int chb_init(int device, chb_ctx** out) {
   if (const char* e = getenv("CHB_E2E_STREAMS")) { int v = atoi(e); if (v >= 1 && v <= kPipeMax) g_pipe = v; }
   if (const char* e = getenv("CHB_E2E_CHUNK_KB")) { int v = atoi(e); if (v >= 64) g_chunk_kb = v; }
   if (const char* e = getenv("CHB_LPT")) g_lpt = (e[0] != '0') ? 1 : 0;
+  if (const char* e = getenv("CHB_SPLIT")) g_split = (e[0] != '0') ? 1 : 0;
+  if (const char* e = getenv("CHB_SPLIT_PCT")) { int v = atoi(e); if (v >= 10 && v <= 1000) g_split_pct = v; }
   const char* fg = getenv("CHB_FORCE_GENERIC");
   ctx->force_generic = (fg && fg[0] && fg[0] != '0') ? 1 : 0;
   *out = ctx;
@@ -659,7 +663,10 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     return fail(ctx, CHB_ERR_UNSUPPORTED, "CHB_ENGINE_RESIDENT: this call is not eligible for the image-resident engine");
   if (resident) {
     const bool temp = overlap && d_in != d_out;
-    int grid = ctx->num_sms < B ? ctx->num_sms : B;
+    // one CTA per SM; the smallest batches may cut expensive images into up to four parts (plan_order)
+    const bool may_split = g_split && !overlap && pol->elementwise && B <= 512;
+    const long long max_items = (long long)B * (may_split ? 4 : 1);
+    int grid = (long long)ctx->num_sms < max_items ? ctx->num_sms : (int)max_items;
     r = get_workspace(ctx, stream, 1, chain >= 2 ? (size_t)grid * stride : 0, temp ? (size_t)B * img_bytes : 0, &ws);
     if (r != CHB_OK) return r;
     chb::KParams p;
@@ -674,6 +681,8 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     p.res_smem_bytes = ctx->res_smem;
     p.res_lpt = g_lpt;
     p.res_rules = 1;
+    p.res_split_pct = g_split_pct;
+    p.res_split = may_split ? 1 : 0;  // (parts of one image run on different CTAs: they must not write what another still reads)
     p.timeline = ctx->timeline;
     {
       const size_t fixed = chb::resident_ctl_bytes() + (pe->host.size() * (sizeof(DevOp) + 256) + 127) / 128 * 128 +

@@ -59,10 +59,14 @@ struct alignas(16) TileState {  // what a tile needs; loaded whole by every tile
   // Solarize and their compositions) is applied with one logic op per word instead of lookups:
   // bit 16 = valid, bits 8..15 = m, bits 0..7 = c
   int32_t l1_aff, l2_aff;
-  int32_t _pad[1];
+  // l1 is exactly ONE blend op against a constant (Brightness: 0, Contrast: its mean constant) applied to
+  // the identity: blend mode + 1 (0 = no), the constant, float32(factor).  The resident engine then
+  // evaluates the blend arithmetically in its flat executor instead of looking 150 K bytes up.
+  int32_t l1_blend;
   Spatial sp[CHB_MAX_CHAIN];
   Spatial kgeo;  // K_BILINEAR: the warp (t, fill_mode, color[0] = fill)
-  int32_t _pad2[2];
+  int32_t l1_blend_const;
+  float l1_blend_factor;
   uint8_t l1[MAXC][256];
   uint8_t l2[MAXC][256];
 };
@@ -116,8 +120,9 @@ struct KParams {
   int res_smem_bytes;                 // resident engine: dynamic shared memory of a CTA (control + policy + image + aux region)
   int res_lpt;                        //   1: small batches are claimed most-expensive-chain-first (CHB_LPT=0 disables)
   int res_rules;                      //   1: advance() materialises non-flat views in front of Sharpness / a histogram op
-  int res_sharp_rows;                 //   Sharpness: rows per sub-strip of the column walk
-  int res_gs_band[2], res_gs_rows[2]; //   gathered Sharpness (WRITE / COUNT): output rows per band, rows per sub-strip
+  int res_sharp_rows[4];              //   Sharpness: rows per sub-strip of the column walk, last pass cut into 1..4 row ranges
+  int res_split_pct;                  //   an item is split when it would outlast this % of the average SM's load (CHB_SPLIT_PCT)
+  int res_split;                      //   1: small batches may cut the last pass of an expensive image into row ranges (not when d_in == d_out)
 };
 
 // Opaque copy of a CUtensorMap (cuda.h), passed to the pass kernel as a __grid_constant__ parameter.

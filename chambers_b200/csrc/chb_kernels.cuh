@@ -230,6 +230,7 @@ __device__ __forceinline__ void reset_view(ImgState* s, int tid, int nt) {  // a
   }
   if (tid == 0) {
     s->t.n_sp = 0; s->t.kmode = K_NONE; s->t.l1_id = 1; s->t.l2_id = 1; s->t.sp_fast = 1; s->t.l1_aff = 0; s->t.l2_aff = 0;
+    s->t.l1_blend = 0;
     s->t.kfactor = 0.0f; s->hist_valid = 0;
   }
 }
@@ -328,6 +329,13 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
           s->t.sp[k].color[c] = CHB_LDP(tab + s->t.sp[k].color[c]);
         }
       if (tid == 0) {
+        // the first op on an identity l1, and it is a blend against a constant: remember its closed form
+        const bool blend_op = (kind == CHB_OP_BRIGHTNESS || kind == CHB_OP_CONTRAST);
+        if (kmode == K_NONE) {
+          s->t.l1_blend = (s->t.l1_id && blend_op) ? CHB_LDP(&op->blend_mode) + 1 : 0;
+          s->t.l1_blend_const = (kind == CHB_OP_CONTRAST) ? CHB_LDP(&op->ip0) : 0;
+          s->t.l1_blend_factor = CHB_LDP(&op->factor);
+        }
         if (kmode == K_NONE) s->t.l1_id = 0; else s->t.l2_id = 0;
         s->next_op = pi + 1;
       }
@@ -368,7 +376,9 @@ __device__ void advance(ImgState* s, ImgState* g, const KParams& p, int C, int H
           s->t.sp[k].color[c] = etab[c * 256 + s->t.sp[k].color[c]];
         }
       if (tid == 0) {
-        if (kmode == K_NONE) s->t.l1_id = 0; else s->t.l2_id = 0;
+        if (kmode == K_NONE) { s->t.l1_id = 0; s->t.l1_blend = 0; } else s->t.l2_id = 0;
+        // a presence-only histogram (resident engine, AutoContrast: hist_valid == 2) serves this op alone
+        if (hist_valid == 2) s->hist_valid = 0;
         s->next_op = pi + 1;
       }
       }

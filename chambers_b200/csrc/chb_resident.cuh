@@ -47,9 +47,10 @@ struct alignas(128) ResCtl {
   unsigned long long full[RES_MAXCHUNK];
   int32_t next_img, n_claimed, _p1, _p2;
   // work splits that depend only on the shape (computed once per launch by thread 0)
-  int32_t sharp_rows;                  // res_sharp: rows per sub-strip
-  int32_t gs_band[2], gs_rows[2];      // res_gather_sharp, WRITE / COUNT: output rows per band, rows per sub-strip
-  int32_t _p4[3];
+  int32_t sharp_rows[4];               // res_sharp: rows per sub-strip when the image's last pass is cut into 1..4 parts
+  int32_t n_items, cost_sum, _p4[2];   // claim positions of this call (images, or image parts); sum of the cost estimates
+  uint32_t mm[MAXC][2];                // presence-only COUNT pass (AutoContrast): min / max per channel
+  int32_t mono[2], _p5[2];             // l1 is non-decreasing / non-increasing in every channel
   uint32_t fillc[2];                   // colour bytes of the last / last-but-one spatial entry ("a miss is just another address")
   uint32_t _p3[2];
   uint32_t rnd[32][4], rndc[32][4];
@@ -77,6 +78,9 @@ struct RC {
   int ncopy;           // histogram copies: 32, 16, 8 or 4
   uint32_t hshift;     // log2(ncopy * 4): byte shift of a counter-pair row
   int tally;           // WRITE pass: also count the bytes written (the materialised view feeds a histogram op next)
+  int y_lo, y_hi;      // WRITE passes: output rows this CTA produces (the whole image unless a small batch split the image's last pass)
+  int sharp_rows;      // Sharpness: rows per sub-strip of the column walk for this row range
+  int minmax;          // COUNT pass: only the smallest and largest value per channel are needed (AutoContrast on a monotone l1)
 };
 
 // Histogram of a COUNT pass: `ncopy` copies of packed 16-bit counters in the aux region, copy =
@@ -126,6 +130,33 @@ __device__ __forceinline__ void wait_image(const RC<C>& c) {
   wait_chunks(c, 0, (c.img_bytes + RES_CHUNK - 1) / RES_CHUNK - 1);
 }
 
+// chambers' blend against a constant (image_augmentations.py:10-49; blend_value in chb_device.cuh) on the
+// UW words of a unit, in float32 steps identical to the table builder's: d = v - a (exact), t = a + f * d
+// (two roundings), clip for factors outside [0, 1], truncate.  v enters as the mantissa of 2^23 (one
+// PRMT), so d is one add; for a == 0 (Brightness) the product f * v is one FFMA on 2^23 + v -- the exact
+// product rounded once, the same float32 -- and the addition of 0 disappears.
+template <int UW>
+__device__ __forceinline__ void blend_unit(uint32_t* w, int extrap, int a, float f) {
+  const float af = (float)a;
+  const float na = -(8388608.0f + af);   // exact
+  const float nf = -8388608.0f * f;      // exact
+#pragma unroll
+  for (int j = 0; j < UW; ++j) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const float xm = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7440u | (uint32_t)b));  // 2^23 + v
+      float t;
+      if (a == 0) t = __fmaf_rn(xm, f, nf);
+      else t = __fadd_rn(af, __fmul_rn(f, __fadd_rn(xm, na)));
+      if (extrap) t = fminf(fmaxf(t, 0.0f), 255.0f);
+      const uint32_t r = trunc_bits(t);
+      o = (b == 0) ? byte_of(r, 0) : put_byte(o, r, b);
+    }
+    w[j] = o;
+  }
+}
+
 // ================================================================================ flat executor
 // No warp pending, K in {none, Color}: units of 48 bytes (16 pixels; 16 bytes for C != 3) are
 // transformed in place as their load chunks arrive, one unit per thread per step of RNT units; a
@@ -136,16 +167,24 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
   constexpr int UW = (C == 3) ? 12 : 4;
   constexpr int UB = UW * 4;
   const TileState& t = *c.t;
-  const int n_units = c.img_bytes / UB;
+  const int upr = c.row / UB;                                  // units per row (rows are whole units)
+  const int u_first = COUNT ? 0 : c.y_lo * upr;                // COUNT passes always see the whole image
+  const int n_units = COUNT ? c.img_bytes / UB : c.y_hi * upr;  // (one past the last unit)
   const int kmode = t.kmode;
   const bool use1 = !t.l1_id, use2 = !t.l2_id;
   const bool aff1 = (t.l1_aff & 0x10000) != 0;
   const uint32_t am1 = (uint32_t)((t.l1_aff >> 8) & 0xFF) * 0x01010101u, ac1 = (uint32_t)(t.l1_aff & 0xFF) * 0x01010101u;
   const float f = t.kfactor;
+  const int blend1 = t.l1_blend, blend_a = t.l1_blend_const;  // l1 as one blend against a constant (closed form)
+  const float blend_f = t.l1_blend_factor;
+  const bool minmax = COUNT && c.minmax;
+  uint32_t mn[C], mx[C];
+#pragma unroll
+  for (int ch = 0; ch < C; ++ch) { mn[ch] = 255u; mx[ch] = 0u; }
   const int n_paint = COUNT ? 0 : t.n_sp;  // this class holds masks only
   const bool touch = COUNT || use1 || kmode != K_NONE;  // else the staged bytes already are the result
-  if (COUNT) hist_zero(c);
-  for (int base = 0; base < n_units; base += RNT) {
+  if (COUNT && !minmax) hist_zero(c);
+  for (int base = u_first; base < n_units; base += RNT) {
     const int wu = base + (c.tid & ~31);
     if (wu < n_units) {
       const int wl = min(wu + 31, n_units - 1);
@@ -165,6 +204,10 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
           if (aff1) {
 #pragma unroll
             for (int j = 0; j < UW; ++j) w[j] = (w[j] & am1) ^ ac1;
+          } else if (blend1 == BLEND_EXTRAP + 1) {
+            if (blend_a == 0) blend_unit<UW>(w, 1, 0, blend_f); else blend_unit<UW>(w, 1, blend_a, blend_f);
+          } else if (blend1 == BLEND_INTERP + 1) {
+            if (blend_a == 0) blend_unit<UW>(w, 0, 0, blend_f); else blend_unit<UW>(w, 0, blend_a, blend_f);
           } else {
             map_unit<C, UW>(w, c.l1a);
           }
@@ -187,10 +230,21 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
         if (!COUNT && use2) map_unit<C, UW>(w, c.l2a);
       }
       if (COUNT) {
+        if (minmax) {  // three ALU instructions per byte and no shared-memory traffic at all
 #pragma unroll
-        for (int j = 0; j < UW; ++j)
+          for (int j = 0; j < UW; ++j)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) hist_add(c, (4 * j + b) % C, byte_of(w[j], b));
+            for (int b = 0; b < 4; ++b) {
+              const uint32_t v = byte_of(w[j], b);
+              mn[(4 * j + b) % C] = min(mn[(4 * j + b) % C], v);
+              mx[(4 * j + b) % C] = max(mx[(4 * j + b) % C], v);
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < UW; ++j)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) hist_add(c, (4 * j + b) % C, byte_of(w[j], b));
+        }
       } else {
 #pragma unroll
         for (int q = 0; q < UW / 4; ++q) sts_v4(ua + q * 16, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
@@ -224,8 +278,23 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
       }
     }
   }
-  if (COUNT) hist_reduce(c);
-  else __syncthreads();
+  if (COUNT && minmax) {
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+      const uint32_t a = __reduce_min_sync(0xFFFFFFFFu, mn[ch]), b = __reduce_max_sync(0xFFFFFFFFu, mx[ch]);
+      if (c.lane == 0) { atomicMin(&c.ctl->mm[ch][0], a); atomicMax(&c.ctl->mm[ch][1], b); }
+    }
+    __syncthreads();
+    if (c.tid < C) {  // a histogram that holds exactly what AutoContrast reads: which values bound the range
+      const uint32_t lo = c.ctl->mm[c.tid][0], hi = c.ctl->mm[c.tid][1];
+      if (lo <= hi) { c.ctl->st.hist[c.tid][lo] += 1u; c.ctl->st.hist[c.tid][hi] += 1u; }
+    }
+    __syncthreads();
+  } else if (COUNT) {
+    hist_reduce(c);
+  } else {
+    __syncthreads();
+  }
 }
 
 // ============================================================================== gather executors
@@ -290,7 +359,10 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
 #define CHB_GATHER_RAW 0
 #endif
   constexpr int G = CHB_GATHER_G;
-  for (UnitWalk q(c.tid, W / (4 * G)); q.y < H; q.next()) {
+  const int y_end = COUNT ? H : c.y_hi;
+  UnitWalk q(c.tid, W / (4 * G));
+  if (!COUNT) q.y += c.y_lo;
+  for (; q.y < y_end; q.next()) {
     const int y = q.y, xu = q.ux * (4 * G);
     const float fy = small_uint_to_float((uint32_t)y);
     const float t1y = __fmul_rn(t1, fy), t4y = __fmul_rn(t4, fy);
@@ -475,7 +547,10 @@ __device__ __forceinline__ void res_gather_rowshift(const RC<C>& c) {
     for (int b = 0; b < 4; ++b) x |= byte_of(fill_a, (4 * w + b) % C) << (8 * b);
     fq[w] = x;
   }
-  for (UnitWalk q(c.tid, W >> 2); q.y < H; q.next()) {
+  const int y_end = COUNT ? H : c.y_hi;
+  UnitWalk q(c.tid, W >> 2);
+  if (!COUNT) q.y += c.y_lo;
+  for (; q.y < y_end; q.next()) {
     const int y = q.y, x0 = q.ux << 2;
     const int iy = y + dy;
     uint32_t o[C];
@@ -592,8 +667,8 @@ __device__ __forceinline__ void res_gather_list(const RC<C>& c) {
   const int kmode = t.kmode;
   const bool use1 = !t.l1_id, use2 = !t.l2_id;
   const float f = t.kfactor;
-  const int n_pix = H * W;
-  for (int i = c.tid; i < n_pix; i += RNT) {
+  const int n_pix = (COUNT ? H : c.y_hi) * W;
+  for (int i = (COUNT ? 0 : c.y_lo * W) + c.tid; i < n_pix; i += RNT) {
     const int y = i / W;
     int sx = i - y * W, sy = y;
     const int k = resolve(t.sp, n_sp, H, W, sx, sy);
@@ -645,12 +720,13 @@ __device__ __forceinline__ void res_gather_list(const RC<C>& c) {
 template <int C, bool COUNT>
 __device__ __forceinline__ void res_gather(const RC<C>& c) {
   const TileState& t = *c.t;
-  wait_image(c);
-  if (COUNT) hist_zero(c);
 #ifndef CHB_ROWSHIFT
 #define CHB_ROWSHIFT 1
 #endif
-  if (CHB_ROWSHIFT && t.n_sp == 1 && t.kmode == K_NONE && is_rowshift(t.sp[0])) res_gather_rowshift<C, COUNT>(c);
+  const bool rowshift = CHB_ROWSHIFT && t.n_sp == 1 && t.kmode == K_NONE && is_rowshift(t.sp[0]);
+  wait_image(c);  // (waiting per source row inside the row-shift copy was measured: the test per quad cost more than the overlap gained)
+  if (COUNT) hist_zero(c);
+  if (rowshift) res_gather_rowshift<C, COUNT>(c);
   else if (t.n_sp == 1 && t.sp[0].type == SP_GEOM) res_gather_fast<C, COUNT, false>(c);
   else if (t.n_sp == 2) res_gather_fast<C, COUNT, true>(c);
   else res_gather_list<C, COUNT>(c);
@@ -693,19 +769,13 @@ inline int res_sharp_split(int columns, int inner) {
 // region, so the host computes them once per call (KParams::res_*).
 template <int C>
 void resident_splits_c(KParams& p, int aux_bytes) {
+  (void)aux_bytes;
   const int H = p.H, W = p.W;
   const int wpr = (W * C) >> 2;
-  p.res_sharp_rows = res_sharp_split(wpr, H - 2);
-  const int vpitch = (4 + (W + 1) * C + 3) & ~3;
-  for (int k = 0; k < 2; ++k) {
-    const int vbytes = aux_bytes - (k ? (int)hist_bytes<C>(4) : 0);
-    int band = vbytes / vpitch - 2;
-    if (band < 1) band = 1;
-    const int n_bands = (H + band - 1) / band;  // bands of equal height: the last one is not a sliver
-    band = (H + n_bands - 1) / n_bands;
-    p.res_gs_band[k] = band;
-    const int inner = band < (H - 2 > 1 ? H - 2 : 1) ? band : (H - 2 > 1 ? H - 2 : 1);
-    p.res_gs_rows[k] = res_sharp_split(wpr, inner);
+  for (int n = 1; n <= 4; ++n) {  // the last pass of an image cut into n row ranges (small batches)
+    const int rows = (H + n - 1) / n;
+    const int inner = n == 1 ? H - 2 : rows;
+    p.res_sharp_rows[n - 1] = res_sharp_split(wpr, inner);
   }
 }
 
@@ -809,18 +879,21 @@ __device__ __forceinline__ void res_sharp(const RC<C>& c) {
     }
   };
   // first and last image row: every pixel is border -> blend(orig, orig) == orig
-  for (int xw = c.tid; xw < wpr; xw += RNT) emit(0, xw, (C == 3) ? (xw % 3) : 0, lds_u32(c.img + ((uint32_t)xw << 2)));
-  if (H > 1)
+  const int y_lo = COUNT ? 0 : c.y_lo, y_hi = COUNT ? H : c.y_hi;
+  if (y_lo == 0)
+    for (int xw = c.tid; xw < wpr; xw += RNT) emit(0, xw, (C == 3) ? (xw % 3) : 0, lds_u32(c.img + ((uint32_t)xw << 2)));
+  if (H > 1 && y_hi == H)
     for (int xw = c.tid; xw < wpr; xw += RNT)
       emit(H - 1, xw, (C == 3) ? (xw % 3) : 0, lds_u32(c.img + (uint32_t)((H - 1) * row + (xw << 2))));
-  const int inner = H - 2;
+  const int in0 = max(1, y_lo), in1 = min(H - 1, y_hi);
+  const int inner = in1 - in0;
   if (inner > 0) {
-    const int R = c.ctl->sharp_rows;
+    const int R = c.sharp_rows;
     const int n_strips = (inner + R - 1) / R;
     const int n_items = wpr * n_strips;
     for (int item = c.tid; item < n_items; item += RNT) {
       const int strip = item / wpr, xw = item - strip * wpr;
-      const int y_begin = 1 + strip * R, y_end = min(H - 1, y_begin + R);
+      const int y_begin = in0 + strip * R, y_end = min(in1, y_begin + R);
       const int xb0 = xw << 2;
       uint32_t bmask = 0;
 #pragma unroll
@@ -839,15 +912,26 @@ __device__ __forceinline__ void res_sharp(const RC<C>& c) {
 // A CTA works on one image at a time, so a 256-image call is 1.7 images per SM and its duration is the
 // most loaded SM's: which images an SM gets matters more than anything else.  Every CTA therefore
 // decodes the op chain of EVERY image of a small batch (Philox again, or the replayed schedule), turns
-// it into a cost estimate and sorts the images by decreasing cost -- the same order in every CTA, no
-// communication -- and the claim counter indexes that order: the expensive chains (a gathered
-// Sharpness is 10x an Invert) start first, one per SM, and the cheap ones fill the gaps (LPT).
-// Only the ORDER depends on the estimate; the pixels do not.
-__device__ __forceinline__ int chain_cost(const KParams& p, const DevOp* ops, int img) {
+// it into a cost estimate and sorts the work by decreasing cost -- the same order in every CTA, no
+// communication -- and the claim counter indexes that order: the expensive chains start first, one
+// per SM, and the cheap ones fill the gaps (LPT).  In the smallest batches (<= SPLIT_MAX images) the
+// LAST pass of an image that alone would outlast the average SM is cut into 2..4 row ranges, each a
+// work item of its own: every part loads the image and repeats the passes in front of the last one
+// (they need the whole image), then writes only its rows.
+// Only the SCHEDULE depends on the estimate; the pixels do not.
+constexpr int SPLIT_MAX = 512;
+constexpr int ORDER_IMG_BITS = 11;  // order entry: image | part << 11 | (parts - 1) << 13
+
+// Estimated microseconds of one image at 224 x 224 x 3 (profiles/r02_v3_timeline_256.txt), following the
+// rules of the chain walk: `sunk` = loading, bookkeeping and every pass in front of the last one (paid
+// by every part), `pend` = the evaluation of the final view (shared between the parts).
+__device__ __forceinline__ void chain_cost(const KParams& p, const DevOp* ops, int img, int& sunk, int& pend) {
   const unsigned long long own = p.image_index_base + (unsigned long long)img;
   const unsigned long long stream_img = p.elementwise ? own : ~0ull;
   const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-  int cost = 8, n_geo = 0, n_mask = 0, k = 0, lut = 0;  // k: 0 none, 1 Color, 2 Sharpness (spatial list frozen)
+  int n_geo = 0, n_mask = 0, k = 0, lut = 0;  // k: 0 none, 1 Color, 2 Sharpness
+  sunk = 8; pend = 0;
+  auto materialise = [&](int extra) { sunk += pend + 3 + extra; pend = 0; n_geo = n_mask = 0; k = 0; lut = 0; };
   for (int i = 0; i < p.n_draws; ++i) {
     const int slot0 = i * (p.K + 1);
     const size_t rbase = ((size_t)img * p.n_draws + i) * p.K * CHB_SCHED_FIELDS;
@@ -871,66 +955,83 @@ __device__ __forceinline__ int chain_cost(const KParams& p, const DevOp* ops, in
         applied = kind >= 0 && (int)(r >> 8) < op.thr24;
       }
       if (!applied) continue;
-      // rough per-image microseconds at 224 x 224 x 3 (profiles/r02_v3_timeline_256.txt), following the rules
-      // of the chain walk: what forces a materialisation, what is evaluated once in the last pass
       switch (kind) {
         case CHB_OP_AUTOCONTRAST: case CHB_OP_EQUALIZE:
-          if (n_geo > 0 || k == 2) cost += 12;            // tallied while materialised, reload, flat apply
-          else if (n_mask > 0 || k == 1) cost += 20;      // in place, flat COUNT, flat apply
-          else cost += 17;                                // flat COUNT, flat apply
-          n_geo = n_mask = 0; k = 0;
+          if (n_geo > 0 || k == 2) materialise(4);            // tallied while written, reload
+          else if (n_mask > 0 || k == 1) materialise(12);      // in place, flat COUNT
+          else sunk += 12;                                     // flat COUNT
+          pend += 5;                                           // flat apply
           break;
         case CHB_OP_COLOR:
           if (op.blend_mode == BLEND_IMAGE2) break;
-          if (k != 0) { cost += 3; n_geo = n_mask = 0; }
-          k = 1; cost += 13;
+          if (k != 0) materialise(0);
+          k = 1; pend += 13;
           break;
         case CHB_OP_SHARPNESS:
           if (op.blend_mode == BLEND_IMAGE2) break;
-          if (k != 0 || n_geo + n_mask > 0) { cost += 3; n_geo = n_mask = 0; }
-          k = 2; cost += lut ? 36 : 30;
+          if (k != 0 || n_geo + n_mask > 0) materialise(0);
+          k = 2; pend += lut ? 36 : 30;
           break;
         case CHB_OP_CUTOUT:
-          if (k == 2) { cost += 3; k = 0; n_geo = 0; n_mask = 0; }
-          ++n_mask; cost += (n_geo > 0) ? 9 : 3;
+          if (k == 2) materialise(0);
+          ++n_mask; pend += (n_geo > 0) ? 9 : 3;
           break;
         case CHB_OP_SHEAR_X: case CHB_OP_SHEAR_Y: case CHB_OP_TRANSLATE_X: case CHB_OP_TRANSLATE_Y: case CHB_OP_ROTATE:
-          if (k == 2) { cost += 3; k = 0; n_geo = 0; n_mask = 0; }
-          ++n_geo; cost += (n_geo + n_mask > 1) ? 14 : 8;
+          if (k == 2) materialise(0);
+          ++n_geo; pend += (n_geo + n_mask > 1) ? 14 : 8;
           break;
         case CHB_OP_INVERT: case CHB_OP_POSTERIZE: case CHB_OP_SOLARIZE:
           break;
         default:  // Brightness, Contrast, SolarizeAdd: table lookups
-          if (!lut) { lut = 1; cost += 5; }
+          if (!lut) { lut = 1; pend += 5; }
           break;
       }
     }
   }
-  return cost;
 }
 
-// Fills ctl->order for a batch of B <= LPT_MAX images.  `scratch`: 64 x 64 uint16 + 64 int of shared memory.
+// Fills ctl->order / ctl->n_items for a batch of B <= LPT_MAX images.  `scratch`: 64 x 64 uint16 + 64 int
+// of shared memory.
 __device__ void plan_order(const KParams& p, const DevOp* ops, ResCtl* ctl, uint16_t* scratch, int tid) {
   constexpr int NBK = 64;                       // cost buckets (bucket 0 = most expensive)
+  constexpr int NR = LPT_MAX / RNT;             // images per thread
   const int B = p.B;
   const int lane = tid & 31;
+  const bool split = p.res_split && B <= SPLIT_MAX;
+  const int slots = split ? 4 : 1;              // item id = image * slots + part: the sort is stable in it
   for (int i = tid; i < NBK * NBK; i += RNT) scratch[i] = 0;
-  __syncthreads();
-  // pass 1: bucket of every image; count per (32-image chunk, bucket)
-  int bk[LPT_MAX / RNT];
+  int sunk[NR], pend[NR];
+  int mine = 0;
 #pragma unroll
-  for (int r = 0; r < LPT_MAX / RNT; ++r) {
+  for (int r = 0; r < NR; ++r) {
     const int i = r * RNT + tid;
-    bk[r] = 0;
+    sunk[r] = pend[r] = 0;
+    if (i < B) { chain_cost(p, ops, i, sunk[r], pend[r]); mine += sunk[r] + pend[r]; }
+  }
+  if (mine) atomicAdd(&ctl->cost_sum, mine);
+  __syncthreads();
+  // an item should not outlast KParams::res_split_pct % of the average SM's share of the batch
+  const int target = max(12, (int)((long long)ctl->cost_sum * p.res_split_pct / (100 * (long long)gridDim.x)));
+  // pass 1: parts and bucket of every image; count per (32-item-id chunk, bucket)
+  int bk[NR], parts[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int i = r * RNT + tid;
+    bk[r] = 0; parts[r] = 1;
     if (i < B) {
-      int cst = chain_cost(p, ops, i);
+      if (split)
+        while (parts[r] < 4 && sunk[r] + pend[r] / parts[r] > target && pend[r] / (parts[r] + 1) >= 8) ++parts[r];
+      const int cst = sunk[r] + pend[r] / parts[r];
       bk[r] = NBK - 1 - min(cst >> 1, NBK - 1);
-      atomicAdd(reinterpret_cast<unsigned int*>(scratch) + (((i >> 5) * NBK + bk[r]) >> 1), (((i >> 5) * NBK + bk[r]) & 1) ? 0x10000u : 1u);
+      for (int q = 0; q < parts[r]; ++q) {
+        const int e = ((i * slots + q) >> 5) * NBK + bk[r];
+        atomicAdd(reinterpret_cast<unsigned int*>(scratch) + (e >> 1), (e & 1) ? 0x10000u : 1u);
+      }
     }
   }
   __syncthreads();
   // exclusive prefix over (bucket major, chunk minor): thread b scans bucket b's chunks, then the bucket totals are scanned
-  const int n_chunks = (B + 31) >> 5;
+  const int n_chunks = (B * slots + 31) >> 5;
   int* bucket_total = reinterpret_cast<int*>(scratch + NBK * NBK);  // (no static shared memory: the kernel takes the SM's whole carve-out dynamically)
   if (tid < NBK) {
     int run = 0;
@@ -945,19 +1046,44 @@ __device__ void plan_order(const KParams& p, const DevOp* ops, ResCtl* ctl, uint
   if (tid == 0) {
     int run = 0;
     for (int b = 0; b < NBK; ++b) { const int v = bucket_total[b]; bucket_total[b] = run; run += v; }
+    ctl->n_items = run;
   }
   __syncthreads();
-  // pass 2: position = bucket start + images of the bucket in earlier chunks + rank among the chunk's lanes
+  // pass 2: position = bucket start + items of the bucket in earlier chunks + rank among the chunk's item ids
 #pragma unroll
-  for (int r = 0; r < LPT_MAX / RNT; ++r) {
+  for (int r = 0; r < NR; ++r) {
     const int i = r * RNT + tid;
     const bool valid = i < B;
-    const unsigned act = __ballot_sync(0xFFFFFFFFu, valid);
-    if (valid) {
-      const unsigned same = __match_any_sync(act, bk[r]);
-      const int rank = __popc(same & ((1u << lane) - 1u));
-      const int pos = bucket_total[bk[r]] + scratch[(i >> 5) * NBK + bk[r]] + rank;
-      ctl->order[pos] = (uint16_t)i;
+    if (split) {
+      // a chunk of 32 item ids is 8 images (lanes 8k .. 8k+7 of a warp... any 8 consecutive images): rank by a
+      // scan over the 8 images of the chunk
+      const unsigned act = __ballot_sync(0xFFFFFFFFu, valid);
+      for (int q = 0; q < 4; ++q) {
+        const bool has = valid && q < parts[r];
+        // items of the same chunk and bucket with a smaller id: images of the same group of 8 with a smaller
+        // index (all their parts), plus this image's earlier parts
+        int rank = q;
+        const int grp = lane & ~7;
+        for (int o = 0; o < 8; ++o) {
+          const int ob = __shfl_sync(0xFFFFFFFFu, bk[r], grp + o);
+          const int op = __shfl_sync(0xFFFFFFFFu, valid ? parts[r] : 0, grp + o);
+          if (grp + o < lane && ob == bk[r]) rank += op;
+        }
+        if (has) {
+          const int id = i * slots + q;
+          const int pos = bucket_total[bk[r]] + scratch[(id >> 5) * NBK + bk[r]] + rank;
+          ctl->order[pos] = (uint16_t)(i | (q << ORDER_IMG_BITS) | ((parts[r] - 1) << (ORDER_IMG_BITS + 2)));
+        }
+      }
+      (void)act;
+    } else {
+      const unsigned act = __ballot_sync(0xFFFFFFFFu, valid);
+      if (valid) {
+        const unsigned same = __match_any_sync(act, bk[r]);
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        const int pos = bucket_total[bk[r]] + scratch[(i >> 5) * NBK + bk[r]] + rank;
+        ctl->order[pos] = (uint16_t)i;
+      }
     }
   }
   __syncthreads();
@@ -1021,8 +1147,9 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
     // shape-only work splits (computed on the host, resident_splits)
-    ctl->sharp_rows = p.res_sharp_rows;
-    for (int k = 0; k < 2; ++k) { ctl->gs_band[k] = p.res_gs_band[k]; ctl->gs_rows[k] = p.res_gs_rows[k]; }
+    for (int k = 0; k < 4; ++k) ctl->sharp_rows[k] = p.res_sharp_rows[k];
+    ctl->n_items = p.B;
+    ctl->cost_sum = 0;
   }
   // Programmatic dependent launch: nothing the previous kernel of the stream wrote (the images, a
   // replayed schedule, the policy table, the work counter it left zeroed) is touched before it has completed.
@@ -1044,9 +1171,19 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   __syncthreads();
   // small batches: positions map to images through the cost-sorted order (all images share one chain in
   // batch mode: nothing to sort)
-  const bool lpt = p.B <= LPT_MAX && p.B > (int)gridDim.x && p.elementwise && p.res_lpt;
+  const bool lpt = p.B <= LPT_MAX && p.elementwise && p.res_lpt && (p.B > (int)gridDim.x || p.res_split);
   if (lpt) plan_order(pl, s_ops, ctl, reinterpret_cast<uint16_t*>(smem_raw + aux_off), tid);
-  auto image_of = [&](int pos) { return (lpt && pos < p.B) ? (int)ctl->order[pos] : pos; };
+  const int n_items = ctl->n_items;  // == p.B unless images were split
+  int part = 0, n_parts = 1;
+  auto image_of = [&](int pos) {     // claim position -> image (and the row range of its last pass)
+    part = 0; n_parts = 1;
+    if (pos >= n_items) return p.B;
+    if (!lpt) return pos;
+    const int e = (int)ctl->order[pos];
+    part = (e >> ORDER_IMG_BITS) & 3;
+    n_parts = ((e >> (ORDER_IMG_BITS + 2)) & 3) + 1;
+    return e & ((1 << ORDER_IMG_BITS) - 1);
+  };
   int img = image_of(ctl->next_img);
   uint8_t* scratch = p.scratch + (size_t)blockIdx.x * p.scratch_stride;
   // Thread 0 issues the chunks IN ORDER: the executors consume them front to back, and chunks issued
@@ -1101,9 +1238,30 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
       c.hcopy = c.aux + (uint32_t)(c.lane & (ncopy - 1)) * 4u;
       __syncthreads();
       c.tally = 0;
+      c.minmax = 0;
       if (pass_kind == PASS_COUNT) {
+        // AutoContrast reads only the smallest and the largest value of each channel (image_augmentations.py:
+        // 69-70).  If the table in front of it (l1) is monotone in every channel, the extremes of l1's INPUT
+        // bytes decide them: a min / max pass in registers replaces 150 K shared-memory atomics.  The
+        // resulting histogram is presence-only and marked so (hist_valid == 2: it serves this op alone).
+        bool want_mm = false;
+        if (t.kmode == K_NONE && t.n_sp == 0 && ctl->st.next_op < ctl->st.n_prog)
+          want_mm = s_ops[ctl->st.prog[ctl->st.next_op].table_index].kind == CHB_OP_AUTOCONTRAST;
+        if (want_mm) {
+          if (tid < 2) ctl->mono[tid] = 1;
+          if (tid < MAXC) { ctl->mm[tid][0] = 255u; ctl->mm[tid][1] = 0u; }
+          __syncthreads();
+          for (int i = tid; i < C * 256; i += RNT)
+            if ((i & 255) != 255) {
+              const int a = t.l1[i >> 8][i & 255], b = t.l1[i >> 8][(i & 255) + 1];
+              if (a > b) ctl->mono[0] = 0;
+              if (a < b) ctl->mono[1] = 0;
+            }
+          __syncthreads();
+          c.minmax = (ctl->mono[0] || ctl->mono[1]) ? 1 : 0;
+        }
         res_count_pass<C>(c);
-        if (tid == 0) ctl->st.hist_valid = 1;
+        if (tid == 0) ctl->st.hist_valid = c.minmax ? 2 : 1;
         __syncthreads();
         advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
         continue;
@@ -1121,6 +1279,9 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
       for (int k = 0; k < t.n_sp; ++k) any_geom = any_geom || (t.sp[k].type == SP_GEOM);
       const bool in_place = !last && (t.kmode == K_NONE || t.kmode == K_COLOR) && !any_geom;
       c.dst = last ? out_img : scratch;
+      c.y_lo = last ? (H * part) / n_parts : 0;
+      c.y_hi = last ? (H * (part + 1)) / n_parts : H;
+      c.sharp_rows = ctl->sharp_rows[last ? n_parts - 1 : 0];
       // a view materialised for a histogram op is counted while it is written (gathers and Sharpness:
       // their bytes pass through registers anyway); in-place materialisations are counted by a flat
       // COUNT pass afterwards

@@ -268,3 +268,79 @@ def test_small_batch_claim_order(A):
         idx = list(range(0, B, max(1, B // 40)))
         want = oracle.apply_schedule(x[idx], policy_of(layer), sched[idx], elementwise=True)
         assert_same(y[idx].cpu().numpy(), want, "B=%d" % B)
+
+
+def test_split_last_pass_of_small_batches(A):
+    """Batches of <= 512 images cut the last pass of an expensive image into row ranges that run on
+    different CTAs (plan_order): every chain class, with its parts, must still produce the oracle's bytes --
+    batch sizes from 1 image (one image on up to four SMs) to the 512 threshold, all 256 pairs at
+    224 x 224 with few images per call so that nearly everything is split, AutoAugment, in place
+    (no split: parts would race with the source), and the tile engine as a second witness."""
+    s_all, rng = _replay_all_pairs()
+    H = W = 224
+    s_all[..., 3] = rng.integers(0, H, size=s_all.shape[:3])
+    s_all[..., 4] = rng.integers(0, W, size=s_all.shape[:3])
+    x_all = random_images(256, H, W, 3, seed=77)
+    layer = A.RandAugment(2, 10, elementwise=True)
+    for lo, hi in ((0, 1), (1, 3), (3, 40), (40, 104), (104, 256)):
+        x, s = x_all[lo:hi], np.ascontiguousarray(s_all[lo:hi])
+        r, t = both_engines(layer, to_gpu(x), training=True, replay=s)
+        same = (r == t).flatten(1).all(dim=1).cpu().numpy()
+        bad = [(oracle.OP_NAMES[s[b, 0, 0, 0]], oracle.OP_NAMES[s[b, 1, 0, 0]]) for b in np.nonzero(~same)[0]]
+        assert not bad, "resident != tiles for pairs %r (images %d..%d)" % (bad[:16], lo, hi)
+    idx = list(range(96, 112)) + list(range(240, 256))   # Sharpness-first and Rotate-first chains
+    with engine("resident"):
+        y = layer(to_gpu(x_all[idx]), training=True, replay=np.ascontiguousarray(s_all[idx])).cpu().numpy()
+        t = to_gpu(x_all[idx])
+        layer._transform(t, replay=np.ascontiguousarray(s_all[idx]), out=t)     # d_in == d_out
+    want = oracle.apply_schedule(x_all[idx], policy_of(layer), s_all[idx], elementwise=True)
+    for k, b in enumerate(idx):
+        assert_same(y[k], want[k], "pair %s -> %s" % (oracle.OP_NAMES[s_all[b, 0, 0, 0]], oracle.OP_NAMES[s_all[b, 1, 0, 0]]))
+    assert (t.cpu().numpy() == y).all(), "in-place call differs"
+    for B in (5, 37, 150, 511, 512, 513):
+        x = random_images(B, 64, 64, 3, seed=B)
+        for pol in (A.RandAugment(3, 10, elementwise=True), A.AutoAugment(elementwise=True)):
+            with engine("resident"):
+                y = pol(to_gpu(x), training=True, seed=B, call_counter=2, record=True).cpu().numpy()
+            want = oracle.apply_schedule(x, policy_of(pol), pol.last_schedule, elementwise=True)
+            assert_same(y, want, "%s B=%d" % (type(pol).__name__, B))
+
+
+def test_closed_form_blend_and_presence_histogram(A):
+    """l1 as one blend op is evaluated arithmetically by the flat executor (Brightness / Contrast at
+    factors below and above 1, Contrast's constant 196 at 224 x 224 and 255 in batch mode), and
+    AutoContrast behind a monotone table takes a min / max pass instead of a histogram -- including
+    the cases that must NOT take the shortcuts: a second point-wise op on top of the blend, a
+    non-monotone table (Solarize, SolarizeAdd) in front of AutoContrast, Equalize right after
+    AutoContrast (the presence-only histogram may not be reused), narrow-range images."""
+    seq = A.Sequential
+    chains = [seq([A.Brightness(f)]) for f in (1.9, 0.28, 2.8, 0.999, 1.0, 0.0)] + \
+             [seq([A.Contrast(f)]) for f in (1.9, 0.46, 2.8)] + \
+             [seq([A.Brightness(1.9), A.Invert()]), seq([A.Contrast(1.9), A.Brightness(0.5)]), seq([A.Invert(), A.Brightness(1.3)]),
+              seq([A.AutoContrast()]), seq([A.Brightness(0.4), A.AutoContrast()]), seq([A.Invert(), A.AutoContrast()]),
+              seq([A.Posterize(3), A.AutoContrast()]), seq([A.Solarize(100), A.AutoContrast()]), seq([A.SolarizeAdd(60), A.AutoContrast()]),
+              seq([A.AutoContrast(), A.Equalize()]), seq([A.AutoContrast(), A.Solarize(77), A.AutoContrast()]),
+              seq([A.Brightness(0.3), A.AutoContrast(), A.AutoContrast()]), seq([A.Equalize(), A.AutoContrast()]),
+              seq([A.CutOut(40, 9), A.AutoContrast()]), seq([A.Color(0.3), A.AutoContrast()]), seq([A.Contrast(0.2), A.AutoContrast(), A.Brightness(1.5)])]
+    for ew in (True, False):
+        layer = A.RandomChoice(chains, 1, elementwise=ew)
+        n = len(chains)
+        x = random_images(2 * n, 224, 224, 3, seed=5)
+        x[n:] = (x[n:] // 3 + 40).astype(np.uint8)               # narrow range: AutoContrast really stretches
+        s = np.zeros((2 * n, 1, 3, 5), np.int32)
+        s[:, 0, :, 0] = np.tile(np.arange(n), 2)[:, None]
+        s[..., 1] = 1; s[..., 3] = 100; s[..., 4] = 60
+        if ew:
+            r, t = both_engines(layer, to_gpu(x), replay=s)
+            assert torch.equal(r, t), "resident != tiles"
+            want = oracle.apply_schedule(x, policy_of(layer), s, elementwise=True)
+            got = r.cpu().numpy()
+            for b in range(2 * n):
+                assert_same(got[b], want[b], "chain %d (%s)" % (b % n, "/".join(type(l).__name__ for l in chains[b % n].layers)))
+        else:  # batch mode: one chain for the whole batch (Contrast's constant becomes 255)
+            for k in range(n):
+                sk = s.copy(); sk[:, 0, :, 0] = k
+                with engine("resident"):
+                    got = layer(to_gpu(x[:6]), replay=sk[:6]).cpu().numpy()
+                want = oracle.apply_schedule(x[:6], policy_of(layer), sk[:6], elementwise=False)
+                assert_same(got, want, "batch mode chain %d" % k)
