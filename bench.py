@@ -278,6 +278,27 @@ def workload_config(args, sample_note=None):
     return cfg
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU BEFORE any pinned buffer
+    is allocated, so the e2e path's host buffers are first-touched on the GPU's own NUMA node (8 ranks reading
+    and writing host memory through one socket was part of round 1's poor e2e scaling).  Returns the number of
+    CPUs bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------------- native arm
 def run_native(args, rank, local_rank, world):
     import torch
@@ -289,6 +310,7 @@ def run_native(args, rank, local_rank, world):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1 and not dist.is_initialized():
@@ -374,7 +396,8 @@ def run_native(args, rank, local_rank, world):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": total * e2e_steps / float(tt), "unit": "images/s",
                "h2d_bytes_per_step": B * img_bytes, "d2h_bytes_per_step": B * img_bytes,
-               "steps": e2e_steps, "api": "RandomChoice.__call__(pinned host tensor) -> chb_policy_apply_host"}
+               "steps": e2e_steps, "api": "RandomChoice.__call__(pinned host tensor) -> chb_policy_apply_host",
+               "cpus_bound_per_rank": affinity}
 
     # position-weighted checksum of the whole job's output for call 0 (strong scaling: equal for every GPU count
     # iff the concatenated pixels are equal)

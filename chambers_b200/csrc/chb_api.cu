@@ -44,7 +44,7 @@ static long long g_nf_first_images = 6;  // a batch is also "small" below this m
 static int g_self_clean = 1;         // CHB_SELF_CLEAN=0: zero the counters with a memset in front of every call instead
 static int g_chunk_kb = 2560;       // target chunk size of the host path in KiB (CHB_E2E_CHUNK_KB)
 static int g_lpt = 1;               // resident engine: cost-sorted claim order for small batches (CHB_LPT=0 disables)
-static int g_split_pct = 90;        // resident engine: split an item that would outlast this % of the average SM's load (CHB_SPLIT_PCT)
+static int g_split_pct = 80;        // resident engine: split an item that would outlast this % of the average SM's load (CHB_SPLIT_PCT)
 static int g_split = 1;             // resident engine: small batches cut expensive last passes into row ranges (CHB_SPLIT=0 disables)
 
 struct chb_ctx {

@@ -322,6 +322,16 @@ __device__ __forceinline__ bool src_raw(float v, float nmh, uint32_t& raw) {
   return (v > -0.5f) && (v < nmh);
 }
 
+// src_index for BOTH coordinates of a pixel with one combined validity: the four range tests are joined
+// with non-short-circuit ANDs so that they become one predicate chain and ONE select of the address
+// (the separate tests compiled to four SELs per pixel, profiles/r02_ncu_op_Rotate_b2048.txt).
+__device__ __forceinline__ bool src_index2(float vx, float vy, int W, int H, int& ix, int& iy) {
+  const uint32_t ux = __float_as_uint(__fadd_rz(vx, 4194304.5f)), uy = __float_as_uint(__fadd_rz(vy, 4194304.5f));
+  ix = (int)((ux - 0x4A800000u) >> 1);
+  iy = (int)((uy - 0x4A800000u) >> 1);
+  return (vx > -0.5f) & (vy > -0.5f) & ((uint32_t)ix < (uint32_t)W) & ((uint32_t)iy < (uint32_t)H);
+}
+
 // One or two spatial entries (all a RandAugment(N=2) chain can produce), K in {none, Color}: the
 // per-pixel arithmetic of the tile engine's gather_warp (exact float32 coordinates, src_index), the
 // source being the resident image.
@@ -369,6 +379,7 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
 #pragma unroll
     for (int g = 0; g < G; ++g) {
     const int x0 = xu + 4 * g;
+    const float fx0 = small_uint_to_float((uint32_t)x0);
     uint32_t adr[4];
     uint32_t hit = 0;  // bit i: pixel i shows entry a's colour, bit 4 + i: entry b's
 #pragma unroll
@@ -399,11 +410,9 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
       adr[i] = !(hit_a || hit_b) ? base_raw + ry * (uint32_t)pitch + rx * (uint32_t)C : (hit_a ? fa_addr : fb_addr);
 #else
       if (a_geom) {
-        const float fx = small_uint_to_float((uint32_t)ix);
+        const float fx = (i == 0) ? fx0 : __fadd_rn(fx0, (float)i);  // exact: small integers
         int jx, jy;
-        const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(t0, fx), t1y), t2), W, jx);
-        const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(t3, fx), t4y), t5), H, jy);
-        hit_a = !(inx && iny);
+        hit_a = !src_index2(__fadd_rn(__fadd_rn(__fmul_rn(t0, fx), t1y), t2), __fadd_rn(__fadd_rn(__fmul_rn(t3, fx), t4y), t5), W, H, jx, jy);
         ix = jx; iy = jy;
       } else {
         hit_a = (iy >= ea.y0) && (iy < ea.y1) && (ix >= ea.x0) && (ix < ea.x1);
@@ -412,15 +421,14 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
         if (b_geom) {
           const float gx = small_uint_to_float((uint32_t)ix), gy = small_uint_to_float((uint32_t)iy);
           int jx, jy;
-          const bool inx = src_index(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[0], gx), __fmul_rn(eb.t[1], gy)), eb.t[2]), W, jx);
-          const bool iny = src_index(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[3], gx), __fmul_rn(eb.t[4], gy)), eb.t[5]), H, jy);
-          hit_b = !(inx && iny);
+          hit_b = !src_index2(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[0], gx), __fmul_rn(eb.t[1], gy)), eb.t[2]),
+                              __fadd_rn(__fadd_rn(__fmul_rn(eb.t[3], gx), __fmul_rn(eb.t[4], gy)), eb.t[5]), W, H, jx, jy);
           ix = jx; iy = jy;
         } else {
-          hit_b = (iy >= eb.y0) && (iy < eb.y1) && (ix >= eb.x0) && (ix < eb.x1);
+          hit_b = (iy >= eb.y0) & (iy < eb.y1) & (ix >= eb.x0) & (ix < eb.x1);
         }
       }
-      adr[i] = !(hit_a || hit_b) ? c.img + (uint32_t)(iy * pitch + ix * C) : (hit_a ? fa_addr : fb_addr);
+      adr[i] = !(hit_a | hit_b) ? c.img + (uint32_t)(iy * pitch + ix * C) : (hit_a ? fa_addr : fb_addr);
 #endif
       hit |= (hit_a ? 1u : 0u) << i | (hit_b ? 16u : 0u) << i;
     }
@@ -998,8 +1006,7 @@ __device__ void plan_order(const KParams& p, const DevOp* ops, ResCtl* ctl, uint
   constexpr int NR = LPT_MAX / RNT;             // images per thread
   const int B = p.B;
   const int lane = tid & 31;
-  const bool split = p.res_split && B <= SPLIT_MAX;
-  const int slots = split ? 4 : 1;              // item id = image * slots + part: the sort is stable in it
+  bool split = p.res_split && B <= SPLIT_MAX;
   for (int i = tid; i < NBK * NBK; i += RNT) scratch[i] = 0;
   int sunk[NR], pend[NR];
   int mine = 0;
@@ -1009,19 +1016,29 @@ __device__ void plan_order(const KParams& p, const DevOp* ops, ResCtl* ctl, uint
     sunk[r] = pend[r] = 0;
     if (i < B) { chain_cost(p, ops, i, sunk[r], pend[r]); mine += sunk[r] + pend[r]; }
   }
-  if (mine) atomicAdd(&ctl->cost_sum, mine);
+  mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+  if (lane == 0 && mine) atomicAdd(&ctl->cost_sum, mine);
   __syncthreads();
   // an item should not outlast KParams::res_split_pct % of the average SM's share of the batch
   const int target = max(12, (int)((long long)ctl->cost_sum * p.res_split_pct / (100 * (long long)gridDim.x)));
   // pass 1: parts and bucket of every image; count per (32-item-id chunk, bucket)
   int bk[NR], parts[NR];
+  int any_split = 0;
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     const int i = r * RNT + tid;
-    bk[r] = 0; parts[r] = 1;
+    parts[r] = 1;
+    if (i < B && split)
+      while (parts[r] < 4 && sunk[r] + pend[r] / parts[r] > target && pend[r] / (parts[r] + 1) >= 15) ++parts[r];  // (only last passes of >= 30 us are worth a second load of the image: Sharpness)
+    any_split |= parts[r] > 1;
+  }
+  split = __syncthreads_or(any_split) != 0;     // nothing to split (e.g. AutoAugment holds no Sharpness): the cheaper one-slot sort
+  const int slots = split ? 4 : 1;              // item id = image * slots + part: the sort is stable in it
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int i = r * RNT + tid;
+    bk[r] = 0;
     if (i < B) {
-      if (split)
-        while (parts[r] < 4 && sunk[r] + pend[r] / parts[r] > target && pend[r] / (parts[r] + 1) >= 8) ++parts[r];
       const int cst = sunk[r] + pend[r] / parts[r];
       bk[r] = NBK - 1 - min(cst >> 1, NBK - 1);
       for (int q = 0; q < parts[r]; ++q) {
@@ -1031,23 +1048,43 @@ __device__ void plan_order(const KParams& p, const DevOp* ops, ResCtl* ctl, uint
     }
   }
   __syncthreads();
-  // exclusive prefix over (bucket major, chunk minor): thread b scans bucket b's chunks, then the bucket totals are scanned
+  // exclusive prefix over (bucket major, chunk minor): a warp scans the chunks of one bucket at a time (lane l
+  // owns chunks l, l + 32, l + 64: at most 96 chunks), then warp 0 scans the 64 bucket totals
   const int n_chunks = (B * slots + 31) >> 5;
   int* bucket_total = reinterpret_cast<int*>(scratch + NBK * NBK);  // (no static shared memory: the kernel takes the SM's whole carve-out dynamically)
-  if (tid < NBK) {
-    int run = 0;
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const int v = scratch[ch * NBK + tid];
-      scratch[ch * NBK + tid] = (uint16_t)run;
-      run += v;
+  for (int b = tid >> 5; b < NBK; b += RNT / 32) {
+    int v[3], run = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int ch = lane + 32 * k;
+      v[k] = ch < n_chunks ? (int)scratch[ch * NBK + b] : 0;
     }
-    bucket_total[tid] = run;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      int incl = v[k];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const int ch = lane + 32 * k;
+      if (ch < n_chunks) scratch[ch * NBK + b] = (uint16_t)(run + incl - v[k]);
+      run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) bucket_total[b] = run;
   }
   __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int b = 0; b < NBK; ++b) { const int v = bucket_total[b]; bucket_total[b] = run; run += v; }
-    ctl->n_items = run;
+  if (tid < 32) {
+    const int a = bucket_total[2 * tid], b2 = bucket_total[2 * tid + 1];
+    int incl = a + b2;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (tid >= d) incl += o;
+    }
+    bucket_total[2 * tid] = incl - a - b2;
+    bucket_total[2 * tid + 1] = incl - b2;
+    if (tid == 31) ctl->n_items = incl;
   }
   __syncthreads();
   // pass 2: position = bucket start + items of the bucket in earlier chunks + rank among the chunk's item ids
@@ -1056,27 +1093,24 @@ __device__ void plan_order(const KParams& p, const DevOp* ops, ResCtl* ctl, uint
     const int i = r * RNT + tid;
     const bool valid = i < B;
     if (split) {
-      // a chunk of 32 item ids is 8 images (lanes 8k .. 8k+7 of a warp... any 8 consecutive images): rank by a
-      // scan over the 8 images of the chunk
-      const unsigned act = __ballot_sync(0xFFFFFFFFu, valid);
-      for (int q = 0; q < 4; ++q) {
-        const bool has = valid && q < parts[r];
-        // items of the same chunk and bucket with a smaller id: images of the same group of 8 with a smaller
-        // index (all their parts), plus this image's earlier parts
-        int rank = q;
-        const int grp = lane & ~7;
-        for (int o = 0; o < 8; ++o) {
-          const int ob = __shfl_sync(0xFFFFFFFFu, bk[r], grp + o);
-          const int op = __shfl_sync(0xFFFFFFFFu, valid ? parts[r] : 0, grp + o);
-          if (grp + o < lane && ob == bk[r]) rank += op;
-        }
-        if (has) {
+      // a chunk of 32 item ids is 8 consecutive images = the 8 lanes lane & ~7 .. of this warp.  Items of the
+      // same chunk and bucket with a smaller id: every part of the earlier images of the group that share the
+      // bucket, plus this image's own earlier parts.
+      if (__ballot_sync(0xFFFFFFFFu, valid) == 0u) continue;  // (warp-uniform: a batch of 256 fills 8 of the 32 warps)
+      int base = 0;
+      const int grp = lane & ~7;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const int ob = __shfl_sync(0xFFFFFFFFu, bk[r], grp + o);
+        const int op = __shfl_sync(0xFFFFFFFFu, valid ? parts[r] : 0, grp + o);
+        if (grp + o < lane && ob == bk[r]) base += op;
+      }
+      if (valid)
+        for (int q = 0; q < parts[r]; ++q) {
           const int id = i * slots + q;
-          const int pos = bucket_total[bk[r]] + scratch[(id >> 5) * NBK + bk[r]] + rank;
+          const int pos = bucket_total[bk[r]] + scratch[(id >> 5) * NBK + bk[r]] + base + q;
           ctl->order[pos] = (uint16_t)(i | (q << ORDER_IMG_BITS) | ((parts[r] - 1) << (ORDER_IMG_BITS + 2)));
         }
-      }
-      (void)act;
     } else {
       const unsigned act = __ballot_sync(0xFFFFFFFFu, valid);
       if (valid) {
