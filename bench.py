@@ -7,17 +7,19 @@ batches (BASELINE.json configs[1]) per B200, weak-scaled over --gpus N with no d
         --master-port P bench.py --gpus N --steps K --warmup W
 
 One JSON line on rank 0.  A "step" is one pass of the policy over one batch:
-  value     whole-job images/s with the inputs already resident in HBM (one plan kernel + one pass
-            kernel per level per step, CUDA-event timed, max over ranks); input/output buffers rotate through a pool larger
-            than L2 so no step re-reads a cached batch
+  value     whole-job images/s with the inputs already resident in HBM (ONE resident_kernel launch per step on
+            the image-resident engine, CUDA-event timed, max over ranks); input/output buffers rotate through a pool
+            larger than L2 so no step re-reads a cached batch
   e2e       the same metric through the public layer API with HOST (pinned) buffers: H2D copy,
             kernels and D2H copy inside the timed region (chb_policy_apply_host)
   roofline  HBM: algorithmic bytes (2*H*W*C per image) / average duration of one step's
-            kernels, against MEASURED_PEAKS.json's measured copy bandwidth; traffic = DRAM bytes of one
-            step from the ncu capture recorded in profiles/r01_traffic.json
+            kernel, against MEASURED_PEAKS.json's measured copy bandwidth; traffic = DRAM bytes of one
+            step from the ncu capture recorded in profiles/r02_traffic.json (tools/gpu_profiles_r02.sh)
   cpu_baseline  the oracle port (numpy restatement of the reference; TensorFlow is not installable
-            here) timed on this box's host cores over a bounded sample -- a reported baseline only
---impl reference times that same CPU port as the reference arm (rank 0 only).
+            here) timed on this box's host cores, whole batches of the native arm's bytes -- a reported baseline only
+--impl reference times that same CPU port as the reference arm (rank 0 only), on the native arm's exact bytes and
+the whole batch per step.  --strong shards ONE fixed batch over the ranks (BASELINE.json configs[2]:
+--policy autoaugment --batch 4096 --strong) and prints a checksum of the whole job's output.
 """
 
 import argparse
