@@ -42,7 +42,7 @@ static const int kPipeMax = 8;      // e2e pipeline: at most this many streams /
 static int g_pipe = 4;              // streams in use (CHB_E2E_STREAMS)
 static long long g_nf_first_images = 6;  // a batch is also "small" below this many images per CTA (CHB_NF_FIRST_IMAGES)
 static int g_self_clean = 1;         // CHB_SELF_CLEAN=0: zero the counters with a memset in front of every call instead
-static int g_chunk_kb = 2560;       // target chunk size of the host path in KiB (CHB_E2E_CHUNK_KB)
+static int g_chunk_kb = 3840;       // target chunk size of the host path in KiB (CHB_E2E_CHUNK_KB)
 static int g_lpt = 1;               // resident engine: cost-sorted claim order for small batches (CHB_LPT=0 disables)
 static int g_split_pct = 80;        // resident engine: split an item that would outlast this % of the average SM's load (CHB_SPLIT_PCT)
 static int g_split = 1;             // resident engine: small batches cut expensive last passes into row ranges (CHB_SPLIT=0 disables)
@@ -926,6 +926,9 @@ extern "C" int chb_policy_apply_host(chb_ctx* ctx, const uint8_t* h_in, uint8_t*
                          seed, call_counter, nullptr, nullptr, 0);
   }
   if (!h_in || !h_out) return fail(ctx, CHB_ERR_INVALID, "NULL image pointer");
+  // (Zero copy was measured and rejected: the resident kernel bulk-loading pinned, device-mapped host buffers
+  // and storing straight back moved 9.6 GB/s each way against 35.8 GB/s for the staged pipeline below,
+  // profiles/r02_ab_notes.md 9.)
   // chunk so that copy-in, kernel and copy-out of neighbouring chunks overlap: small enough that the
   // first copy-in and the last copy-out (which overlap nothing) are short, large enough that a chunk's
   // copies dwarf its launch overheads.

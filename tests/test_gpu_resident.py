@@ -344,3 +344,26 @@ def test_closed_form_blend_and_presence_histogram(A):
                     got = layer(to_gpu(x[:6]), replay=sk[:6]).cpu().numpy()
                 want = oracle.apply_schedule(x[:6], policy_of(layer), sk[:6], elementwise=False)
                 assert_same(got, want, "batch mode chain %d" % k)
+
+
+def test_pinned_host_path(A):
+    """Pinned host tensors through chb_policy_apply_host (staged, chunked copies on rotating streams): same
+    bytes as the device path and as pageable numpy arrays; record on one, replay on the other; output tensor
+    given by the caller; 512 x 512 images (tile engine) as well."""
+    x = random_images(300, 224, 224, 3, seed=12)
+    xp = torch.from_numpy(x).pin_memory()
+    for layer in (A.RandAugment(2, 10, elementwise=True), A.AutoAugment(elementwise=True), A.RandAugment(2, 10, elementwise=False)):
+        dev = layer(to_gpu(x), training=True, seed=3, call_counter=8, image_index_base=50, batch_total=900, record=True)
+        dev_sched = layer.last_schedule
+        hp = layer(xp, training=True, seed=3, call_counter=8, image_index_base=50, batch_total=900, record=True)
+        assert isinstance(hp, torch.Tensor) and not hp.is_cuda
+        assert (layer.last_schedule == dev_sched).all()
+        assert torch.equal(hp, dev.cpu()), "pinned host path != device path"
+        staged = layer(x, training=True, seed=3, call_counter=8, image_index_base=50, batch_total=900)   # pageable numpy
+        assert (staged == hp.numpy()).all()
+        out = torch.empty_like(xp).pin_memory()
+        res = layer._transform(xp, replay=dev_sched, batch_total=900, out=out)
+        assert res.data_ptr() == out.data_ptr() and torch.equal(out, hp)
+    big = torch.from_numpy(random_images(3, 512, 512, 3, seed=1)).pin_memory()
+    ra = A.RandAugment(2, 10, elementwise=True)
+    assert torch.equal(ra(big, training=True, seed=1, call_counter=1), ra(big.cuda(), training=True, seed=1, call_counter=1).cpu())
