@@ -491,7 +491,7 @@ def test_host_path_chunk_pipeline(A):
     last chunk is ragged): bit-identical to the device path, elementwise and batch mode (Contrast's
     constant and the batch-level schedule must be the same in every chunk; CutOut centres are keyed by
     the global image index), record on the host path then replay on both."""
-    B = 157  # 157 x 150528 B = 23.6 MB -> 10 chunks of 16 images, the last one of 13
+    B = 223  # 223 x 150528 B = 33.6 MB -> 9 chunks (3840 KiB target) of 25 images, the last one of 23: every one of the 4 staging slots is reused
     x = random_images(B, 224, 224, 3, seed=77, kind="smooth")
     xg = to_gpu(x)
     kw = dict(interpolation="nearest", fill_mode="constant", fill_value=128.0)
