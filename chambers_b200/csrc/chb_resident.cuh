@@ -1151,6 +1151,21 @@ __device__ __forceinline__ void res_write_pass(RC<C>& c, int store) {
   }
 }
 
+// The chain walk is a sequence of short dependent steps separated by barriers: it runs on the first
+// CHB_WALK_NT threads with a named barrier (a 1024-thread barrier costs ~200 cycles a time, and 32 warps
+// replicating the walk's scalar control flow were 15 % of all executed instructions of a mixed batch,
+// profiles/r02_ncu_op_RandAugment_b2048.txt); the table loops (768 entries) still get enough threads.
+#ifndef CHB_WALK_NT
+#define CHB_WALK_NT 128
+#endif
+template <int C>
+__device__ __forceinline__ void res_advance(ResCtl* ctl, const KParams& pl, int H, int W, int tid) {
+  if (tid < CHB_WALK_NT)
+    advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, CHB_WALK_NT,
+            [] { asm volatile("bar.sync 1, %0;" ::"n"(CHB_WALK_NT) : "memory"); });
+  __syncthreads();
+}
+
 template <int C>
 __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -1249,12 +1264,19 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
     // schedule decode + chain walk up to the first pass (the loads are in flight)
     for (int i = tid; i < STATE_VECS; i += RNT) reinterpret_cast<uint4*>(&ctl->st)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
+#ifdef CHB_TIMELINE
+    if (p.timeline && tid == 0) atomicAdd(p.timeline + 2, tl_now() - tl_t0);  // load issue + state reset
+    unsigned long long tl_ta = tl_now();
+#endif
     // (the first chain walk on ONE warp with warp-level barriers was measured: the 768-entry table loops on
     // 32 threads cost more than the CTA barriers they save -- 4.9 us against 3.0 us of bookkeeping per image)
     if (tid < 32) decode_image(pl, &ctl->st, ctl->rnd, ctl->rndc, img, H, W, tid);
     reset_view(&ctl->st, tid, RNT);
     __syncthreads();
-    advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
+#ifdef CHB_TIMELINE
+    if (p.timeline && tid == 0) atomicAdd(p.timeline + 3, tl_now() - tl_ta);  // schedule decode
+#endif
+    res_advance<C>(ctl, pl, H, W, tid);
     uint8_t* out_img = p.out + (size_t)img * img_bytes;
 #ifdef CHB_TIMELINE
     if (tid == 0) tl_t1 = tl_now();
@@ -1300,7 +1322,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
         res_count_pass<C>(c);
         if (tid == 0) ctl->st.hist_valid = c.minmax ? 2 : 1;
         __syncthreads();
-        advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
+        res_advance<C>(ctl, pl, H, W, tid);
         continue;
       }
       // WRITE_OUT, or WRITE_SCRATCH: point-wise views (and CutOut rectangles, painted over them)
@@ -1346,7 +1368,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
       reset_view(&ctl->st, tid, RNT);
       __syncthreads();
       if (tally && tid == 0) ctl->st.hist_valid = 1;  // reset_view cleared it: the tallied bytes ARE the new source
-      advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, RNT, [] { __syncthreads(); });
+      res_advance<C>(ctl, pl, H, W, tid);
     }
     // every thread is done with the resident source; bulk stores out of it have read their bytes;
     // in-place writes (generic proxy) are ordered before the TMA refills the buffer
