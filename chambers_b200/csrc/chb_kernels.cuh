@@ -513,47 +513,48 @@ __device__ void decode_image(const KParams& p, ImgState* s, uint32_t (*rnd)[4], 
     rndc[lane][2] = wc.z; rndc[lane][3] = wc.w;
   }
   __syncwarp();
-  if (lane == 0) {
-    int n = 0;
-    for (int i = 0; i < p.n_draws; ++i) {
-      const int slot0 = i * (p.K + 1);
-      const size_t rbase = ((size_t)img * p.n_draws + i) * p.K * CHB_SCHED_FIELDS;
-      int choice;
-      if (p.replay) {
-        choice = p.replay[rbase];
-        if (choice < 0 || choice >= p.T) choice = 0;
-      } else {
-        choice = (int)__umulhi(rnd[slot0][0], (uint32_t)p.T);
-      }
-      for (int j = 0; j < p.K; ++j) {
-        const int opi = choice * p.K + j;
-        const int kind = CHB_LDP(&p.ops[opi].kind);
-        int applied, negate, cy, cx;
-        if (p.replay) {
-          const int32_t* r = p.replay + rbase + (size_t)j * CHB_SCHED_FIELDS;
-          applied = (r[1] != 0) && kind >= 0;
-          negate = r[2] != 0;
-          cy = r[3];
-          cx = r[4];
-        } else {
-          const int slot = slot0 + 1 + j;
-          applied = (kind >= 0) && ((int)(rnd[slot][0] >> 8) < CHB_LDP(&p.ops[opi].thr24));
-          negate = rnd[slot][1] < 0x80000000u;
-          cy = (int)__umulhi(rndc[slot][2], (uint32_t)H);
-          cx = (int)__umulhi(rndc[slot][3], (uint32_t)W);
-        }
-        if (p.record) {
-          int32_t* r = p.record + rbase + (size_t)j * CHB_SCHED_FIELDS;
-          r[0] = choice; r[1] = applied; r[2] = negate; r[3] = cy; r[4] = cx;
-        }
-        if (applied && n < CHB_MAX_CHAIN) {
-          s->prog[n].table_index = opi; s->prog[n].negate = negate; s->prog[n].cy = cy; s->prog[n].cx = cx;
-          ++n;
-        }
-      }
+  // one lane per (draw, sub-op) slot -- at most CHB_MAX_CHAIN of them -- in chain order; the applied ops
+  // are compacted into s->prog with a ballot
+  const int n_ops = p.n_draws * p.K;
+  bool applied = false;
+  int opi = 0, negate = 0, cy = 0, cx = 0;
+  if (lane < n_ops) {
+    const int i = lane / p.K, j = lane - i * p.K;
+    const int slot0 = i * (p.K + 1);
+    const size_t rbase = ((size_t)img * p.n_draws + i) * p.K * CHB_SCHED_FIELDS;
+    int choice;
+    if (p.replay) {
+      choice = p.replay[rbase];
+      if (choice < 0 || choice >= p.T) choice = 0;
+    } else {
+      choice = (int)__umulhi(rnd[slot0][0], (uint32_t)p.T);
     }
-    s->n_prog = n;
+    opi = choice * p.K + j;
+    const int kind = CHB_LDP(&p.ops[opi].kind);
+    if (p.replay) {
+      const int32_t* r = p.replay + rbase + (size_t)j * CHB_SCHED_FIELDS;
+      applied = (r[1] != 0) && kind >= 0;
+      negate = r[2] != 0;
+      cy = r[3];
+      cx = r[4];
+    } else {
+      const int slot = slot0 + 1 + j;
+      applied = (kind >= 0) && ((int)(rnd[slot][0] >> 8) < CHB_LDP(&p.ops[opi].thr24));
+      negate = rnd[slot][1] < 0x80000000u;
+      cy = (int)__umulhi(rndc[slot][2], (uint32_t)H);
+      cx = (int)__umulhi(rndc[slot][3], (uint32_t)W);
+    }
+    if (p.record) {
+      int32_t* r = p.record + rbase + (size_t)j * CHB_SCHED_FIELDS;
+      r[0] = choice; r[1] = applied ? 1 : 0; r[2] = negate; r[3] = cy; r[4] = cx;
+    }
   }
+  const unsigned mask = __ballot_sync(0xFFFFFFFFu, applied);
+  const int pos = __popc(mask & ((1u << lane) - 1u));
+  if (applied && pos < CHB_MAX_CHAIN) {
+    s->prog[pos].table_index = opi; s->prog[pos].negate = negate; s->prog[pos].cy = cy; s->prog[pos].cx = cx;
+  }
+  if (lane == 0) s->n_prog = min(__popc(mask), CHB_MAX_CHAIN);
   __syncwarp();
 }
 
