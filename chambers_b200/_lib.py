@@ -83,6 +83,8 @@ SIGNATURES = {
     "chb_autoaugment_table": (_i, [ctypes.POINTER(ChbTransform)]),
     "chb_policy_apply": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChbPolicy), _i64, _i64,
                               _u64, _u32, _vp, _vp, _vp]),
+    "chb_policy_apply_normalized": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChbPolicy), _i, _i64, _i64,
+                                         _u64, _u32, _vp, _vp, _vp]),
     "chb_randaugment": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.c_double, _i, _i64, _i64, _u64,
                              _u32, _vp, _vp, _vp]),
     "chb_autoaugment": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _u64, _u32, _vp, _vp, _vp]),

@@ -165,6 +165,49 @@ def check_uint8(x, who):
                          % (who, dt))
 
 
+def _run_policy_normalized(inputs, transforms, n_draws, elementwise, seed, call_counter, batch_total,
+                           image_index_base, replay, record, built, mode):
+    if mode not in _lib.NORM_MODES:
+        raise ValueError("Unknown mode " + str(mode))
+    if torch is None:
+        raise _lib.ChambersAugError(4, "torch is required as the device-memory provider")
+    is_torch = isinstance(inputs, torch.Tensor)
+    x = inputs if is_torch else torch.from_numpy(np.ascontiguousarray(inputs))
+    on_device = x.is_cuda
+    if not on_device:
+        if not torch.cuda.is_available():
+            _lib.context(0)  # raises with the real reason
+        x = x.cuda(non_blocking=True)
+    x = x.contiguous()
+    B, H, W, C = (int(d) for d in x.shape)
+    if batch_total is None:
+        batch_total = B
+    pol, _keep, K = built if built is not None else build_policy(transforms, n_draws, elementwise)
+    sched_shape = (B, int(n_draws), K, _lib.CHB_SCHED_FIELDS)
+    dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    d_replay = d_record = None
+    if replay is not None:
+        d_replay = torch.as_tensor(np.ascontiguousarray(replay.cpu() if isinstance(replay, torch.Tensor) else replay,
+                                                        dtype=np.int32)).reshape(sched_shape).to(x.device)
+    if record:
+        d_record = torch.zeros(sched_shape, dtype=torch.int32, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ctx = _lib.context(dev)
+        rc = lib.chb_policy_apply_normalized(
+            ctx, x.data_ptr(), out.data_ptr(), B, H, W, C, ctypes.byref(pol), _lib.NORM_MODES[mode], int(batch_total),
+            int(image_index_base), seed, call_counter,
+            d_replay.data_ptr() if d_replay is not None else None,
+            d_record.data_ptr() if d_record is not None else None, torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(ctx, rc)
+    sched = d_record.cpu().numpy() if record else None
+    if on_device:
+        return out, sched
+    res = out.cpu()
+    return (res if is_torch else res.numpy()), sched
+
+
 # ----------------------------------------------------------------------- policy -> C structs
 def build_policy(transforms, n_draws, elementwise):
     """``transforms``: list of lists of (op_layer, probability-or-None).  Returns (ChbPolicy,
@@ -194,12 +237,20 @@ def build_policy(transforms, n_draws, elementwise):
 
 
 def run_policy(inputs, transforms, n_draws, elementwise, seed, call_counter, batch_total=None,
-               image_index_base=0, replay=None, record=False, out=None, built=None):
+               image_index_base=0, replay=None, record=False, out=None, built=None, normalize=None):
     """Apply RandomChoice(transforms, n_draws, elementwise) to ``inputs`` on the GPU.
 
     Returns (output, schedule-or-None).  ``inputs``: torch CUDA uint8 NHWC (stream-ordered device
-    path) or numpy / CPU torch uint8 (host path, synchronous)."""
+    path) or numpy / CPU torch uint8 (host path, synchronous).
+
+    ``normalize`` ("tf" | "torch" | "caffe", an extension of the reference API): also apply
+    ``ImageNetNormalization(mode)`` -- the layer every chambers backbone puts right behind the policy --
+    and return float32; on the image-resident engine it is the write epilogue of the policy's last pass
+    (``chb_policy_apply_normalized``)."""
     check_uint8(inputs, "RandomChoice")
+    if normalize is not None:
+        return _run_policy_normalized(inputs, transforms, n_draws, elementwise, seed, call_counter, batch_total,
+                                      image_index_base, replay, record, built, normalize)
     B, H, W, C = (int(d) for d in inputs.shape)
     if batch_total is None:
         batch_total = B

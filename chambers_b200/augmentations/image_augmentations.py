@@ -350,7 +350,7 @@ class RandomChoice(Layer):
         self.elementwise = elementwise
 
     def call(self, inputs, seed=None, call_counter=None, replay=None, record=False, batch_total=None,
-             image_index_base=0, out=None, **kwargs):
+             image_index_base=0, out=None, normalize=None, **kwargs):
         seed, call_counter = self._stream(seed, call_counter)
         # the C structs of the policy are built once per (transforms, n, elementwise): per call this
         # costs tens of microseconds of Python, more than the kernels of a small batch
@@ -362,7 +362,7 @@ class RandomChoice(Layer):
             self._built_policy = cached
         res, sched = run_policy(inputs, cached[1], self.n_transforms, self.elementwise, seed, call_counter,
                                 batch_total=batch_total, image_index_base=image_index_base,
-                                replay=replay, record=record, out=out, built=cached[2])
+                                replay=replay, record=record, out=out, built=cached[2], normalize=normalize)
         self.last_schedule = sched
         return res
 

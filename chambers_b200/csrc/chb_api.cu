@@ -36,6 +36,8 @@ struct Workspace {
   size_t scratch_bytes = 0;
   uint8_t* inplace = nullptr;
   size_t inplace_bytes = 0;
+  uint8_t* norm_tmp = nullptr;       // uint8 policy output in front of an unfused normalisation
+  size_t norm_tmp_bytes = 0;
 };
 
 static const int kPipeMax = 8;      // e2e pipeline: at most this many streams / staging buffers
@@ -427,6 +429,7 @@ extern "C" void chb_destroy(chb_ctx* ctx) {
   for (PolicyEntry* pe : ctx->cache) { cudaFree(pe->dev); cudaFree(pe->optab); delete pe; }
   for (Workspace* ws : ctx->workspaces) {
     cudaFree(ws->states); cudaFree(ws->lists); cudaFree(ws->counters); cudaFree(ws->scratch); cudaFree(ws->inplace);
+    cudaFree(ws->norm_tmp);
     delete ws;
   }
   for (int i = 0; i < kPipeMax; ++i) {
@@ -626,7 +629,7 @@ static bool resident_eligible(const chb_ctx* ctx, const PolicyEntry* pe, const u
 static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int B, int H, int W, int C,
                          const chb_policy* pol, int64_t batch_total, int64_t image_index_base,
                          uint64_t seed, uint32_t call_counter, const int32_t* d_replay,
-                         int32_t* d_record, cudaStream_t stream) {
+                         int32_t* d_record, cudaStream_t stream, float* d_outf = nullptr, int norm_mode = -1) {
   if (!ctx) return CHB_ERR_INVALID;
   if (B < 0 || H < 0 || W < 0) return fail(ctx, CHB_ERR_INVALID, "negative shape");
   if (C < 1 || C > 4) return fail(ctx, CHB_ERR_UNSUPPORTED, "channels must be 1..4");
@@ -641,7 +644,7 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   r = get_policy(ctx, pol, K, H, W, C, batch_total, stream, &pe);  // validates ops even when B == 0
   if (r != CHB_OK) return r;
   if (B == 0 || H == 0 || W == 0) return CHB_OK;
-  if (!d_in || !d_out) return fail(ctx, CHB_ERR_INVALID, "NULL image pointer");
+  if (!d_in || (!d_out && !d_outf)) return fail(ctx, CHB_ERR_INVALID, "NULL image pointer");
   const size_t img_bytes = (size_t)H * W * C;
   const chb::TilePlan tp = chb::plan_tiles(H, W);
   if ((unsigned long long)B * 2ull * (unsigned long long)tp.n_tiles >= 0xFFFF0000ull)
@@ -653,12 +656,33 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
   // launch holds a ticket (chb_kernels.cuh), so a call is one plan launch and one pass launch
   // whatever the chain length.
   // tiles read neighbours of their own region: an in-place call goes through a temporary.
-  const bool overlap = (d_in < d_out + (size_t)B * img_bytes) && (d_out < d_in + (size_t)B * img_bytes);
+  // Fused ImageNetNormalization epilogue (d_outf): the resident engine writes float32 from its last pass (modes tf /
+  // torch).  Anything else -- caffe's channel reversal, calls only the tile engine can take -- runs the policy into a
+  // library-owned uint8 buffer and the standalone normalisation kernel behind it (same bytes, one more pass).
+  if (d_outf) {
+    const bool fusable = (norm_mode == CHB_NORM_TF || norm_mode == CHB_NORM_TORCH) && (((uintptr_t)d_outf) & 15) == 0 &&
+                         resident_eligible(ctx, pe, d_in, d_in, H, W, C);
+    if (!fusable) {
+      Workspace* wt = nullptr;
+      r = get_workspace(ctx, stream, 1, 0, 0, &wt);
+      if (r != CHB_OK) return r;
+      r = grow(ctx, (void**)&wt->norm_tmp, &wt->norm_tmp_bytes, (size_t)B * img_bytes);
+      if (r != CHB_OK) return r;
+      r = launch_device(ctx, d_in, wt->norm_tmp, B, H, W, C, pol, batch_total, image_index_base, seed, call_counter, d_replay, d_record, stream);
+      if (r != CHB_OK) return r;
+      cudaError_t e = chb::launch_normalize(wt->norm_tmp, 0, d_outf, (unsigned long long)B * img_bytes, C, norm_mode, ctx->num_sms, stream);
+      if (e != cudaSuccess) return cuda_fail(ctx, e, "normalize kernel launch");
+      ctx->launches += 1;
+      return CHB_OK;
+    }
+    d_out = nullptr;
+  }
+  const bool overlap = d_out && (d_in < d_out + (size_t)B * img_bytes) && (d_out < d_in + (size_t)B * img_bytes);
   const size_t stride = (img_bytes + 255) / 256 * 256;
   Workspace* ws = nullptr;
   // The resident engine reads an image completely before it writes any byte of it and never reads
   // another image's bytes: d_in == d_out needs no temporary there (a partial overlap still does).
-  const bool resident = resident_eligible(ctx, pe, d_in, d_out, H, W, C);
+  const bool resident = resident_eligible(ctx, pe, d_in, d_out ? d_out : d_in, H, W, C);
   if (ctx->engine == CHB_ENGINE_RESIDENT && !resident)
     return fail(ctx, CHB_ERR_UNSUPPORTED, "CHB_ENGINE_RESIDENT: this call is not eligible for the image-resident engine");
   if (resident) {
@@ -679,6 +703,7 @@ static int launch_device(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int 
     p.scratch = ws->scratch; p.scratch_stride = stride;
     p.counters = ws->counters;
     p.res_smem_bytes = ctx->res_smem;
+    p.outf = d_outf; p.norm_mode = norm_mode;
     p.res_lpt = g_lpt;
     p.res_rules = 1;
     p.res_split_pct = g_split_pct;
@@ -781,6 +806,20 @@ extern "C" int chb_policy_apply(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_ou
                                 const int32_t* d_replay, int32_t* d_record, void* stream) {
   return launch_device(ctx, d_in, d_out, B, H, W, C, policy, batch_total, image_index_base, seed,
                        call_counter, d_replay, d_record, (cudaStream_t)stream);
+}
+
+extern "C" int chb_policy_apply_normalized(chb_ctx* ctx, const uint8_t* d_in, float* d_out, int B, int H, int W, int C,
+                                           const chb_policy* policy, int norm_mode, int64_t batch_total,
+                                           int64_t image_index_base, uint64_t seed, uint32_t call_counter,
+                                           const int32_t* d_replay, int32_t* d_record, void* stream) {
+  if (!ctx) return CHB_ERR_INVALID;
+  if (norm_mode != CHB_NORM_CAFFE && norm_mode != CHB_NORM_TF && norm_mode != CHB_NORM_TORCH)
+    return fail(ctx, CHB_ERR_INVALID, "Unknown mode");
+  if (norm_mode != CHB_NORM_TF && C != 3)
+    return fail(ctx, CHB_ERR_INVALID, "caffe / torch normalisation broadcast 3-element constants: C must be 3");
+  if (!d_out && (long long)B * H * W > 0) return fail(ctx, CHB_ERR_INVALID, "NULL image pointer");
+  return launch_device(ctx, d_in, nullptr, B, H, W, C, policy, batch_total, image_index_base, seed, call_counter,
+                       d_replay, d_record, (cudaStream_t)stream, d_out, norm_mode);
 }
 
 extern "C" int chb_randaugment(chb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int B, int H, int W,

@@ -274,5 +274,22 @@ __device__ __forceinline__ void affine_source(const float* t, int x, int y, floa
   sy = __fadd_rn(__fadd_rn(__fmul_rn(t[3], fx), __fmul_rn(t[4], fy)), t[5]);
 }
 
+// ImageNetNormalization.call, image_augmentations.py:629-682 (chb_frontend.cu and the fused write epilogue of
+// the resident engine).
+// float32 steps of the reference, one rounding per op (TensorFlow's CPU kernels do not contract):
+//   tf     :660-665   x / 127.5 - 1.0
+//   torch  :652-657   ((x / 255.0) - mean[c]) / std[c]
+//   caffe  :647-650   x[..., ::-1] - mean[c]        (c indexes the REVERSED channels)
+__device__ __forceinline__ float norm_value(float x, int mode, int c) {
+  if (mode == CHB_NORM_TF) return __fsub_rn(__fdiv_rn(x, 127.5f), 1.0f);
+  if (mode == CHB_NORM_TORCH) {
+    const float mean = c == 0 ? 0.485f : c == 1 ? 0.456f : 0.406f;
+    const float sd = c == 0 ? 0.229f : c == 1 ? 0.224f : 0.225f;
+    return __fdiv_rn(__fsub_rn(__fdiv_rn(x, 255.0f), mean), sd);
+  }
+  const float mean = c == 0 ? 103.939f : c == 1 ? 116.779f : 123.68f;
+  return __fsub_rn(x, mean);
+}
+
 }  // namespace
 }  // namespace chb

@@ -118,6 +118,8 @@ struct KParams {
   int flags;                          // 1: in is 16-byte aligned, 2: out is, 4: images are whole 16-byte units, 8: rows are
   unsigned long long* timeline;       // debug builds (-DCHB_TIMELINE): [1024 CTAs][2][16] words, else NULL
   int res_smem_bytes;                 // resident engine: dynamic shared memory of a CTA (control + policy + image + aux region)
+  float* outf;                        //   fused ImageNetNormalization epilogue: float32 output (NULL: uint8 output to `out`)
+  int norm_mode;                      //   chb_norm_mode of the epilogue (CHB_NORM_TF / CHB_NORM_TORCH)
   int res_lpt;                        //   1: small batches are claimed most-expensive-chain-first (CHB_LPT=0 disables)
   int res_rules;                      //   1: advance() materialises non-flat views in front of Sharpness / a histogram op
   int res_sharp_rows[4];              //   Sharpness: rows per sub-strip of the column walk, last pass cut into 1..4 row ranges

@@ -58,6 +58,7 @@ struct alignas(128) ResCtl {
   uint8_t etab[MAXC * 256];
   KParams kp;                          // the launch parameters with ops / optab pointing at the shared-memory copy
   uint16_t order[LPT_MAX];             // small batches: claim position -> image, most expensive chains first
+  float nlut[3][256];                  // fused ImageNetNormalization epilogue: value -> float32, per channel
   ImgState st;
 };
 
@@ -80,6 +81,8 @@ struct RC {
   int tally;           // WRITE pass: also count the bytes written (the materialised view feeds a histogram op next)
   int y_lo, y_hi;      // WRITE passes: output rows this CTA produces (the whole image unless a small batch split the image's last pass)
   int sharp_rows;      // Sharpness: rows per sub-strip of the column walk for this row range
+  float* dstf;         // last pass with the fused normalisation epilogue: float32 destination image (else NULL)
+  uint32_t nlut;       //   shared address of the value -> float table
   int minmax;          // COUNT pass: only the smallest and largest value per channel are needed (AutoContrast on a monotone l1)
 };
 
@@ -155,6 +158,19 @@ __device__ __forceinline__ void blend_unit(uint32_t* w, int extrap, int a, float
     }
     w[j] = o;
   }
+}
+
+// Fused ImageNetNormalization epilogue (modes tf / torch: no channel reversal): the 4 bytes of output word
+// `widx` of the image (channel of byte 0 = ph) leave as one float4 -- the table holds exactly the float32
+// values the standalone layer would compute from the uint8 result.
+template <int C>
+__device__ __forceinline__ void store_norm_word(const RC<C>& c, size_t widx, int ph, uint32_t w) {
+  float4 f;
+  f.x = __uint_as_float(lds_u32(c.nlut + (uint32_t)(((ph + 0) % C) % 3) * 1024u + (byte_of(w, 0) << 2)));
+  f.y = __uint_as_float(lds_u32(c.nlut + (uint32_t)(((ph + 1) % C) % 3) * 1024u + (byte_of(w, 1) << 2)));
+  f.z = __uint_as_float(lds_u32(c.nlut + (uint32_t)(((ph + 2) % C) % 3) * 1024u + (byte_of(w, 2) << 2)));
+  f.w = __uint_as_float(lds_u32(c.nlut + (uint32_t)(((ph + 3) % C) % 3) * 1024u + (byte_of(w, 3) << 2)));
+  __stcs(reinterpret_cast<float4*>(c.dstf) + widx, f);
 }
 
 // ================================================================================ flat executor
@@ -268,7 +284,14 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
             asm volatile("st.shared.u8 [%0], %1;" ::"r"(c.img + (uint32_t)pix_b), "r"(e.color[rb % C]) : "memory");
         }
       }
-      if (store) {
+      if (store && c.dstf) {
+        // normalisation epilogue: the step's words are read back (consecutive lanes, consecutive words) and
+        // leave as coalesced float4 stores
+        __syncthreads();
+        const int w0 = base * UW, w1 = u1 * UW;
+        for (int wi = w0 + c.tid; wi < w1; wi += RNT)
+          store_norm_word(c, (size_t)wi, (C == 3) ? (wi % 3) : 0, lds_u32(c.img + ((uint32_t)wi << 2)));
+      } else if (store) {
         fence_proxy_async();  // this thread's shared-memory writes -> visible to the TMA
         __syncthreads();
         if (c.tid == 0) {
@@ -506,6 +529,11 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
           const int bi = i * C + ch;
           o[bi >> 2] = ((bi & 3) == 0) ? v[i][ch] : put_byte(o[bi >> 2], v[i][ch], bi & 3);  // (every v is a zero-extended byte)
         }
+      if (c.dstf) {
+        const size_t w0 = (((size_t)y * W + x0) * C) >> 2;  // a quad is C whole words starting at channel 0
+#pragma unroll
+        for (int w = 0; w < C; ++w) store_norm_word(c, w0 + w, (4 * w) % C, o[w]);
+      } else {
       uint32_t* gp = reinterpret_cast<uint32_t*>(c.dst + ((size_t)y * W + x0) * C);
       if (C == 4) {
         __stcg(reinterpret_cast<uint4*>(gp), make_uint4(o[0], o[1 % C], o[2 % C], o[3 % C]));
@@ -514,6 +542,7 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
       } else {
 #pragma unroll
         for (int w = 0; w < C; ++w) __stcg(gp + w, o[w]);
+      }
       }
     }
     }
@@ -645,6 +674,12 @@ __device__ __forceinline__ void res_gather_rowshift(const RC<C>& c) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) hist_add(c, (4 * k + b) % C, byte_of(o[k], b));
     }
+    if (!COUNT && c.dstf) {
+      const size_t w0 = (((size_t)y * W + x0) * C) >> 2;
+#pragma unroll
+      for (int w = 0; w < C; ++w) store_norm_word(c, w0 + w, (4 * w) % C, o[w]);
+      continue;
+    }
     uint32_t* gp = reinterpret_cast<uint32_t*>(c.dst + ((size_t)y * W + x0) * C);
     if (C == 4) {
       __stcg(reinterpret_cast<uint4*>(gp), make_uint4(o[0], o[1 % C], o[2 % C], o[3 % C]));
@@ -717,6 +752,12 @@ __device__ __forceinline__ void res_gather_list(const RC<C>& c) {
       if (c.tally) {
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) hist_add(c, ch, v[ch] & 255u);
+      }
+      if (c.dstf) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch)
+          c.dstf[(size_t)i * C + ch] = __uint_as_float(lds_u32(c.nlut + (uint32_t)(ch % 3) * 1024u + ((v[ch] & 255u) << 2)));
+        continue;
       }
       uint8_t* d = c.dst + (size_t)i * C;
 #pragma unroll
@@ -884,7 +925,8 @@ __device__ __forceinline__ void res_sharp(const RC<C>& c) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) hist_add(c, (ph + b) % C, byte_of(o, b));
       }
-      __stcg(reinterpret_cast<uint32_t*>(c.dst + (size_t)y * row) + xw, o);
+      if (c.dstf) store_norm_word(c, (size_t)y * (size_t)(row >> 2) + (size_t)xw, ph, o);
+      else __stcg(reinterpret_cast<uint32_t*>(c.dst + (size_t)y * row) + xw, o);
     }
   };
   // first and last image row: every pixel is border -> blend(orig, orig) == orig
@@ -1218,6 +1260,10 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
     ctl->kp.optab = s_optab;
   }
   const KParams& pl = ctl->kp;
+  if (p.outf)  // fused normalisation epilogue: the 3 x 256 float32 values of the standalone layer
+    for (int i = tid; i < 3 * 256; i += RNT) ctl->nlut[i >> 8][i & 255] = norm_value((float)(i & 255), p.norm_mode, i >> 8);
+  c.nlut = smem_addr(&ctl->nlut[0][0]);
+  c.dstf = nullptr;
   __syncthreads();
   // small batches: positions map to images through the cost-sorted order (all images share one chain in
   // batch mode: nothing to sort)
@@ -1277,7 +1323,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
     if (p.timeline && tid == 0) atomicAdd(p.timeline + 3, tl_now() - tl_ta);  // schedule decode
 #endif
     res_advance<C>(ctl, pl, H, W, tid);
-    uint8_t* out_img = p.out + (size_t)img * img_bytes;
+    uint8_t* out_img = p.outf ? nullptr : p.out + (size_t)img * img_bytes;
 #ifdef CHB_TIMELINE
     if (tid == 0) tl_t1 = tl_now();
 #endif
@@ -1338,6 +1384,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
       for (int k = 0; k < t.n_sp; ++k) any_geom = any_geom || (t.sp[k].type == SP_GEOM);
       const bool in_place = !last && (t.kmode == K_NONE || t.kmode == K_COLOR) && !any_geom;
       c.dst = last ? out_img : scratch;
+      c.dstf = (last && p.outf) ? p.outf + (size_t)img * img_bytes : nullptr;
       c.y_lo = last ? (H * part) / n_parts : 0;
       c.y_hi = last ? (H * (part + 1)) / n_parts : H;
       c.sharp_rows = ctl->sharp_rows[last ? n_parts - 1 : 0];

@@ -180,6 +180,17 @@ enum chb_norm_mode { CHB_NORM_CAFFE = 0, CHB_NORM_TF = 1, CHB_NORM_TORCH = 2 };
 int chb_imagenet_normalize(chb_ctx* ctx, const void* d_in, int in_is_f32, float* d_out, int64_t n_values, int C,
                            int mode, void* stream);
 
+/* The policy followed by ImageNetNormalization(mode) -- the reference's call order in front of every backbone
+ * (RandAugment / AutoAugment, then preprocess_input = ImageNetNormalization(mode="tf"), vision_transformer.py:655) --
+ * as ONE call: d_out is float32 NHWC of the input's shape and holds exactly what chb_imagenet_normalize would
+ * produce from chb_policy_apply's uint8 result.  On the image-resident engine (modes tf / torch) the
+ * normalisation is the write epilogue of the policy's last pass (no uint8 image is written or re-read);
+ * otherwise the library runs the two kernels back to back through a buffer of its own. */
+int chb_policy_apply_normalized(chb_ctx* ctx, const uint8_t* d_in, float* d_out, int B, int H, int W, int C,
+                                const chb_policy* policy, int norm_mode, int64_t batch_total,
+                                int64_t image_index_base, uint64_t seed, uint32_t call_counter,
+                                const int32_t* d_replay, int32_t* d_record, void* stream);
+
 /* ResizingMinMax(min_side, max_side, interpolation)(x), image_augmentations.py:685-748.
  * chb_resize_min_max_shape is the size arithmetic of :711-730 (float32 scale, truncating casts);
  * min_side / max_side <= 0 mean None; returns CHB_ERR_INVALID if both are.  chb_resize is the

@@ -98,3 +98,36 @@ def test_resizing_min_max(A, ref):
     xf = rng.random(size=(2, 40, 30, 3)).astype(np.float32)
     got = A.ResizingMinMax(min_side=64)(xf)                      # float32 numpy in -> numpy out
     assert isinstance(got, np.ndarray) and np.array_equal(got, oracle.resizing_min_max(xf, min_side=64))
+
+
+@pytest.mark.parametrize("mode", ["tf", "torch", "caffe"])
+def test_fused_normalization_epilogue(A, mode):
+    """policy(x, normalize=mode) == ImageNetNormalization(mode)(policy(x)) bit for bit: every ordered op pair at
+    224 x 224 (flat, gather, row-shift and Sharpness last passes all write float32 from the resident engine for
+    tf / torch; caffe and the tile engine take the two-kernel fallback inside the library), a small batch that
+    splits images over several CTAs, AutoAugment, numpy in / out, and the oracle on a sample."""
+    from test_gpu_parity import policy_of, _replay_all_pairs
+    s, rng = _replay_all_pairs()
+    s[..., 3] = rng.integers(0, 224, size=s.shape[:3])
+    s[..., 4] = rng.integers(0, 224, size=s.shape[:3])
+    x = random_images(256, 224, 224, 3, seed=31)
+    xg = torch.from_numpy(x).cuda()
+    ra = A.RandAugment(2, 10, elementwise=True)
+    norm = A.ImageNetNormalization(mode=mode)
+    for lo, hi in ((0, 256), (96, 112), (200, 203)):
+        want = norm(ra(xg[lo:hi], training=True, replay=s[lo:hi]))
+        got = ra(xg[lo:hi], training=True, replay=s[lo:hi], normalize=mode)
+        assert got.dtype == torch.float32 and got.shape == want.shape
+        same = (got == want).flatten(1).all(dim=1).cpu().numpy()
+        bad = [(oracle.OP_NAMES[s[lo + b, 0, 0, 0]], oracle.OP_NAMES[s[lo + b, 1, 0, 0]]) for b in np.nonzero(~same)[0]]
+        assert not bad, "fused != separate for pairs %r" % (bad[:12],)
+    idx = list(range(3, 256, 29))
+    ref = oracle.imagenet_normalization(oracle.apply_schedule(x[idx], policy_of(ra), s[idx], elementwise=True), mode)
+    assert np.array_equal(ra(xg[idx], training=True, replay=s[idx], normalize=mode).cpu().numpy(), ref)
+    aa = A.AutoAugment(elementwise=True)
+    y = aa(xg, training=True, seed=4, call_counter=2, normalize=mode, record=True)
+    assert torch.equal(y, norm(aa(xg, training=True, replay=aa.last_schedule)))
+    yh = ra(x[:9], training=True, seed=1, call_counter=1, normalize=mode)          # numpy in -> numpy out
+    assert isinstance(yh, np.ndarray) and np.array_equal(yh, norm(ra(xg[:9], training=True, seed=1, call_counter=1)).cpu().numpy())
+    big = torch.from_numpy(random_images(3, 512, 512, 3, seed=2)).cuda()             # tile engine: fallback
+    assert torch.equal(ra(big, training=True, seed=2, call_counter=0, normalize=mode), norm(ra(big, training=True, seed=2, call_counter=0)))
