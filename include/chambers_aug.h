@@ -202,7 +202,7 @@ int chb_resize(chb_ctx* ctx, const void* d_in, int in_is_f32, void* d_out, int B
 
 /* Engine selection.  The library holds two engines with identical results:
  *   CHB_ENGINE_RESIDENT  one CTA per SM keeps a whole image in shared memory for its entire op chain
- *                        (images of up to ~190 KB whose rows are whole 16-byte units, nearest /
+ *                        (images of up to ~180 KB whose rows are whole 16-byte units, nearest /
  *                        constant-fill geometric ops: every BASELINE 224 x 224 x 3 configuration);
  *   CHB_ENGINE_TILES     the tile-parallel engine: any shape, any fill mode, bilinear warps.
  * CHB_ENGINE_AUTO (default) takes the resident engine whenever a call is eligible.  Forcing

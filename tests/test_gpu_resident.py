@@ -367,3 +367,38 @@ def test_pinned_host_path(A):
     big = torch.from_numpy(random_images(3, 512, 512, 3, seed=1)).pin_memory()
     ra = A.RandAugment(2, 10, elementwise=True)
     assert torch.equal(ra(big, training=True, seed=1, call_counter=1), ra(big.cuda(), training=True, seed=1, call_counter=1).cpu())
+
+
+def test_fuzz_resident_shapes(A):
+    """Seeded fuzz over what the resident engine's arithmetic depends on: image shape (rows of one to a few hundred
+    16-byte units, 1 to 300 rows, images just below the ~180 KB that fit beside the control block and 16 KB of working space), channel count, batch size (more or fewer
+    images than SMs, split and unsplit), magnitude and chain length -- device coins, the tile engine as replay
+    witness, the oracle on a sample."""
+    rng = np.random.default_rng(77)
+    cases = [(3, 1, 16, 3, 3, 10.0), (5, 2, 32, 3, 4, 15.0), (2, 234, 256, 3, 3, 10.0), (4, 280, 208, 3, 2, 5.0), (300, 16, 16, 3, 2, 10.0),
+             (7, 58, 3072, 1, 3, 10.0), (6, 90, 480, 4, 4, 12.0), (9, 84, 1064, 2, 3, 10.0), (1, 224, 224, 3, 6, 10.0)]
+    for _ in range(10):
+        C = int(rng.choice([1, 2, 3, 4]))
+        step = {1: 16, 2: 8, 3: 16, 4: 4}[C]
+        W = step * int(rng.integers(1, 20))
+        H = int(rng.integers(1, min(300, 175000 // (W * C)) + 1))
+        cases.append((int(rng.integers(1, 200)), H, W, C, int(rng.integers(1, 6)), float(rng.integers(0, 16))))
+    for (B, H, W, C, n, m) in cases:
+        x = random_images(B, H, W, C, seed=B * H + W, kind="smooth" if (H + W) % 2 else "uniform")
+        if C == 3:
+            layer = A.RandAugment(n, m, elementwise=True)._transform
+        else:
+            names = [nm for nm in oracle.OP_NAMES if nm not in ("Color", "Contrast")]
+            layer = A.RandomChoice([getattr(A, nm)(**oracle.magnitude_kwargs(nm, m)) for nm in names], n, elementwise=True)
+        xg = to_gpu(x)
+        with engine("resident"):
+            y = layer(xg, seed=77, call_counter=3, record=True)
+            sched = layer.last_schedule
+        with engine("tiles"):
+            t = layer(xg, replay=sched)
+        assert torch.equal(y, t), "resident != tiles for case %r" % ((B, H, W, C, n, m),)
+        idx = list(range(0, B, max(1, B // 12)))
+        want = oracle.apply_schedule(x[idx], policy_of(layer), sched[idx], elementwise=True)
+        got = y[idx].cpu().numpy()
+        for k, b in enumerate(idx):
+            assert_same(got[k], want[k], "case %r image %d chain %r" % ((B, H, W, C, n, m), b, sched[b, :, 0, 0].tolist()))
