@@ -617,7 +617,7 @@ static bool resident_eligible(const chb_ctx* ctx, const PolicyEntry* pe, const u
   if (fixed > (size_t)ctx->res_smem) return false;
   const size_t aux = (size_t)ctx->res_smem - fixed;
   const size_t hist_copy = (size_t)C * 1024 + 16;
-  if (aux < hist_copy + 4 * (row + 16) || aux < 16 * 1024) return false;
+  if (aux < hist_copy + 4 * (row + 16) || aux < 10 * 1024) return false;  // (plan_order scratch 8.4 KB, 4 histogram copies <= 8 KB)
   for (const DevOp& d : pe->host) {
     const bool geo = d.kind == CHB_OP_SHEAR_X || d.kind == CHB_OP_SHEAR_Y || d.kind == CHB_OP_TRANSLATE_X ||
                      d.kind == CHB_OP_TRANSLATE_Y || d.kind == CHB_OP_ROTATE;

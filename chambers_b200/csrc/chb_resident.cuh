@@ -40,7 +40,7 @@ static_assert(RNT % 256 == 0, "whole warps, and flat steps of whole 16-byte unit
 constexpr int RES_CHUNK = RES_CHUNK_BYTES;       // bytes per load chunk: one flat step of 1024 48-byte units (issuing a bulk copy costs
                                                  // the issuing thread ~150 ns: 13 chunks of 12 KB were 2 us of every image's start-up)
 constexpr int RES_MAXCHUNK = 4;        // -> images of up to 192 KB
-constexpr int RES_MIN_AUX = 16 * 1024;
+constexpr int RES_MIN_AUX = 10 * 1024;    // plan_order scratch (8.4 KB) / four histogram copies (<= 8 KB); the host checks it (resident_eligible)
 constexpr int LPT_MAX = 2048;          // batches up to this size are claimed longest-chain-first
 
 struct alignas(128) ResCtl {
@@ -368,6 +368,10 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
   const bool a_geom = !TWO || ea.type == SP_GEOM;
   const bool b_geom = TWO && eb.type == SP_GEOM;
   const float t0 = ea.t[0], t1 = ea.t[1], t2 = ea.t[2], t3 = ea.t[3], t4 = ea.t[4], t5 = ea.t[5];
+  // (entry b's coefficients and rectangle in registers too: read through the reference they were six shared-memory
+  // loads per pixel of the second stage)
+  const float u0 = eb.t[0], u1 = eb.t[1], u2 = eb.t[2], u3 = eb.t[3], u4 = eb.t[4], u5 = eb.t[5];
+  const int by0 = eb.y0, by1 = eb.y1, bx0 = eb.x0, bx1 = eb.x1;
   const int kmode = t.kmode;
   const bool use1 = !t.l1_id, use2 = !t.l2_id;
   const bool aff1 = (t.l1_aff & 0x10000) != 0;
@@ -444,11 +448,11 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
         if (b_geom) {
           const float gx = small_uint_to_float((uint32_t)ix), gy = small_uint_to_float((uint32_t)iy);
           int jx, jy;
-          hit_b = !src_index2(__fadd_rn(__fadd_rn(__fmul_rn(eb.t[0], gx), __fmul_rn(eb.t[1], gy)), eb.t[2]),
-                              __fadd_rn(__fadd_rn(__fmul_rn(eb.t[3], gx), __fmul_rn(eb.t[4], gy)), eb.t[5]), W, H, jx, jy);
+          hit_b = !src_index2(__fadd_rn(__fadd_rn(__fmul_rn(u0, gx), __fmul_rn(u1, gy)), u2),
+                              __fadd_rn(__fadd_rn(__fmul_rn(u3, gx), __fmul_rn(u4, gy)), u5), W, H, jx, jy);
           ix = jx; iy = jy;
         } else {
-          hit_b = (iy >= eb.y0) & (iy < eb.y1) & (ix >= eb.x0) & (ix < eb.x1);
+          hit_b = (iy >= by0) & (iy < by1) & (ix >= bx0) & (ix < bx1);
         }
       }
       adr[i] = !(hit_a | hit_b) ? c.img + (uint32_t)(iy * pitch + ix * C) : (hit_a ? fa_addr : fb_addr);
