@@ -1247,10 +1247,12 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
     ctl->n_items = p.B;
     ctl->cost_sum = 0;
   }
-  // Programmatic dependent launch: nothing the previous kernel of the stream wrote (the images, a
-  // replayed schedule, the policy table, the work counter it left zeroed) is touched before it has completed.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (tid == 0) ctl->next_img = (int)atomicAdd(p.counters, 1u);  // a claim POSITION (see plan_order)
+  // Programmatic dependent launch.  What this call alone owns is set up BEFORE waiting for the previous kernel of
+  // the stream -- the policy table (uploaded and synchronised when the policy was first seen, chb_api.cu get_policy),
+  // the normalisation table, and, unless the schedule is replayed from a buffer that kernel may have written, the
+  // cost-sorted claim order -- so that a back-to-back call does this part in the shadow of its predecessor's tail.
+  // Nothing the previous kernel wrote (the images, a replayed schedule, the work counter it left zeroed) is touched
+  // before it has completed.
   // the policy table comes to shared memory once: the chain walk of every image reads it many times
   DevOp* s_ops = reinterpret_cast<DevOp*>(smem_raw + pol_off);
   uint8_t* s_optab = smem_raw + pol_off + (size_t)n_pol * sizeof(DevOp);
@@ -1272,7 +1274,11 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   // small batches: positions map to images through the cost-sorted order (all images share one chain in
   // batch mode: nothing to sort)
   const bool lpt = p.B <= LPT_MAX && p.elementwise && p.res_lpt && (p.B > (int)gridDim.x || p.res_split);
-  if (lpt) plan_order(pl, s_ops, ctl, reinterpret_cast<uint16_t*>(smem_raw + aux_off), tid);
+  if (lpt && !p.replay) plan_order(pl, s_ops, ctl, reinterpret_cast<uint16_t*>(smem_raw + aux_off), tid);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (lpt && p.replay) plan_order(pl, s_ops, ctl, reinterpret_cast<uint16_t*>(smem_raw + aux_off), tid);
+  if (tid == 0) ctl->next_img = (int)atomicAdd(p.counters, 1u);  // a claim POSITION (see plan_order)
+  __syncthreads();
   const int n_items = ctl->n_items;  // == p.B unless images were split
   int part = 0, n_parts = 1;
   auto image_of = [&](int pos) {     // claim position -> image (and the row range of its last pass)
