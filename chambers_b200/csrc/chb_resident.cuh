@@ -1274,23 +1274,42 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   // small batches: positions map to images through the cost-sorted order (all images share one chain in
   // batch mode: nothing to sort)
   const bool lpt = p.B <= LPT_MAX && p.elementwise && p.res_lpt && (p.B > (int)gridDim.x || p.res_split);
-  if (lpt && !p.replay) plan_order(pl, s_ops, ctl, reinterpret_cast<uint16_t*>(smem_raw + aux_off), tid);
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (lpt && p.replay) plan_order(pl, s_ops, ctl, reinterpret_cast<uint16_t*>(smem_raw + aux_off), tid);
-  if (tid == 0) ctl->next_img = (int)atomicAdd(p.counters, 1u);  // a claim POSITION (see plan_order)
-  __syncthreads();
-  const int n_items = ctl->n_items;  // == p.B unless images were split
   int part = 0, n_parts = 1;
   auto image_of = [&](int pos) {     // claim position -> image (and the row range of its last pass)
     part = 0; n_parts = 1;
-    if (pos >= n_items) return p.B;
+    if (pos >= ctl->n_items) return p.B;  // (n_items == p.B unless images were split)
     if (!lpt) return pos;
     const int e = (int)ctl->order[pos];
     part = (e >> ORDER_IMG_BITS) & 3;
     n_parts = ((e >> (ORDER_IMG_BITS + 2)) & 3) + 1;
     return e & ((1 << ORDER_IMG_BITS) - 1);
   };
-  int img = image_of(ctl->next_img);
+  // schedule decode + chain walk of an image up to its first pass
+  auto bookkeeping = [&](int image) {
+    for (int i = tid; i < STATE_VECS; i += RNT) reinterpret_cast<uint4*>(&ctl->st)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    // (the first chain walk on ONE warp with warp-level barriers was measured: the 768-entry table loops on
+    // 32 threads cost more than the CTA barriers they save -- 4.9 us against 3.0 us of bookkeeping per image)
+    if (tid < 32) decode_image(pl, &ctl->st, ctl->rnd, ctl->rndc, image, H, W, tid);
+    reset_view(&ctl->st, tid, RNT);
+    __syncthreads();
+    res_advance<C>(ctl, pl, H, W, tid);
+  };
+  // A CTA's FIRST item is position blockIdx.x (no claim needed: later claims start behind the grid), so when the
+  // schedule comes from the RNG and is not recorded, its bookkeeping runs before the wait as well.
+  const bool early = !p.replay && !p.record;
+  int img = p.B;
+  if (early) {
+    if (lpt) plan_order(pl, s_ops, ctl, reinterpret_cast<uint16_t*>(smem_raw + aux_off), tid);
+    img = image_of((int)blockIdx.x);
+    if (img < p.B) bookkeeping(img);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (!early) {
+    if (lpt) plan_order(pl, s_ops, ctl, reinterpret_cast<uint16_t*>(smem_raw + aux_off), tid);
+    img = image_of((int)blockIdx.x);
+  }
+  bool booked = early;  // the current image's bookkeeping is already done
   uint8_t* scratch = p.scratch + (size_t)blockIdx.x * p.scratch_stride;
   // Thread 0 issues the chunks IN ORDER: the executors consume them front to back, and chunks issued
   // by different lanes of a warp were served in an order that made every step of a flat image wait for
@@ -1318,21 +1337,8 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
     c.par ^= 1u;
     issue_load(p.in + (size_t)img * img_bytes);
     // schedule decode + chain walk up to the first pass (the loads are in flight)
-    for (int i = tid; i < STATE_VECS; i += RNT) reinterpret_cast<uint4*>(&ctl->st)[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
-#ifdef CHB_TIMELINE
-    if (p.timeline && tid == 0) atomicAdd(p.timeline + 2, tl_now() - tl_t0);  // load issue + state reset
-    unsigned long long tl_ta = tl_now();
-#endif
-    // (the first chain walk on ONE warp with warp-level barriers was measured: the 768-entry table loops on
-    // 32 threads cost more than the CTA barriers they save -- 4.9 us against 3.0 us of bookkeeping per image)
-    if (tid < 32) decode_image(pl, &ctl->st, ctl->rnd, ctl->rndc, img, H, W, tid);
-    reset_view(&ctl->st, tid, RNT);
-    __syncthreads();
-#ifdef CHB_TIMELINE
-    if (p.timeline && tid == 0) atomicAdd(p.timeline + 3, tl_now() - tl_ta);  // schedule decode
-#endif
-    res_advance<C>(ctl, pl, H, W, tid);
+    if (!booked) bookkeeping(img);
+    booked = false;
     uint8_t* out_img = p.outf ? nullptr : p.out + (size_t)img * img_bytes;
 #ifdef CHB_TIMELINE
     if (tid == 0) tl_t1 = tl_now();
@@ -1389,7 +1395,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
       // -- unlike a claim at the image's start -- a CTA with a long chain does not sit on a second image that
       // an idle CTA could have taken (profiles/r02_v3_timeline_256.txt: the tail of a 256-image call was the
       // pre-claimed image behind the longest chain).
-      if (last && tid == 0) ctl->n_claimed = (int)atomicAdd(p.counters, 1u);
+      if (last && tid == 0) ctl->n_claimed = (int)(atomicAdd(p.counters, 1u) + gridDim.x);  // (positions 0 .. grid-1 are the CTAs' first items)
       bool any_geom = false;
       for (int k = 0; k < t.n_sp; ++k) any_geom = any_geom || (t.sp[k].type == SP_GEOM);
       const bool in_place = !last && (t.kmode == K_NONE || t.kmode == K_COLOR) && !any_geom;

@@ -88,9 +88,8 @@ def main():
         len(busy), busy.mean() / span, last.min() / 1e3, np.median(last) / 1e3, last.max() / 1e3))
     dur = (t2 - t0) / 1e3
     book = (t1 - t0) / 1e3
-    print("per image: mean %.1f us (bookkeeping before the first pass %.2f us: load issue + state reset %.2f, schedule decode %.2f, chain walk %.2f), sum %.0f us = %.1f us per SM over 148 SMs" % (
-        dur.mean(), book.mean(), int(host[2]) / 1e3 / nrec, int(host[3]) / 1e3 / nrec, book.mean() - (int(host[2]) + int(host[3])) / 1e3 / nrec,
-        dur.sum(), dur.sum() / 148))
+    print("per image: mean %.1f us (load issue + bookkeeping before the first pass %.2f us), sum %.0f us = %.1f us per SM over 148 SMs" % (
+        dur.mean(), book.mean(), dur.sum(), dur.sum() / 148))
     cls = collections.defaultdict(list)
     for k in range(nrec):
         ops = [NAMES[o] for o in sched[img[k], :, 0, 0]] if args.policy == "randaugment" else ["sub%d" % sched[img[k], 0, 0, 0]] + \
