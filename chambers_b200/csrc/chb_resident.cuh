@@ -75,9 +75,8 @@ struct RC {
   uint8_t* dst;        // global destination of a WRITE pass
   int H, W, row, img_bytes, tid, lane;
   uint32_t l1a, l2a;   // shared addresses of the two LUTs
-  uint32_t hcopy;      // shared address of this lane's histogram copy (word 0)
-  int ncopy;           // histogram copies: 32, 16, 8 or 4
-  uint32_t hshift;     // log2(ncopy * 4): byte shift of a counter-pair row
+  uint32_t hcopy;      // shared address of this lane's histogram copy
+  int ncopy;           // histogram copies: 8, 4, 2 or 1
   int tally;           // WRITE pass: also count the bytes written (the materialised view feeds a histogram op next)
   int y_lo, y_hi;      // WRITE passes: output rows this CTA produces (the whole image unless a small batch split the image's last pass)
   int sharp_rows;      // Sharpness: rows per sub-strip of the column walk for this row range
@@ -86,16 +85,16 @@ struct RC {
   int minmax;          // COUNT pass: only the smallest and largest value per channel are needed (AutoContrast on a monotone l1)
 };
 
-// Histogram of a COUNT pass: `ncopy` copies of packed 16-bit counters in the aux region, copy =
-// lane & (ncopy - 1).  Counter of (channel ch, value v) in copy k: half (v & 1) of the 32-bit word
-//     ((ch * 128 + (v >> 1)) * ncopy + k)
-// so with ncopy == 32 every lane of a warp owns one shared-memory bank: a red.shared of 32 random
-// values is ONE conflict-free wavefront (the 8 skewed u32 copies of the first version averaged 3.5:
-// profiles/r02_v1_ncu_op_Equalize.txt, 52 % of the wavefronts were bank conflicts and mio_throttle
-// was the top stall).  A copy counts at most (pixels / ncopy) * (32 / 32) ... <= 4 x 6656 values for
-// ncopy >= 4 (images of <= 192 KB), so 16 bits never overflow.  ncopy = 32 needs C x 16 KB.
+// Histogram of a COUNT pass (or the tally of a materialised view): `ncopy` copies of the u32 histogram in the
+// aux region, copy = lane & (ncopy - 1), skewed by four banks each -- three instructions per byte (byte
+// extract, address, red.shared).  Shared-memory atomics retire ~6-8 distinct addresses per clock whatever
+// their banks: a conflict-free layout (32 lane-owned copies of packed 16-bit counters) was measured and
+// bought nothing on noise, lost 35 % on constant images where ATOMS.POPC.INC merges the lanes of a copy, and
+// cost three more instructions per byte (profiles/r02_ab_notes.md 3).
 template <int C>
-__host__ __device__ constexpr uint32_t hist_bytes(int ncopy) { return (uint32_t)C * 512u * (uint32_t)ncopy; }
+__host__ __device__ constexpr uint32_t hist_copy_bytes() { return (uint32_t)C * 1024u + 16u; }
+template <int C>
+__host__ __device__ constexpr uint32_t hist_bytes(int ncopy) { return hist_copy_bytes<C>() * (uint32_t)ncopy; }
 
 template <int C>
 __device__ __forceinline__ void hist_zero(const RC<C>& c) {
@@ -105,20 +104,15 @@ __device__ __forceinline__ void hist_zero(const RC<C>& c) {
 }
 template <int C>
 __device__ __forceinline__ void hist_add(const RC<C>& c, int ch, uint32_t v) {  // v: a zero-extended byte
-  reds_add(c.hcopy + (((uint32_t)ch * 128u + (v >> 1)) << c.hshift), 1u + (v & 1u) * 0xFFFFu);
+  reds_add(c.hcopy + (uint32_t)ch * 1024u + (v << 2), 1u);
 }
 // Sums the copies into st.hist (which advance() zeroed when it asked for the COUNT pass).
 template <int C>
 __device__ __forceinline__ void hist_reduce(const RC<C>& c) {
   __syncthreads();
   for (int i = c.tid; i < C * 256; i += RNT) {
-    const uint32_t rowa = c.aux + ((uint32_t)(i >> 1) << c.hshift);
-    const uint32_t sh = (uint32_t)(i & 1) * 16u;
     uint32_t sum = 0;
-    for (int k = 0; k < c.ncopy; ++k) {
-      const uint32_t kk = (uint32_t)(k + c.lane) & (uint32_t)(c.ncopy - 1);  // staggered: a row of copies is one bank per lane
-      sum += (lds_u32(rowa + kk * 4u) >> sh) & 0xFFFFu;
-    }
+    for (int k = 0; k < c.ncopy; ++k) sum += lds_u32(c.aux + (uint32_t)k * hist_copy_bytes<C>() + (uint32_t)i * 4u);
     (&c.ctl->st.hist[0][0])[i] += sum;
   }
   __syncthreads();
@@ -1234,8 +1228,8 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   c.full0 = smem_addr(&ctl->full[0]);
   c.H = H; c.W = W; c.row = W * C; c.img_bytes = img_bytes; c.tid = tid; c.lane = tid & 31;
   c.l1a = smem_addr(&ctl->st.t.l1[0][0]); c.l2a = smem_addr(&ctl->st.t.l2[0][0]);
-  int ncopy = 32;
-  while (ncopy > 4 && hist_bytes<C>(ncopy) > (uint32_t)c.aux_bytes) ncopy >>= 1;
+  int ncopy = 8;
+  while (ncopy > 1 && hist_bytes<C>(ncopy) > (uint32_t)c.aux_bytes) ncopy >>= 1;
   c.par = 1;  // toggled to 0 by the first load
   c.dst = nullptr;
   if (tid == 0) {
@@ -1355,8 +1349,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
         ctl->fillc[0] = fa; ctl->fillc[1] = fb;
       }
       c.ncopy = ncopy;
-      c.hshift = 31u - (uint32_t)__clz(ncopy * 4);
-      c.hcopy = c.aux + (uint32_t)(c.lane & (ncopy - 1)) * 4u;
+      c.hcopy = c.aux + (uint32_t)(c.lane & (ncopy - 1)) * hist_copy_bytes<C>();
       __syncthreads();
       c.tally = 0;
       c.minmax = 0;
