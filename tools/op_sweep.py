@@ -135,6 +135,24 @@ def main():
         ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), cbufs, args.iters)
         report("op:%s(constant image)" % n, B, 224, 224, ms)
     del cbufs
+    # natural images (SURVEY.md 8d distribution B): the reference's sample_data batch tiled to B -- peaked histograms
+    try:
+        import numpy as np
+        nat = np.load(os.path.join(ROOT, "tests", "golden", "c1_batch.npz"))["images"]
+        reps = (B + nat.shape[0] - 1) // nat.shape[0]
+        xn = torch.from_numpy(np.tile(nat, (reps, 1, 1, 1))[:B]).cuda()
+        nb = max(2, min(8, (768 << 20) // (2 * xn.numel())))
+        nbufs = [(xn.roll(k, 0).contiguous(), torch.empty_like(xn)) for k in range(nb)]
+        for n in ("Equalize", "AutoContrast", "Sharpness", "Rotate"):
+            layer = A.RandomChoice([getattr(A, n)(**magnitude_kwargs(n, 10))], 1)
+            ms = time_layer(lambda i, x, y: layer(x, seed=0, call_counter=i, out=y), nbufs, args.iters)
+            report("op:%s(natural images)" % n, B, 224, 224, ms)
+        ran = A.RandAugment(2, 10, elementwise=True)._transform
+        ms = time_layer(lambda i, x, y: ran(x, seed=0, call_counter=i, out=y), nbufs, args.iters)
+        report("RandAugment(2,10) elementwise=True (natural images)", B, 224, 224, ms)
+        del nbufs, xn
+    except Exception as e:  # the fixture is optional for a throughput sweep
+        print("natural-image cases skipped: %r" % (e,))
     for ew in (True, False):
         ra = A.RandAugment(2, 10, elementwise=ew)._transform
         ms = time_layer(lambda i, x, y: ra(x, seed=0, call_counter=i, out=y), bufs, args.iters)
