@@ -1,28 +1,35 @@
 // Image-resident policy kernel for sm_100a: ONE launch per call, one CTA per SM, one image per CTA
 // at a time, the whole image in shared memory for as long as its op chain needs it.
 //
-//   resident_kernel<C>   claims images from an atomic counter.  Per image: thread 0 issues the bulk
-//                        loads (cp.async.bulk + mbarrier, 12 KB chunks) of the whole image into shared
-//                        memory; while they fly, warp 0 decodes the image's schedule (Philox4x32-10 or
-//                        replay) and the CTA folds the chain into the lazy per-image state (advance(),
-//                        chb_kernels.cuh -- the same chain walk the tile engine uses, so both engines
-//                        share every line that decides WHAT is computed).  Then the image's passes run
-//                        back to back on the resident source:
-//                          COUNT          histogram of the virtual image (8 skewed copies in shared
-//                                         memory, red.shared), Equalize / AutoContrast table, chain walk
-//                                         resumed -- no second trip to HBM, no election, no ticket;
-//                          WRITE_SCRATCH  Color materialises in place; the rare neighbourhood-of-
-//                                         neighbourhood chains go through a per-CTA scratch image
-//                                         (L2-resident) and are loaded back;
-//                          WRITE_OUT      flat chains are transformed in place and leave as 48 KB bulk
-//                                         stores (TMA, shared -> global); gathers and Sharpness store
-//                                         from registers.
+//   resident_kernel<C>   Work items (images; in the smallest batches also row ranges of an expensive image's last
+//                        pass) are claimed from an atomic counter, in a cost-sorted order for batches of up to 2048
+//                        images (plan_order).  Per image: one thread issues the bulk loads (cp.async.bulk +
+//                        mbarrier, 48 KB chunks, front to back) of the whole image into shared memory; while they
+//                        fly, warp 0 decodes the image's schedule (Philox4x32-10 or replay) and the CTA folds the
+//                        chain into the lazy per-image state (advance(), chb_kernels.cuh -- the same chain walk
+//                        the tile engine uses, so both engines share every line that decides WHAT is computed).
+//                        Then the image's passes run back to back on the resident source:
+//                          COUNT          histogram of the (flat) view: 8 skewed copies in shared memory,
+//                                         red.shared -- or, for AutoContrast behind a monotone table, a min / max
+//                                         pass in registers; Equalize / AutoContrast table, chain walk resumed --
+//                                         no second trip to HBM, no election, no ticket;
+//                          WRITE_SCRATCH  a view is materialised when an op finds the kernel slot occupied, and
+//                                         (KParams::res_rules) in front of Sharpness / a histogram op whenever it
+//                                         holds a warp, a mask or an occupied slot: point-wise views and CutOut in
+//                                         place, gathers and Sharpness through a per-CTA scratch image (L2-
+//                                         resident) that is loaded back, tallied while written if a histogram op
+//                                         comes next;
+//                          WRITE_OUT      flat chains are transformed in place and leave as 48 KB bulk stores
+//                                         (TMA, shared -> global); gathers, row-shift copies and Sharpness store
+//                                         from registers; with the fused ImageNetNormalization epilogue all of
+//                                         them write float32 instead.
 //   An image costs exactly one HBM read and one HBM write whatever its chain.
 //
-// Eligibility (decided on the host, chb_api.cu): the image plus ~30 KB of working set fit one SM's
-// shared memory (224 x 224 x 3 = 147 KB does; 512 x 512 x 3 does not and runs on the tile engine),
-// rows are whole 16-byte units, every geometric op is nearest / constant-fill (what the policies
-// use, augmentation_schemes.py:7-9).  Everything else stays on the tile engine (chb_kernels.cuh).
+// Eligibility (decided on the host, chb_api.cu resident_eligible): the image, the policy table and >= 10 KB of
+// working space fit one SM's shared memory beside the 22 KB control block (images up to ~180 KB: 224 x 224 x 3 =
+// 147 KB does; 512 x 512 x 3 does not and runs on the tile engine), rows are whole 16-byte units, every geometric
+// op is nearest / constant-fill (what the policies use, augmentation_schemes.py:7-9).  Everything else stays on
+// the tile engine (chb_kernels.cuh).
 #pragma once
 #define RES_CHUNK_BYTES 49152
 // the policy table is staged in shared memory: plain loads (see chb_kernels.cuh)
@@ -341,7 +348,7 @@ __device__ __forceinline__ bool src_raw(float v, float nmh, uint32_t& raw) {
 
 // src_index for BOTH coordinates of a pixel with one combined validity: the four range tests are joined
 // with non-short-circuit ANDs so that they become one predicate chain and ONE select of the address
-// (the separate tests compiled to four SELs per pixel, profiles/r02_ncu_op_Rotate_b2048.txt).
+// (the separate tests compiled to four SELs per pixel, profiles/r02_ab_notes.md 8).
 __device__ __forceinline__ bool src_index2(float vx, float vy, int W, int H, int& ix, int& iy) {
   const uint32_t ux = __float_as_uint(__fadd_rz(vx, 4194304.5f)), uy = __float_as_uint(__fadd_rz(vy, 4194304.5f));
   ix = (int)((ux - 0x4A800000u) >> 1);
@@ -382,7 +389,7 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
   // A thread takes G quads (4 adjacent pixels, C words each) at a time.  G = 1: the lanes of a warp read
   // source pixels that are neighbours along the warp's direction, i.e. nearly consecutive shared-memory
   // words (with G = 4 for C = 3 -- one 48-byte unit per lane -- the lanes are 16 source pixels apart and
-  // 61 % of the gather's wavefronts were bank conflicts, profiles/r02_v1_ncu_op_Rotate.txt).
+  // 61 % of the gather's wavefronts were bank conflicts, profiles/r02_ab_notes.md 4).
 #ifndef CHB_GATHER_G
 #define CHB_GATHER_G 1
 #endif
@@ -971,7 +978,7 @@ __device__ __forceinline__ void res_sharp(const RC<C>& c) {
 constexpr int SPLIT_MAX = 512;
 constexpr int ORDER_IMG_BITS = 11;  // order entry: image | part << 11 | (parts - 1) << 13
 
-// Estimated microseconds of one image at 224 x 224 x 3 (profiles/r02_v3_timeline_256.txt), following the
+// Estimated microseconds of one image at 224 x 224 x 3 (profiles/r02_timeline_256.txt), following the
 // rules of the chain walk: `sunk` = loading, bookkeeping and every pass in front of the last one (paid
 // by every part), `pend` = the evaluation of the final view (shared between the parts).
 __device__ __forceinline__ void chain_cost(const KParams& p, const DevOp* ops, int img, int& sunk, int& pend) {
@@ -1307,7 +1314,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   uint8_t* scratch = p.scratch + (size_t)blockIdx.x * p.scratch_stride;
   // Thread 0 issues the chunks IN ORDER: the executors consume them front to back, and chunks issued
   // by different lanes of a warp were served in an order that made every step of a flat image wait for
-  // the tail of the load (profiles/r02_v2_ab_notes.txt: identity 102 % -> 79 % of the copy peak).
+  // the tail of the load (profiles/r02_ab_notes.md 1: identity 102 % -> 79 % of the copy peak).
   auto issue_load = [&](const uint8_t* src) {
     if (tid == 32) {  // (not thread 0: that one drives the claims and the bulk stores)
       for (int k = 0; k < n_chunks; ++k) {
@@ -1386,7 +1393,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
       const bool last = pass_kind == PASS_WRITE_OUT;
       // The next image is claimed when this one's last pass starts: the round trip hides behind the pass, and
       // -- unlike a claim at the image's start -- a CTA with a long chain does not sit on a second image that
-      // an idle CTA could have taken (profiles/r02_v3_timeline_256.txt: the tail of a 256-image call was the
+      // an idle CTA could have taken (profiles/r02_timeline_256.txt: the tail of a 256-image call was the
       // pre-claimed image behind the longest chain).
       if (last && tid == 0) ctl->n_claimed = (int)(atomicAdd(p.counters, 1u) + gridDim.x);  // (positions 0 .. grid-1 are the CTAs' first items)
       bool any_geom = false;
