@@ -66,14 +66,16 @@ struct alignas(128) ResCtl {
   KParams kp;                          // the launch parameters with ops / optab pointing at the shared-memory copy
   uint16_t order[LPT_MAX];             // small batches: claim position -> image, most expensive chains first
   float nlut[3][256];                  // fused ImageNetNormalization epilogue: value -> float32, per channel
-  ImgState st;
+  ImgState st[2];                      // the current image's state | the next image's, prepared by warp 31 during the last pass
 };
 
 template <int C>
 struct RC {
   const KParams* p;
   ResCtl* ctl;
-  const TileState* t;
+  ImgState* st;        // the current image's state
+  const TileState* t;  // == &st->t
+  int nt;              // threads working on this pass: RNT, or RNT - 32 while warp 31 prepares the next image
   uint32_t img;        // shared address of the resident source image
   uint32_t aux;        // shared address of the auxiliary region (histogram copies | band buffer)
   int aux_bytes;
@@ -120,7 +122,7 @@ __device__ __forceinline__ void hist_reduce(const RC<C>& c) {
   for (int i = c.tid; i < C * 256; i += RNT) {
     uint32_t sum = 0;
     for (int k = 0; k < c.ncopy; ++k) sum += lds_u32(c.aux + (uint32_t)k * hist_copy_bytes<C>() + (uint32_t)i * 4u);
-    (&c.ctl->st.hist[0][0])[i] += sum;
+    (&c.st->hist[0][0])[i] += sum;
   }
   __syncthreads();
 }
@@ -174,6 +176,14 @@ __device__ __forceinline__ void store_norm_word(const RC<C>& c, size_t widx, int
   __stcs(reinterpret_cast<float4*>(c.dstf) + widx, f);
 }
 
+// Barrier of the threads that work on a pass: the whole CTA, or warps 0 .. 30 while warp 31 decodes and walks
+// the NEXT image's chain (named barrier 2; warp 31 never joins it).
+template <int C>
+__device__ __forceinline__ void work_sync(const RC<C>& c) {
+  if (c.nt == RNT) __syncthreads();
+  else asm volatile("bar.sync 2, %0;" ::"n"(RNT - 32) : "memory");
+}
+
 // ================================================================================ flat executor
 // No warp pending, K in {none, Color}: units of 48 bytes (16 pixels; 16 bytes for C != 3) are
 // transformed in place as their load chunks arrive, one unit per thread per step of RNT units; a
@@ -184,6 +194,7 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
   constexpr int UW = (C == 3) ? 12 : 4;
   constexpr int UB = UW * 4;
   const TileState& t = *c.t;
+  const int NT = c.nt;  // (COUNT passes always run on the whole CTA)
   const int upr = c.row / UB;                                  // units per row (rows are whole units)
   const int u_first = COUNT ? 0 : c.y_lo * upr;                // COUNT passes always see the whole image
   const int n_units = COUNT ? c.img_bytes / UB : c.y_hi * upr;  // (one past the last unit)
@@ -201,7 +212,7 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
   const int n_paint = COUNT ? 0 : t.n_sp;  // this class holds masks only
   const bool touch = COUNT || use1 || kmode != K_NONE;  // else the staged bytes already are the result
   if (COUNT && !minmax) hist_zero(c);
-  for (int base = u_first; base < n_units; base += RNT) {
+  for (int base = u_first; base < n_units; base += NT) {
     const int wu = base + (c.tid & ~31);
     if (wu < n_units) {
       const int wl = min(wu + 31, n_units - 1);
@@ -268,17 +279,17 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
       }
     }
     if (!COUNT) {
-      const int u1 = min(n_units, base + RNT);
+      const int u1 = min(n_units, base + NT);
       // CutOut rectangles, in list order, over the pixels [P0, P1) of this step
       const int P0 = base * (UB / C), P1 = u1 * (UB / C);
       for (int k = 0; k < n_paint; ++k) {
-        __syncthreads();
+        work_sync(c);
         const Spatial& e = t.sp[k];
         const int rw = (e.x1 - e.x0) * C;
         if (rw <= 0) continue;
         const int ylo = max(e.y0, P0 / c.W), yhi = min(e.y1, (P1 - 1) / c.W + 1);
         const int n = (yhi - ylo) * rw;
-        for (int i = c.tid; i < n; i += RNT) {
+        for (int i = c.tid; i < n; i += NT) {
           const int ry = i / rw, rb = i - ry * rw;
           const int pix_b = ((ylo + ry) * c.W + e.x0) * C + rb;  // byte index in the image
           if (pix_b >= P0 * C && pix_b < P1 * C)
@@ -288,13 +299,13 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
       if (store && c.dstf) {
         // normalisation epilogue: the step's words are read back (consecutive lanes, consecutive words) and
         // leave as coalesced float4 stores
-        __syncthreads();
+        work_sync(c);
         const int w0 = base * UW, w1 = u1 * UW;
-        for (int wi = w0 + c.tid; wi < w1; wi += RNT)
+        for (int wi = w0 + c.tid; wi < w1; wi += NT)
           store_norm_word(c, (size_t)wi, (C == 3) ? (wi % 3) : 0, lds_u32(c.img + ((uint32_t)wi << 2)));
       } else if (store) {
         fence_proxy_async();  // this thread's shared-memory writes -> visible to the TMA
-        __syncthreads();
+        work_sync(c);
         if (c.tid == 0) {
           bulk_store(c.dst + (size_t)base * UB, c.img + (uint32_t)base * UB, (uint32_t)(u1 - base) * UB);
           bulk_commit();
@@ -311,24 +322,24 @@ __device__ __forceinline__ void res_flat(const RC<C>& c, int store) {
     __syncthreads();
     if (c.tid < C) {  // a histogram that holds exactly what AutoContrast reads: which values bound the range
       const uint32_t lo = c.ctl->mm[c.tid][0], hi = c.ctl->mm[c.tid][1];
-      if (lo <= hi) { c.ctl->st.hist[c.tid][lo] += 1u; c.ctl->st.hist[c.tid][hi] += 1u; }
+      if (lo <= hi) { c.st->hist[c.tid][lo] += 1u; c.st->hist[c.tid][hi] += 1u; }
     }
     __syncthreads();
   } else if (COUNT) {
     hist_reduce(c);
   } else {
-    __syncthreads();
+    work_sync(c);
   }
 }
 
 // ============================================================================== gather executors
-// Division-free walk over the units of an image: thread t starts at unit t and advances by RNT.
+// Division-free walk over the units of an image: thread t starts at unit t and advances by the pass's thread count.
 struct UnitWalk {
   int ux, y, dux, dy, upr;
-  __device__ __forceinline__ UnitWalk(int tid, int upr_) {
+  __device__ __forceinline__ UnitWalk(int tid, int upr_, int nt) {
     upr = upr_;
     y = tid / upr; ux = tid - y * upr;
-    dy = RNT / upr; dux = RNT - dy * upr;
+    dy = nt / upr; dux = nt - dy * upr;
   }
   __device__ __forceinline__ void next() {
     ux += dux; y += dy;
@@ -398,7 +409,7 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
 #endif
   constexpr int G = CHB_GATHER_G;
   const int y_end = COUNT ? H : c.y_hi;
-  UnitWalk q(c.tid, W / (4 * G));
+  UnitWalk q(c.tid, W / (4 * G), c.nt);
   if (!COUNT) q.y += c.y_lo;
   for (; q.y < y_end; q.next()) {
     const int y = q.y, xu = q.ux * (4 * G);
@@ -553,8 +564,8 @@ __device__ __forceinline__ void res_gather_fast(const RC<C>& c) {
     }
   }
   if (COUNT) {
-    if (n_fill_a) atomicAdd(&c.ctl->st.color_cnt[n_sp - 1], n_fill_a);
-    if (TWO && n_fill_b) atomicAdd(&c.ctl->st.color_cnt[n_sp - 2], n_fill_b);
+    if (n_fill_a) atomicAdd(&c.st->color_cnt[n_sp - 1], n_fill_a);
+    if (TWO && n_fill_b) atomicAdd(&c.st->color_cnt[n_sp - 2], n_fill_b);
   }
 }
 
@@ -590,7 +601,7 @@ __device__ __forceinline__ void res_gather_rowshift(const RC<C>& c) {
     fq[w] = x;
   }
   const int y_end = COUNT ? H : c.y_hi;
-  UnitWalk q(c.tid, W >> 2);
+  UnitWalk q(c.tid, W >> 2, c.nt);
   if (!COUNT) q.y += c.y_lo;
   for (; q.y < y_end; q.next()) {
     const int y = q.y, x0 = q.ux << 2;
@@ -695,7 +706,7 @@ __device__ __forceinline__ void res_gather_rowshift(const RC<C>& c) {
       for (int w = 0; w < C; ++w) __stcg(gp + w, o[w]);
     }
   }
-  if (COUNT && n_fill) atomicAdd(&c.ctl->st.color_cnt[0], n_fill);
+  if (COUNT && n_fill) atomicAdd(&c.st->color_cnt[0], n_fill);
 }
 
 // Does the single spatial entry qualify for res_gather_rowshift?
@@ -716,7 +727,7 @@ __device__ __forceinline__ void res_gather_list(const RC<C>& c) {
   const bool use1 = !t.l1_id, use2 = !t.l2_id;
   const float f = t.kfactor;
   const int n_pix = (COUNT ? H : c.y_hi) * W;
-  for (int i = (COUNT ? 0 : c.y_lo * W) + c.tid; i < n_pix; i += RNT) {
+  for (int i = (COUNT ? 0 : c.y_lo * W) + c.tid; i < n_pix; i += c.nt) {
     const int y = i / W;
     int sx = i - y * W, sy = y;
     const int k = resolve(t.sp, n_sp, H, W, sx, sy);
@@ -747,7 +758,7 @@ __device__ __forceinline__ void res_gather_list(const RC<C>& c) {
       }
     } else {
       if (COUNT) {
-        atomicAdd(&c.ctl->st.color_cnt[k], 1u);
+        atomicAdd(&c.st->color_cnt[k], 1u);
       } else {
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) v[ch] = (uint32_t)t.sp[k].color[ch];
@@ -792,19 +803,19 @@ __device__ __forceinline__ void res_gather(const RC<C>& c) {
 // then continues with l1 = identity.
 template <int C>
 __device__ __forceinline__ void res_bake_l1(const RC<C>& c) {
-  TileState& t = c.ctl->st.t;
+  TileState& t = c.st->t;
   if (t.l1_id) return;
   wait_image(c);
   const int total = c.img_bytes >> 4;
-  for (int i = c.tid; i < total; i += RNT) {
+  for (int i = c.tid; i < total; i += c.nt) {
     const uint4 v = map_vec_phase<C>(lds_v4(c.img + ((uint32_t)i << 4)), c.l1a, (C == 3) ? (i % 3) : 0);
     sts_v4(c.img + ((uint32_t)i << 4), v);
   }
-  __syncthreads();
-  for (int i = c.tid; i < MAXC * 256; i += RNT) t.l1[i >> 8][i & 255] = (uint8_t)(i & 255);
+  work_sync(c);
+  for (int i = c.tid; i < MAXC * 256; i += c.nt) t.l1[i >> 8][i & 255] = (uint8_t)(i & 255);
   if (c.tid == 0) { t.l1_id = 1; t.l1_aff = 0; }
   fence_proxy_async();  // the image buffer is refilled by the TMA later
-  __syncthreads();
+  work_sync(c);
 }
 
 // Rows per sub-strip so that (word columns x sub-strips) fills the CTA: minimise rounds * (rows + 2).
@@ -937,9 +948,9 @@ __device__ __forceinline__ void res_sharp(const RC<C>& c) {
   // first and last image row: every pixel is border -> blend(orig, orig) == orig
   const int y_lo = COUNT ? 0 : c.y_lo, y_hi = COUNT ? H : c.y_hi;
   if (y_lo == 0)
-    for (int xw = c.tid; xw < wpr; xw += RNT) emit(0, xw, (C == 3) ? (xw % 3) : 0, lds_u32(c.img + ((uint32_t)xw << 2)));
+    for (int xw = c.tid; xw < wpr; xw += c.nt) emit(0, xw, (C == 3) ? (xw % 3) : 0, lds_u32(c.img + ((uint32_t)xw << 2)));
   if (H > 1 && y_hi == H)
-    for (int xw = c.tid; xw < wpr; xw += RNT)
+    for (int xw = c.tid; xw < wpr; xw += c.nt)
       emit(H - 1, xw, (C == 3) ? (xw % 3) : 0, lds_u32(c.img + (uint32_t)((H - 1) * row + (xw << 2))));
   const int in0 = max(1, y_lo), in1 = min(H - 1, y_hi);
   const int inner = in1 - in0;
@@ -947,7 +958,7 @@ __device__ __forceinline__ void res_sharp(const RC<C>& c) {
     const int R = c.sharp_rows;
     const int n_strips = (inner + R - 1) / R;
     const int n_items = wpr * n_strips;
-    for (int item = c.tid; item < n_items; item += RNT) {
+    for (int item = c.tid; item < n_items; item += c.nt) {
       const int strip = item / wpr, xw = item - strip * wpr;
       const int y_begin = in0 + strip * R, y_end = min(in1, y_begin + R);
       const int xb0 = xw << 2;
@@ -1206,11 +1217,25 @@ __device__ __forceinline__ void res_write_pass(RC<C>& c, int store) {
 #define CHB_WALK_NT 128
 #endif
 template <int C>
-__device__ __forceinline__ void res_advance(ResCtl* ctl, const KParams& pl, int H, int W, int tid) {
+__device__ __forceinline__ void res_advance(ResCtl* ctl, ImgState* st, const KParams& pl, int H, int W, int tid) {
   if (tid < CHB_WALK_NT)
-    advance(&ctl->st, &ctl->st, pl, C, H, W, ctl->hmap, ctl->etab, tid, CHB_WALK_NT,
+    advance(st, st, pl, C, H, W, ctl->hmap, ctl->etab, tid, CHB_WALK_NT,
             [] { asm volatile("bar.sync 1, %0;" ::"n"(CHB_WALK_NT) : "memory"); });
   __syncthreads();
+}
+
+// Schedule decode and chain walk of the NEXT image on one warp (warp 31), while the other 31 warps run the current
+// image's last pass: slower than the cooperative walk (~5 us against ~3) but entirely off the critical path.  The
+// first walk of an image never builds a histogram table (nothing has been counted yet), the one step that wants a
+// warp per channel; hmap / etab are free during a last pass (only COUNT passes and the walk behind them use them).
+template <int C>
+__device__ __forceinline__ void res_bookkeeping_warp(ResCtl* ctl, ImgState* st, const KParams& pl, int image, int H, int W, int lane) {
+  for (int i = lane; i < STATE_VECS; i += 32) reinterpret_cast<uint4*>(st)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncwarp();
+  decode_image(pl, st, ctl->rnd, ctl->rndc, image, H, W, lane);
+  reset_view(st, lane, 32);
+  __syncwarp();
+  advance(st, st, pl, C, H, W, ctl->hmap, ctl->etab, lane, 32, [] { __syncwarp(); });
 }
 
 template <int C>
@@ -1228,13 +1253,14 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   const uint32_t aux_off = img_off + (uint32_t)((img_bytes + 127) / 128 * 128);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   RC<C> c;
-  c.p = &p; c.ctl = ctl; c.t = &ctl->st.t;
+  ImgState* cur = &ctl->st[0];  // the current image's state; the other buffer is where warp 31 prepares the next image
+  c.p = &p; c.ctl = ctl; c.st = cur; c.t = &cur->t; c.nt = RNT;
   c.img = smem_addr(smem_raw) + img_off;
   c.aux = smem_addr(smem_raw) + aux_off;
   c.aux_bytes = p.res_smem_bytes - (int)aux_off;
   c.full0 = smem_addr(&ctl->full[0]);
   c.H = H; c.W = W; c.row = W * C; c.img_bytes = img_bytes; c.tid = tid; c.lane = tid & 31;
-  c.l1a = smem_addr(&ctl->st.t.l1[0][0]); c.l2a = smem_addr(&ctl->st.t.l2[0][0]);
+  c.l1a = smem_addr(&cur->t.l1[0][0]); c.l2a = smem_addr(&cur->t.l2[0][0]);
   int ncopy = 8;
   while (ncopy > 1 && hist_bytes<C>(ncopy) > (uint32_t)c.aux_bytes) ncopy >>= 1;
   c.par = 1;  // toggled to 0 by the first load
@@ -1287,14 +1313,12 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
   };
   // schedule decode + chain walk of an image up to its first pass
   auto bookkeeping = [&](int image) {
-    for (int i = tid; i < STATE_VECS; i += RNT) reinterpret_cast<uint4*>(&ctl->st)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < STATE_VECS; i += RNT) reinterpret_cast<uint4*>(cur)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    // (the first chain walk on ONE warp with warp-level barriers was measured: the 768-entry table loops on
-    // 32 threads cost more than the CTA barriers they save -- 4.9 us against 3.0 us of bookkeeping per image)
-    if (tid < 32) decode_image(pl, &ctl->st, ctl->rnd, ctl->rndc, image, H, W, tid);
-    reset_view(&ctl->st, tid, RNT);
+    if (tid < 32) decode_image(pl, cur, ctl->rnd, ctl->rndc, image, H, W, tid);
+    reset_view(cur, tid, RNT);
     __syncthreads();
-    res_advance<C>(ctl, pl, H, W, tid);
+    res_advance<C>(ctl, cur, pl, H, W, tid);
   };
   // A CTA's FIRST item is position blockIdx.x (no claim needed: later claims start behind the grid), so when the
   // schedule comes from the RNG and is not recorded, its bookkeeping runs before the wait as well.
@@ -1345,7 +1369,7 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
     if (tid == 0) tl_t1 = tl_now();
 #endif
     for (;;) {
-      const TileState& t = ctl->st.t;
+      const TileState& t = cur->t;
       const int pass_kind = t.pass_kind;
       if (tid == 0) {
         uint32_t fa = 0, fb = 0;
@@ -1366,8 +1390,8 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
         // bytes decide them: a min / max pass in registers replaces 150 K shared-memory atomics.  The
         // resulting histogram is presence-only and marked so (hist_valid == 2: it serves this op alone).
         bool want_mm = false;
-        if (t.kmode == K_NONE && t.n_sp == 0 && ctl->st.next_op < ctl->st.n_prog)
-          want_mm = s_ops[ctl->st.prog[ctl->st.next_op].table_index].kind == CHB_OP_AUTOCONTRAST;
+        if (t.kmode == K_NONE && t.n_sp == 0 && cur->next_op < cur->n_prog)
+          want_mm = s_ops[cur->prog[cur->next_op].table_index].kind == CHB_OP_AUTOCONTRAST;
         if (want_mm) {
           if (tid < 2) ctl->mono[tid] = 1;
           if (tid < MAXC) { ctl->mm[tid][0] = 255u; ctl->mm[tid][1] = 0u; }
@@ -1382,9 +1406,9 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
           c.minmax = (ctl->mono[0] || ctl->mono[1]) ? 1 : 0;
         }
         res_count_pass<C>(c);
-        if (tid == 0) ctl->st.hist_valid = c.minmax ? 2 : 1;
+        if (tid == 0) cur->hist_valid = c.minmax ? 2 : 1;
         __syncthreads();
-        res_advance<C>(ctl, pl, H, W, tid);
+        res_advance<C>(ctl, cur, pl, H, W, tid);
         continue;
       }
       // WRITE_OUT, or WRITE_SCRATCH: point-wise views (and CutOut rectangles, painted over them)
@@ -1408,15 +1432,15 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
       // their bytes pass through registers anyway); in-place materialisations are counted by a flat
       // COUNT pass afterwards
       bool tally = false;
-      if (!last && !in_place && ctl->st.next_op < ctl->st.n_prog) {
-        const int kind = s_ops[ctl->st.prog[ctl->st.next_op].table_index].kind;
+      if (!last && !in_place && cur->next_op < cur->n_prog) {
+        const int kind = s_ops[cur->prog[cur->next_op].table_index].kind;
         tally = (kind == CHB_OP_EQUALIZE || kind == CHB_OP_AUTOCONTRAST);
       }
       if (tally) {
         c.tally = 1;
         wait_image(c);
         hist_zero(c);
-        for (int i = tid; i < MAXC * 256; i += RNT) (&ctl->st.hist[0][0])[i] = 0u;
+        for (int i = tid; i < MAXC * 256; i += RNT) (&cur->hist[0][0])[i] = 0u;
       }
       res_write_pass<C>(c, last ? 1 : 0);
       if (last) break;
@@ -1428,10 +1452,10 @@ __global__ void __launch_bounds__(RNT, 1) resident_kernel(const KParams p) {
         c.par ^= 1u;
         issue_load(scratch);
       }
-      reset_view(&ctl->st, tid, RNT);
+      reset_view(cur, tid, RNT);
       __syncthreads();
-      if (tally && tid == 0) ctl->st.hist_valid = 1;  // reset_view cleared it: the tallied bytes ARE the new source
-      res_advance<C>(ctl, pl, H, W, tid);
+      if (tally && tid == 0) cur->hist_valid = 1;  // reset_view cleared it: the tallied bytes ARE the new source
+      res_advance<C>(ctl, cur, pl, H, W, tid);
     }
     // every thread is done with the resident source; bulk stores out of it have read their bytes;
     // in-place writes (generic proxy) are ordered before the TMA refills the buffer
